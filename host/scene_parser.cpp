@@ -1,0 +1,259 @@
+// host/scene_parser.cpp -- see scene_parser.h.  Grammar of the reference's parseScene (src/scene.cpp:12-227).
+#include "scene_parser.h"
+
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace skr_host
+{
+namespace
+{
+struct MaterialState // reference: src/material.h:9-26 defaults
+{
+	float ambient[3]	  = {0, 0, 0};
+	float diffuse[3]	  = {0, 0, 0};
+	float specular[3]	  = {0, 0, 0};
+	float transmissive[3] = {0, 0, 0};
+	float power			  = 1.0f;
+	float ior			  = 1.0f;
+};
+
+// Reads up to `max` floats after the command word; returns how many were converted (sscanf %f semantics:
+// stops at the first token that is not a number).
+int read_floats(const char *p, float *out, int max)
+{
+	int n = 0;
+	while(n < max)
+	{
+		char *end = nullptr;
+		errno	  = 0;
+		float v	  = strtof(p, &end);
+		if(end == p)
+		{
+			break;
+		}
+		out[n++] = v;
+		p		 = end;
+	}
+	return n;
+}
+} // namespace
+
+skr_scene_desc HostScene::desc() const
+{
+	skr_scene_desc d;
+	memset(&d, 0, sizeof d);
+	d.nspheres = nspheres();
+	d.spheres  = spheres.data();
+	d.ntris	   = ntris();
+	d.tris	   = tris.data();
+	d.nplights = nplights();
+	d.plights  = plights.data();
+	d.ndlights = ndlights();
+	d.dlights  = dlights.data();
+	d.nfogs	   = nfogs();
+	d.fogs	   = fogs.data();
+	memcpy(d.camera, camera, sizeof camera);
+	memcpy(d.ambient, ambient, sizeof ambient);
+	memcpy(d.background, background, sizeof background);
+	return d;
+}
+
+bool parse_scn(const std::string &path, HostScene &scene, std::string &error, const ParseOptions &opt)
+{
+	FILE *fp = fopen(path.c_str(), "r");
+	if(!fp)
+	{
+		error = "Can't open file '" + path + "'"; // src/scene.cpp:22-26 prints this and exit(0)s
+		return false;
+	}
+	scene = HostScene();
+	MaterialState mat;
+	char line[1024]; // the reference assumes no line is longer than 1024 characters (src/scene.cpp:19)
+	int lineno = 0;
+	bool ok	   = true;
+	while(fgets(line, sizeof line, fp))
+	{
+		lineno++;
+		if(line[0] == '#')
+		{
+			continue; // src/scene.cpp:31-35: only a '#' in column 0 starts a comment
+		}
+		char command[100];
+		int consumed = 0;
+		if(sscanf(line, "%99s%n", command, &consumed) < 1)
+		{
+			continue; // blank line
+		}
+		const char *args = line + consumed;
+		float f[16];
+		for(float &v : f)
+		{
+			v = 0.0f;
+		}
+		if(strcmp(command, "sphere") == 0)
+		{
+			read_floats(args, f, 4); // x y z r
+			const float rec[18] = {f[0], f[1], f[2], f[3], mat.ambient[0], mat.ambient[1], mat.ambient[2], mat.diffuse[0], mat.diffuse[1],
+								   mat.diffuse[2], mat.specular[0], mat.specular[1], mat.specular[2], mat.transmissive[0], mat.transmissive[1],
+								   mat.transmissive[2], mat.power, mat.ior};
+			scene.spheres.insert(scene.spheres.end(), rec, rec + 18);
+			if(opt.verbose)
+			{
+				printf("Sphere as position (%f, %f, %f) with radius %f\n", f[0], f[1], f[2], f[3]);
+			}
+		}
+		else if(strcmp(command, "vertex") == 0)
+		{
+			read_floats(args, f, 3);
+			scene.vertices.insert(scene.vertices.end(), f, f + 3);
+		}
+		else if(strcmp(command, "triangle") == 0)
+		{
+			// indices are read as floats and used as vector subscripts (src/scene.cpp:66-75)
+			read_floats(args, f, 3);
+			const size_t nv = scene.vertices.size() / 3;
+			for(int k = 0; k < 3; k++)
+			{
+				if(!(f[k] >= 0.0f) || (size_t) f[k] >= nv)
+				{
+					char buf[256];
+					snprintf(buf, sizeof buf, "%s:%d: triangle references vertex %g but only %zu vertices are defined", path.c_str(), lineno, f[k], nv);
+					error = buf;
+					ok	  = false;
+					break;
+				}
+			}
+			if(!ok)
+			{
+				break;
+			}
+			for(int k = 0; k < 3; k++)
+			{
+				const float *v = scene.vertices.data() + 3 * (size_t) f[k];
+				scene.tris.insert(scene.tris.end(), v, v + 3);
+			}
+		}
+		else if(strcmp(command, "camera") == 0)
+		{
+			read_floats(args, f, 10); // pos3 dir3 up3 halfHeightAngle (the angle is never used)
+			float *c = scene.camera;
+			memcpy(c, f, 9 * sizeof(float));
+			// Camera ctor: right = cross(direction * -1.0f, up); nothing is normalised (src/camera.h:24-31,
+			// the glm::normalize results at src/scene.cpp:91-93 are discarded)
+			const float nx = f[3] * -1.0f, ny = f[4] * -1.0f, nz = f[5] * -1.0f;
+			c[9]  = ny * f[8] - f[7] * nz;
+			c[10] = nz * f[6] - f[8] * nx;
+			c[11] = nx * f[7] - f[6] * ny;
+			if(opt.verbose)
+			{
+				printf("Camera with position (%f, %f, %f) with viewing direction (%f, %f, %f), up (%f, %f, %f), and halfHeightAngle %f\n", f[0], f[1],
+					   f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9]);
+			}
+		}
+		else if(strcmp(command, "film_resolution") == 0)
+		{
+			int w = scene.film_width, h = scene.film_height;
+			sscanf(args, "%d %d", &w, &h);
+			scene.film_width  = w;
+			scene.film_height = h;
+		}
+		else if(strcmp(command, "background") == 0)
+		{
+			read_floats(args, f, 3);
+			memcpy(scene.background, f, 3 * sizeof(float));
+		}
+		else if(strcmp(command, "material") == 0)
+		{
+			// ambient3 diffuse3 specular3 phongCos transmissive3 ior (src/scene.cpp:119-137)
+			read_floats(args, f, 14);
+			memcpy(mat.ambient, f, 3 * sizeof(float));
+			memcpy(mat.diffuse, f + 3, 3 * sizeof(float));
+			memcpy(mat.specular, f + 6, 3 * sizeof(float));
+			mat.power = f[9];
+			memcpy(mat.transmissive, f + 10, 3 * sizeof(float));
+			mat.ior = f[13];
+		}
+		else if(strcmp(command, "directional_light") == 0)
+		{
+			read_floats(args, f, 6); // colour3 direction3; colour clamped to <= 1 (src/scene.cpp:144-155)
+			for(int k = 0; k < 3; k++)
+			{
+				if(f[k] > 1)
+				{
+					f[k] = 1;
+				}
+			}
+			if(opt.keep_directional)
+			{
+				const float rec[6] = {f[3], f[4], f[5], f[0], f[1], f[2]};
+				scene.dlights.insert(scene.dlights.end(), rec, rec + 6);
+			}
+		}
+		else if(strcmp(command, "point_light") == 0)
+		{
+			read_floats(args, f, 6); // colour3 position3
+			const float rec[6] = {f[3], f[4], f[5], f[0], f[1], f[2]};
+			scene.plights.insert(scene.plights.end(), rec, rec + 6);
+		}
+		else if(strcmp(command, "ambient_light") == 0)
+		{
+			read_floats(args, f, 3); // accumulates (src/scene.cpp:188-190)
+			scene.ambient[0] += f[0];
+			scene.ambient[1] += f[1];
+			scene.ambient[2] += f[2];
+		}
+		else if(strcmp(command, "max_depth") == 0)
+		{
+			read_floats(args, f, 1);
+			scene.max_depth = (int) f[0];
+		}
+		else if(strcmp(command, "output_image") == 0)
+		{
+			char out_file[1024] = {0};
+			sscanf(args, "%1023s", out_file);
+			scene.output_image = out_file;
+		}
+		else if(strcmp(command, "spherical_fog") == 0)
+		{
+			if(opt.fog)
+			{
+				read_floats(args, f, 9); // x y z radius r g b scattering absorption
+				const float rec[9] = {f[7], f[8], f[4], f[5], f[6], f[3], f[0], f[1], f[2]};
+				scene.fogs.insert(scene.fogs.end(), rec, rec + 9);
+			}
+		}
+		else
+		{
+			scene.unknown_commands++;
+			if(opt.verbose)
+			{
+				printf("WARNING. Do not know command: %s\n", command);
+			}
+		}
+	}
+	fclose(fp);
+	return ok;
+}
+
+bool write_ppm(const std::string &path, int width, int height, const unsigned char *rgb8, std::string &error)
+{
+	FILE *fp = fopen(path.c_str(), "wb");
+	if(!fp)
+	{
+		error = "cannot open '" + path + "' for writing";
+		return false;
+	}
+	fprintf(fp, "P6\n%d %d\n255\n", width, height);
+	const size_t n	= (size_t) width * height * 3;
+	const bool good = fwrite(rgb8, 1, n, fp) == n;
+	fclose(fp);
+	if(!good)
+	{
+		error = "short write to '" + path + "'";
+	}
+	return good;
+}
+} // namespace skr_host

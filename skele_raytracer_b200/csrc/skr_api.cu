@@ -1,0 +1,1009 @@
+// skr_api.cu -- implementation of the C ABI in include/skr.h (libskr.so).
+//
+// Replaces the body of the reference's frame function generate_rays_parallel (reference src/main.cpp:19-104).
+// Host side of the renderer: scene flattening/upload (+ device LBVH build), wavefront scheduling (queue levels,
+// chunking so that a full fan-out always fits the next level), output copies, timing.  No CPU rendering path exists
+// in this file or anywhere in the library: if CUDA is unavailable every entry point fails.
+#include "../../include/skr.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "skr_bvh_build.cuh"
+#include "skr_kernels.cuh"
+
+namespace
+{
+thread_local std::string g_init_error;
+
+enum
+{
+	CAT_PRIMARY = 0,
+	CAT_BOUNCE	= 1,
+	CAT_RESOLVE = 2,
+	CAT_COUNT	= 3
+};
+
+struct Span
+{
+	cudaEvent_t a, b;
+	int cat;
+};
+
+constexpr size_t SMEM_BLOB_LIMIT = 64 * 1024;
+constexpr unsigned DEFAULT_QUEUE_CAP = 4u << 20;
+constexpr int DEFAULT_TILE = 32;
+} // namespace
+
+struct skr_ctx
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::string err;
+	int sm_count = 0;
+
+	// scene
+	bool have_scene = false;
+	SceneView sv{};
+	float4 *d_blob = nullptr;
+	float *d_tris_raw = nullptr;
+	float4 *d_tri_v = nullptr;
+	float4 *d_bvh = nullptr;
+	size_t smem_bytes = 0;
+
+	// frame buffers
+	uint8_t *d_rgb8 = nullptr;
+	size_t rgb8_bytes = 0;
+	float *d_rgb32 = nullptr;
+	size_t rgb32_bytes = 0;
+	long long *d_accum = nullptr;
+	size_t accum_bytes = 0;
+
+	// wavefront queues
+	std::vector<Queue> queues;
+	unsigned queue_cap = 0;
+	unsigned *d_counts = nullptr; // one per level
+	int n_levels_alloc = 0;
+	unsigned *h_count = nullptr; // pinned
+
+	unsigned long long *d_counters = nullptr; // 8
+	int *d_err = nullptr;
+	int *h_err = nullptr; // pinned
+
+	// timing
+	std::vector<Span> spans;
+	size_t spans_used = 0;
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
+
+	unsigned launches = 0, chunks = 0;
+	unsigned long long queue_entries = 0;
+};
+
+namespace
+{
+int fail(skr_ctx *ctx, int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if(ctx)
+	{
+		ctx->err = buf;
+	}
+	else
+	{
+		g_init_error = buf;
+	}
+	return code;
+}
+
+#define CK(call)                                                                                                    \
+	do                                                                                                               \
+	{                                                                                                                \
+		cudaError_t e_ = (call);                                                                                     \
+		if(e_ != cudaSuccess)                                                                                        \
+		{                                                                                                            \
+			return fail(ctx, SKR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));        \
+		}                                                                                                            \
+	} while(0)
+
+template <typename T>
+cudaError_t ensure(T *&ptr, size_t &have, size_t want)
+{
+	if(have >= want && ptr)
+	{
+		return cudaSuccess;
+	}
+	if(ptr)
+	{
+		cudaFree(ptr);
+		ptr = nullptr;
+		have = 0;
+	}
+	cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ptr), want);
+	if(e == cudaSuccess)
+	{
+		have = want;
+	}
+	return e;
+}
+
+struct V3
+{
+	float x, y, z;
+};
+inline V3 ld3(const float *p) { return V3{p[0], p[1], p[2]}; }
+inline float hdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+void span_begin(skr_ctx *ctx, int cat)
+{
+	if(ctx->spans_used == ctx->spans.size())
+	{
+		Span s;
+		cudaEventCreate(&s.a);
+		cudaEventCreate(&s.b);
+		s.cat = cat;
+		ctx->spans.push_back(s);
+	}
+	Span &s = ctx->spans[ctx->spans_used];
+	s.cat	= cat;
+	cudaEventRecord(s.a, ctx->stream);
+}
+void span_end(skr_ctx *ctx)
+{
+	cudaEventRecord(ctx->spans[ctx->spans_used].b, ctx->stream);
+	ctx->spans_used++;
+}
+
+int set_smem_attr(skr_ctx *ctx)
+{
+	const int bytes = (int) ctx->smem_bytes;
+	if(bytes > 48 * 1024)
+	{
+		CK(cudaFuncSetAttribute(primary_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(primary_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(primary_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(primary_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(shade_expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(shade_expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	}
+	return SKR_OK;
+}
+
+int build_bvh(skr_ctx *ctx, int T)
+{
+	using namespace bvhb;
+	cudaStream_t st = ctx->stream;
+	const int B		= 256;
+	const int gridT = (T + B - 1) / B;
+	if(ctx->d_tri_v)
+	{
+		cudaFree(ctx->d_tri_v);
+		ctx->d_tri_v = nullptr;
+	}
+	if(ctx->d_bvh)
+	{
+		cudaFree(ctx->d_bvh);
+		ctx->d_bvh = nullptr;
+	}
+	CK(cudaMalloc(&ctx->d_tri_v, sizeof(float4) * 3 * (size_t) T));
+	const char *nobvh = getenv("SKR_NO_BVH");
+	if((nobvh && nobvh[0] == '1') || T == 1)
+	{
+		iota_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, ctx->d_tri_v);
+		CK(cudaGetLastError());
+		ctx->sv.bvh				 = nullptr;
+		ctx->sv.bvh_root_is_leaf = 0;
+		return SKR_OK;
+	}
+	float4 *box_lo = nullptr, *box_hi = nullptr, *node_lo = nullptr, *node_hi = nullptr;
+	float *scene_box = nullptr;
+	unsigned long long *keys[2] = {nullptr, nullptr};
+	unsigned *vals[2] = {nullptr, nullptr};
+	unsigned *hist = nullptr;
+	int2 *children = nullptr;
+	int *parent = nullptr, *flags = nullptr;
+	const int nwarps  = (T + SORT_ITEMS_PER_WARP - 1) / SORT_ITEMS_PER_WARP;
+	const int sblocks = (nwarps + SORT_WARPS - 1) / SORT_WARPS;
+	int rc = SKR_OK;
+	auto cleanup = [&]() {
+		cudaFree(box_lo), cudaFree(box_hi), cudaFree(node_lo), cudaFree(node_hi), cudaFree(scene_box);
+		cudaFree(keys[0]), cudaFree(keys[1]), cudaFree(vals[0]), cudaFree(vals[1]), cudaFree(hist);
+		cudaFree(children), cudaFree(parent), cudaFree(flags);
+	};
+#define CKB(call)                                                                                                   \
+	do                                                                                                               \
+	{                                                                                                                \
+		cudaError_t e_ = (call);                                                                                     \
+		if(e_ != cudaSuccess)                                                                                        \
+		{                                                                                                            \
+			rc = fail(ctx, SKR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));          \
+			cleanup();                                                                                               \
+			return rc;                                                                                               \
+		}                                                                                                            \
+	} while(0)
+	CKB(cudaMalloc(&box_lo, sizeof(float4) * T));
+	CKB(cudaMalloc(&box_hi, sizeof(float4) * T));
+	CKB(cudaMalloc(&node_lo, sizeof(float4) * T));
+	CKB(cudaMalloc(&node_hi, sizeof(float4) * T));
+	CKB(cudaMalloc(&scene_box, sizeof(float) * 6));
+	CKB(cudaMalloc(&keys[0], sizeof(unsigned long long) * T));
+	CKB(cudaMalloc(&keys[1], sizeof(unsigned long long) * T));
+	CKB(cudaMalloc(&vals[0], sizeof(unsigned) * T));
+	CKB(cudaMalloc(&vals[1], sizeof(unsigned) * T));
+	CKB(cudaMalloc(&hist, sizeof(unsigned) * 256 * (size_t) nwarps));
+	CKB(cudaMalloc(&children, sizeof(int2) * T));
+	CKB(cudaMalloc(&parent, sizeof(int) * 2 * (size_t) T));
+	CKB(cudaMalloc(&flags, sizeof(int) * T));
+	CKB(cudaMalloc(&ctx->d_bvh, sizeof(float4) * 4 * (size_t) (T - 1)));
+
+	const float init_box[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+	CKB(cudaMemcpyAsync(scene_box, init_box, sizeof init_box, cudaMemcpyHostToDevice, st));
+	tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box);
+	morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0]);
+	int cur = 0;
+	for(int pass = 0; pass < 8; pass++)
+	{
+		const int shift = 8 * pass;
+		sort_hist_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], T, shift, hist, nwarps);
+		sort_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * nwarps);
+		sort_scatter_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], T, shift, hist, nwarps, keys[cur ^ 1], vals[cur ^ 1]);
+		cur ^= 1;
+	}
+	CKB(cudaMemsetAsync(flags, 0, sizeof(int) * T, st));
+	karras_kernel<<<gridT, B, 0, st>>>(keys[cur], T, children, parent);
+	refit_kernel<<<gridT, B, 0, st>>>(T, vals[cur], box_lo, box_hi, children, parent, node_lo, node_hi, flags, ctx->d_bvh);
+	gather_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, vals[cur], T, ctx->d_tri_v);
+	CKB(cudaGetLastError());
+	CKB(cudaStreamSynchronize(st));
+	cleanup();
+#undef CKB
+	ctx->sv.bvh				 = ctx->d_bvh;
+	ctx->sv.bvh_root_is_leaf = 0;
+	return SKR_OK;
+}
+
+struct Plan
+{
+	FrameParams fp;
+	long long npix_local; // local pixels incl. padding (tiles_local * tile^2)
+	long long tiles_local;
+	int levels;
+};
+
+int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
+{
+	if(!o || o->width <= 0 || o->height <= 0)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_options: width/height must be positive");
+	}
+	if(o->grid_size < 0 || o->grid_size > 255)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_options: grid_size (--jsample) must be in [0,255]");
+	}
+	if(o->monte_carlo && o->num_path_traces < 0)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_options: num_path_traces (--gillum) must be >= 0");
+	}
+	if((long long) o->width * o->height > 0x7fffffffLL)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_options: frame too large");
+	}
+	const int world = o->world > 1 ? o->world : 1;
+	const int rank	= o->world > 1 ? o->rank : 0;
+	if(rank < 0 || rank >= world)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_options: rank %d outside world %d", rank, world);
+	}
+	const int tile = o->tile > 0 ? o->tile : DEFAULT_TILE;
+	if(tile % 8 != 0 || tile > 1024)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_options: tile must be a multiple of 8 (got %d)", tile);
+	}
+	FrameParams &fp = pl.fp;
+	memset(&fp, 0, sizeof fp);
+	fp.width		= o->width;
+	fp.height		= o->height;
+	fp.tile			= tile;
+	fp.tiles_x		= (o->width + tile - 1) / tile;
+	const int tiles_y = (o->height + tile - 1) / tile;
+	fp.tiles_total	= fp.tiles_x * tiles_y;
+	fp.rank			= rank;
+	fp.world		= world;
+	fp.wpr			= tile / 8;
+	fp.grid			= o->grid_size;
+	fp.spp			= o->grid_size > 0 ? o->grid_size * o->grid_size : 1;
+	fp.max_depth	= o->max_depth;
+	fp.gi			= o->monte_carlo ? 1 : 0;
+	fp.n_gi			= o->monte_carlo ? o->num_path_traces : 0;
+	fp.shadows		= o->use_shadows ? 1 : 0;
+	// src/main.cpp:40-43
+	fp.inv_w  = 1 / float(o->width);
+	fp.inv_h  = 1 / float(o->height);
+	fp.aspect = o->width / float(o->height);
+	fp.angle  = (float) tan(M_PI * 0.5 * o->fov / 180.);
+	fp.key	  = make_uint2((uint32_t) o->seed, (uint32_t) (o->seed >> 32));
+	fp.node_base = (uint32_t) fp.n_gi + 1u;
+	fp.slot_gi	 = 1u + 2u * (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
+	pl.tiles_local = (fp.tiles_total + world - 1) / world;
+	pl.npix_local  = pl.tiles_local * tile * tile;
+	pl.levels	   = (fp.gi && fp.max_depth > 0) ? fp.max_depth : 0;
+	if(o->fresnel)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_options: fresnel mode is not implemented yet");
+	}
+	return SKR_OK;
+}
+
+int ensure_queues(skr_ctx *ctx, int levels, unsigned cap)
+{
+	if(levels <= ctx->n_levels_alloc && cap == ctx->queue_cap)
+	{
+		return SKR_OK;
+	}
+	for(Queue &q : ctx->queues)
+	{
+		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c);
+	}
+	ctx->queues.clear();
+	if(ctx->d_counts)
+	{
+		cudaFree(ctx->d_counts);
+		ctx->d_counts = nullptr;
+	}
+	ctx->n_levels_alloc = 0;
+	CK(cudaMalloc(&ctx->d_counts, sizeof(unsigned) * (size_t) (levels + 1)));
+	for(int l = 0; l < levels; l++)
+	{
+		Queue q{};
+		CK(cudaMalloc(&q.a, sizeof(float4) * (size_t) cap));
+		CK(cudaMalloc(&q.b, sizeof(float4) * (size_t) cap));
+		CK(cudaMalloc(&q.c, sizeof(uint32_t) * (size_t) cap));
+		q.count = ctx->d_counts + l;
+		q.cap	= cap;
+		ctx->queues.push_back(q);
+	}
+	ctx->n_levels_alloc = levels;
+	ctx->queue_cap		= cap;
+	return SKR_OK;
+}
+
+int read_count(skr_ctx *ctx, int level, unsigned &out)
+{
+	CK(cudaMemcpyAsync(ctx->h_count, ctx->d_counts + level, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	out = *ctx->h_count;
+	return SKR_OK;
+}
+
+template <bool STATS>
+int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int depth)
+{
+	if(count == 0)
+	{
+		return SKR_OK;
+	}
+	const FrameParams &fp = pl.fp;
+	const bool expand	  = depth - 1 >= 1 && fp.n_gi > 0;
+	const Queue &in		  = ctx->queues[level];
+	ctx->queue_entries += count;
+	if(!expand)
+	{
+		span_begin(ctx, CAT_BOUNCE);
+		shade_expand_kernel<STATS><<<(count + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, 0u, count, in, 0);
+		span_end(ctx);
+		ctx->launches++;
+		CK(cudaGetLastError());
+		return SKR_OK;
+	}
+	const Queue &out	 = ctx->queues[level + 1];
+	const unsigned chunk = out.cap / (unsigned) fp.n_gi;
+	for(unsigned s = 0; s < count; s += chunk)
+	{
+		const unsigned m = count - s < chunk ? count - s : chunk;
+		CK(cudaMemsetAsync(out.count, 0, sizeof(unsigned), ctx->stream));
+		span_begin(ctx, CAT_BOUNCE);
+		shade_expand_kernel<STATS><<<(m + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, s, m, out, 1);
+		span_end(ctx);
+		ctx->launches++;
+		ctx->chunks++;
+		CK(cudaGetLastError());
+		unsigned next = 0;
+		int rc		  = read_count(ctx, level + 1, next);
+		if(rc)
+		{
+			return rc;
+		}
+		rc = process_level<STATS>(ctx, pl, level + 1, next, depth - 1);
+		if(rc)
+		{
+			return rc;
+		}
+	}
+	return SKR_OK;
+}
+
+template <bool STATS>
+int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
+{
+	FrameParams &fp = pl.fp;
+	cudaStream_t st = ctx->stream;
+	const size_t smem = ctx->smem_bytes;
+	if(fp.gi)
+	{
+		unsigned cap = o->queue_capacity > 0 ? (unsigned) o->queue_capacity : DEFAULT_QUEUE_CAP;
+		const unsigned need = (unsigned) (fp.n_gi > fp.spp ? fp.n_gi : fp.spp);
+		if(cap < need * SKR_BLOCK)
+		{
+			cap = need * SKR_BLOCK;
+		}
+		int rc = ensure_queues(ctx, pl.levels, cap);
+		if(rc)
+		{
+			return rc;
+		}
+		CK(ensure(ctx->d_accum, ctx->accum_bytes, sizeof(long long) * 3 * (size_t) pl.npix_local));
+		fp.accum = ctx->d_accum;
+	}
+	if(!fp.gi || pl.levels == 0)
+	{
+		span_begin(ctx, CAT_PRIMARY);
+		const unsigned blocks = (unsigned) ((pl.npix_local + SKR_BLOCK - 1) / SKR_BLOCK);
+		Queue none{};
+		primary_kernel<false, STATS><<<blocks, SKR_BLOCK, smem, st>>>(ctx->sv, fp, none, 0, pl.npix_local);
+		span_end(ctx);
+		ctx->launches++;
+		CK(cudaGetLastError());
+		return SKR_OK;
+	}
+	const Queue &q0	  = ctx->queues[0];
+	long long batch	  = (long long) (q0.cap / (unsigned) fp.spp) / SKR_BLOCK * SKR_BLOCK;
+	for(long long lp0 = 0; lp0 < pl.npix_local; lp0 += batch)
+	{
+		const long long n = pl.npix_local - lp0 < batch ? pl.npix_local - lp0 : batch;
+		CK(cudaMemsetAsync(q0.count, 0, sizeof(unsigned), st));
+		span_begin(ctx, CAT_PRIMARY);
+		primary_kernel<true, STATS><<<(unsigned) ((n + SKR_BLOCK - 1) / SKR_BLOCK), SKR_BLOCK, smem, st>>>(ctx->sv, fp, q0, lp0, n);
+		span_end(ctx);
+		ctx->launches++;
+		ctx->chunks++;
+		CK(cudaGetLastError());
+		unsigned c0 = 0;
+		int rc		= read_count(ctx, 0, c0);
+		if(rc)
+		{
+			return rc;
+		}
+		rc = process_level<STATS>(ctx, pl, 0, c0, fp.max_depth);
+		if(rc)
+		{
+			return rc;
+		}
+	}
+	span_begin(ctx, CAT_RESOLVE);
+	resolve_kernel<<<(unsigned) ((pl.npix_local + SKR_BLOCK - 1) / SKR_BLOCK), SKR_BLOCK, 0, st>>>(fp, 0, pl.npix_local);
+	span_end(ctx);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	return SKR_OK;
+}
+
+// common driver: outputs already set in pl.fp
+int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats)
+{
+	cudaStream_t st = ctx->stream;
+	ctx->spans_used = 0;
+	ctx->launches = ctx->chunks = 0;
+	ctx->queue_entries = 0;
+	const bool want_stats = o->collect_stats != 0;
+	pl.fp.counters = ctx->d_counters;
+	pl.fp.err	   = ctx->d_err;
+	CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, st));
+	CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
+	CK(cudaEventRecord(ctx->ev_begin, st));
+	int rc = want_stats ? render_frame<true>(ctx, o, pl) : render_frame<false>(ctx, o, pl);
+	if(rc)
+	{
+		return rc;
+	}
+	CK(cudaEventRecord(ctx->ev_end, st));
+	CK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+	unsigned long long hc[8] = {0};
+	if(want_stats)
+	{
+		CK(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+	}
+	CK(cudaStreamSynchronize(st));
+	if(*ctx->h_err)
+	{
+		return fail(ctx, SKR_ERR_CUDA, "internal: wavefront queue overflow (flag %d)", *ctx->h_err);
+	}
+	if(stats)
+	{
+		memset(stats, 0, sizeof *stats);
+		stats->closest_hit_rays = hc[0];
+		stats->shadow_rays		= hc[1];
+		stats->sphere_tests		= hc[2];
+		stats->sphere_tests_pos = hc[3];
+		stats->tri_tests		= hc[4];
+		stats->bvh_node_visits	= hc[5];
+		stats->sphere_hits		= hc[6];
+		stats->light_evals		= hc[7];
+		stats->queue_entries	= ctx->queue_entries;
+		stats->kernel_launches	= ctx->launches;
+		stats->queue_chunks		= ctx->chunks;
+		CK(cudaEventElapsedTime(&stats->ms_total, ctx->ev_begin, ctx->ev_end));
+		float cat[CAT_COUNT] = {0, 0, 0};
+		for(size_t i = 0; i < ctx->spans_used; i++)
+		{
+			float ms = 0;
+			CK(cudaEventElapsedTime(&ms, ctx->spans[i].a, ctx->spans[i].b));
+			cat[ctx->spans[i].cat] += ms;
+		}
+		stats->ms_primary = cat[CAT_PRIMARY];
+		stats->ms_bounce  = cat[CAT_BOUNCE];
+		stats->ms_resolve = cat[CAT_RESOLVE];
+	}
+	return SKR_OK;
+}
+
+#define REQUIRE_CTX()                                                     \
+	if(!ctx)                                                               \
+	{                                                                      \
+		return fail(nullptr, SKR_ERR_ARG, "null context");                 \
+	}                                                                      \
+	if(cudaSetDevice(ctx->device) != cudaSuccess)                          \
+	{                                                                      \
+		return fail(ctx, SKR_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device); \
+	}
+#define REQUIRE_SCENE()                                                                      \
+	if(!ctx->have_scene)                                                                      \
+	{                                                                                         \
+		return fail(ctx, SKR_ERR_NO_SCENE, "skr_scene_upload must be called before rendering"); \
+	}
+} // namespace
+
+extern "C" {
+
+int skr_abi_version(void)
+{
+	return SKR_ABI_VERSION;
+}
+
+const char *skr_last_error(const skr_ctx *ctx)
+{
+	return ctx ? ctx->err.c_str() : g_init_error.c_str();
+}
+
+int skr_init(int device, skr_ctx **out)
+{
+	skr_ctx *ctx = nullptr;
+	if(!out)
+	{
+		return fail(nullptr, SKR_ERR_ARG, "skr_init: out is null");
+	}
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if(e != cudaSuccess || ndev == 0)
+	{
+		return fail(nullptr, SKR_ERR_NO_DEVICE, "skr_init: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+	}
+	if(device < 0)
+	{
+		if(cudaGetDevice(&device) != cudaSuccess)
+		{
+			device = 0;
+		}
+	}
+	if(device >= ndev)
+	{
+		return fail(nullptr, SKR_ERR_NO_DEVICE, "skr_init: device %d out of range (%d devices)", device, ndev);
+	}
+	e = cudaSetDevice(device);
+	if(e != cudaSuccess)
+	{
+		return fail(nullptr, SKR_ERR_CUDA, "skr_init: cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+	}
+	skr_ctx *c = new skr_ctx();
+	c->device  = device;
+	ctx		   = c;
+	auto bail  = [&](cudaError_t err, const char *what) {
+		 fail(nullptr, SKR_ERR_CUDA, "skr_init: %s: %s", what, cudaGetErrorString(err));
+		 skr_destroy(c);
+		 return (int) SKR_ERR_CUDA;
+	};
+	if((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess)
+	{
+		return bail(e, "cudaStreamCreate");
+	}
+	cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+	if((e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8)) != cudaSuccess)
+	{
+		return bail(e, "cudaMalloc");
+	}
+	if((e = cudaMalloc(&c->d_err, sizeof(int))) != cudaSuccess)
+	{
+		return bail(e, "cudaMalloc");
+	}
+	if((e = cudaHostAlloc(&c->h_count, sizeof(unsigned), cudaHostAllocDefault)) != cudaSuccess)
+	{
+		return bail(e, "cudaHostAlloc");
+	}
+	if((e = cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocDefault)) != cudaSuccess)
+	{
+		return bail(e, "cudaHostAlloc");
+	}
+	cudaEventCreate(&c->ev_begin);
+	cudaEventCreate(&c->ev_end);
+	cudaEventCreate(&c->ev_x0);
+	cudaEventCreate(&c->ev_x1);
+	*out = c;
+	return SKR_OK;
+}
+
+void skr_destroy(skr_ctx *ctx)
+{
+	if(!ctx)
+	{
+		return;
+	}
+	cudaSetDevice(ctx->device);
+	if(ctx->stream)
+	{
+		cudaStreamSynchronize(ctx->stream);
+	}
+	cudaFree(ctx->d_blob), cudaFree(ctx->d_tris_raw), cudaFree(ctx->d_tri_v), cudaFree(ctx->d_bvh);
+	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
+	for(Queue &q : ctx->queues)
+	{
+		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c);
+	}
+	cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_err);
+	if(ctx->h_count)
+	{
+		cudaFreeHost(ctx->h_count);
+	}
+	if(ctx->h_err)
+	{
+		cudaFreeHost(ctx->h_err);
+	}
+	for(Span &s : ctx->spans)
+	{
+		cudaEventDestroy(s.a), cudaEventDestroy(s.b);
+	}
+	if(ctx->ev_begin)
+	{
+		cudaEventDestroy(ctx->ev_begin), cudaEventDestroy(ctx->ev_end), cudaEventDestroy(ctx->ev_x0), cudaEventDestroy(ctx->ev_x1);
+	}
+	if(ctx->stream)
+	{
+		cudaStreamDestroy(ctx->stream);
+	}
+	delete ctx;
+}
+
+void *skr_stream(skr_ctx *ctx)
+{
+	return ctx ? (void *) ctx->stream : nullptr;
+}
+
+int skr_sync(skr_ctx *ctx)
+{
+	REQUIRE_CTX();
+	CK(cudaStreamSynchronize(ctx->stream));
+	return SKR_OK;
+}
+
+int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
+{
+	REQUIRE_CTX();
+	if(!sc)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_scene_upload: scene is null");
+	}
+	if(sc->nspheres < 0 || sc->ntris < 0 || sc->nplights < 0 || sc->ndlights < 0 || sc->nfogs < 0)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_scene_upload: negative count");
+	}
+	if(sc->nspheres > 65535)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_scene_upload: at most 65535 spheres (got %d)", sc->nspheres);
+	}
+	if((sc->nspheres && !sc->spheres) || (sc->ntris && !sc->tris) || (sc->nplights && !sc->plights) || (sc->ndlights && !sc->dlights) ||
+	   (sc->nfogs && !sc->fogs))
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_scene_upload: null array with nonzero count");
+	}
+	ctx->have_scene = false;
+	const int S = sc->nspheres, T = sc->ntris, L = sc->nplights, D = sc->ndlights, F = sc->nfogs;
+	SceneView &sv = ctx->sv;
+	memset(&sv, 0, sizeof sv);
+	sv.S = S, sv.T = T, sv.L = L, sv.D = D, sv.F = F;
+	int off		  = 0;
+	sv.off_geom	  = off, off += S;
+	sv.off_prim	  = off, off += S;
+	sv.off_amb	  = off, off += S;
+	sv.off_diff	  = off, off += S;
+	sv.off_spec	  = off, off += S;
+	sv.off_plpos  = off, off += L;
+	sv.off_plcol  = off, off += L;
+	sv.off_dldir  = off, off += D;
+	sv.off_dlcol  = off, off += D;
+	sv.off_foga	  = off, off += F;
+	sv.off_fogalb = off, off += F;
+	sv.off_fogp	  = off, off += (S * L * F + 3) / 4;
+	sv.blob_f4	  = off > 0 ? off : 1;
+	std::vector<float4> blob((size_t) sv.blob_f4, make_float4(0, 0, 0, 0));
+	const V3 cam = ld3(sc->camera);
+	for(int s = 0; s < S; s++)
+	{
+		const float *p = sc->spheres + 18 * (size_t) s;
+		const V3 c	   = ld3(p);
+		const float r  = p[3];
+		// e = camera - centre, c-term = e.e - r*r in the reference's operand order (src/utils.h:115-118)
+		const V3 e			   = V3{cam.x - c.x, cam.y - c.y, cam.z - c.z};
+		const float ee		   = hdot(e, e);
+		const float cterm	   = ee - r * r;
+		blob[sv.off_geom + s]  = make_float4(c.x, c.y, c.z, r);
+		blob[sv.off_prim + s]  = make_float4(2 * e.x, 2 * e.y, 2 * e.z, cterm);
+		blob[sv.off_amb + s]   = make_float4(sc->ambient[0] * p[4], sc->ambient[1] * p[5], sc->ambient[2] * p[6], p[16]);
+		blob[sv.off_diff + s]  = make_float4(p[7], p[8], p[9], p[17]);
+		const bool has_spec	   = p[10] != 0.0f || p[11] != 0.0f || p[12] != 0.0f;
+		blob[sv.off_spec + s]  = make_float4(p[10], p[11], p[12], has_spec ? 1.0f : 0.0f);
+	}
+	for(int i = 0; i < L; i++)
+	{
+		const float *p		   = sc->plights + 6 * (size_t) i;
+		blob[sv.off_plpos + i] = make_float4(p[0], p[1], p[2], 0);
+		blob[sv.off_plcol + i] = make_float4(p[3], p[4], p[5], 0);
+	}
+	for(int i = 0; i < D; i++)
+	{
+		const float *p	= sc->dlights + 6 * (size_t) i;
+		const V3 d		= ld3(p);
+		const float inv = 1.0f / sqrtf(d.x * d.x + d.y * d.y + d.z * d.z); // glm::normalize
+		blob[sv.off_dldir + i] = make_float4(d.x * inv, d.y * inv, d.z * inv, 0);
+		blob[sv.off_dlcol + i] = make_float4(p[3], p[4], p[5], 0);
+	}
+	float *fogp = reinterpret_cast<float *>(blob.data() + sv.off_fogp);
+	for(int j = 0; j < F; j++)
+	{
+		const float *f			= sc->fogs + 9 * (size_t) j;
+		blob[sv.off_foga + j]	= make_float4(f[0], f[1], f[5], 0);
+		blob[sv.off_fogalb + j] = make_float4(f[2], f[3], f[4], 0);
+	}
+	for(int s = 0; s < S; s++)
+	{
+		const V3 c = ld3(sc->spheres + 18 * (size_t) s);
+		for(int i = 0; i < L; i++)
+		{
+			const V3 lp = ld3(sc->plights + 6 * (size_t) i);
+			const V3 dv = V3{c.x - lp.x, c.y - lp.y, c.z - lp.z};
+			for(int j = 0; j < F; j++)
+			{
+				const float *f = sc->fogs + 9 * (size_t) j;
+				// src/blinn_phong.h:22-29: distance clamp and probability of no interaction (exp in double)
+				float distance = sqrtf(hdot(dv, dv));
+				if(distance > 2 * f[5])
+				{
+					distance = 2 * f[5];
+				}
+				fogp[((size_t) s * L + i) * F + j] = (float) exp((double) (-1.0f * distance * (f[1] + f[0])));
+			}
+		}
+	}
+	sv.cam_pos	  = make_float3(sc->camera[0], sc->camera[1], sc->camera[2]);
+	sv.cam_dir	  = make_float3(sc->camera[3], sc->camera[4], sc->camera[5]);
+	sv.cam_up	  = make_float3(sc->camera[6], sc->camera[7], sc->camera[8]);
+	sv.cam_right  = make_float3(sc->camera[9], sc->camera[10], sc->camera[11]);
+	sv.background = make_float3(sc->background[0], sc->background[1], sc->background[2]);
+
+	if(ctx->d_blob)
+	{
+		cudaFree(ctx->d_blob);
+		ctx->d_blob = nullptr;
+	}
+	CK(cudaMalloc(&ctx->d_blob, sizeof(float4) * blob.size()));
+	CK(cudaMemcpyAsync(ctx->d_blob, blob.data(), sizeof(float4) * blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+	sv.blob			= ctx->d_blob;
+	const size_t bb = sizeof(float4) * blob.size();
+	sv.blob_in_smem = bb <= SMEM_BLOB_LIMIT ? 1 : 0;
+	ctx->smem_bytes = sv.blob_in_smem ? bb : 0;
+	int rc			= set_smem_attr(ctx);
+	if(rc)
+	{
+		return rc;
+	}
+
+	if(ctx->d_tris_raw)
+	{
+		cudaFree(ctx->d_tris_raw);
+		ctx->d_tris_raw = nullptr;
+	}
+	sv.tri_v = nullptr;
+	sv.bvh	 = nullptr;
+	if(T > 0)
+	{
+		CK(cudaMalloc(&ctx->d_tris_raw, sizeof(float) * 9 * (size_t) T));
+		CK(cudaMemcpyAsync(ctx->d_tris_raw, sc->tris, sizeof(float) * 9 * (size_t) T, cudaMemcpyHostToDevice, ctx->stream));
+		rc = build_bvh(ctx, T);
+		if(rc)
+		{
+			return rc;
+		}
+		sv.tri_v = ctx->d_tri_v;
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->have_scene = true;
+	return SKR_OK;
+}
+
+int skr_render_device(skr_ctx *ctx, const skr_options *opt, void *d_rgb8, void *d_rgb32, skr_stats *stats)
+{
+	REQUIRE_CTX();
+	REQUIRE_SCENE();
+	Plan pl;
+	int rc = make_plan(ctx, opt, pl);
+	if(rc)
+	{
+		return rc;
+	}
+	pl.fp.rgb8	= static_cast<uint8_t *>(d_rgb8);
+	pl.fp.rgb32 = static_cast<float *>(d_rgb32);
+	return render_common(ctx, opt, pl, stats);
+}
+
+int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32, skr_stats *stats)
+{
+	REQUIRE_CTX();
+	REQUIRE_SCENE();
+	Plan pl;
+	int rc = make_plan(ctx, opt, pl);
+	if(rc)
+	{
+		return rc;
+	}
+	const size_t npx = (size_t) opt->width * opt->height;
+	if(rgb8)
+	{
+		CK(ensure(ctx->d_rgb8, ctx->rgb8_bytes, npx * 3));
+		pl.fp.rgb8 = ctx->d_rgb8;
+		if(pl.fp.world > 1)
+		{
+			CK(cudaMemsetAsync(ctx->d_rgb8, 0, npx * 3, ctx->stream));
+		}
+	}
+	if(rgb32)
+	{
+		CK(ensure(ctx->d_rgb32, ctx->rgb32_bytes, npx * 3 * sizeof(float)));
+		pl.fp.rgb32 = ctx->d_rgb32;
+		if(pl.fp.world > 1)
+		{
+			CK(cudaMemsetAsync(ctx->d_rgb32, 0, npx * 3 * sizeof(float), ctx->stream));
+		}
+	}
+	skr_stats local;
+	rc = render_common(ctx, opt, pl, &local);
+	if(rc)
+	{
+		return rc;
+	}
+	CK(cudaEventRecord(ctx->ev_x0, ctx->stream));
+	if(rgb8)
+	{
+		CK(cudaMemcpyAsync(rgb8, ctx->d_rgb8, npx * 3, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	if(rgb32)
+	{
+		CK(cudaMemcpyAsync(rgb32, ctx->d_rgb32, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CK(cudaEventRecord(ctx->ev_x1, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaEventElapsedTime(&local.ms_d2h, ctx->ev_x0, ctx->ev_x1));
+	if(stats)
+	{
+		*stats = local;
+	}
+	return SKR_OK;
+}
+
+int64_t skr_tiles_bytes(const skr_options *opt)
+{
+	if(!opt || opt->width <= 0 || opt->height <= 0)
+	{
+		return -1;
+	}
+	const int tile	  = opt->tile > 0 ? opt->tile : DEFAULT_TILE;
+	const int world	  = opt->world > 1 ? opt->world : 1;
+	const int64_t tx  = (opt->width + tile - 1) / tile, ty = (opt->height + tile - 1) / tile;
+	const int64_t per = (tx * ty + world - 1) / world;
+	return per * tile * tile * 3;
+}
+
+int skr_render_tiles_device(skr_ctx *ctx, const skr_options *opt, void *d_tiles, skr_stats *stats)
+{
+	REQUIRE_CTX();
+	REQUIRE_SCENE();
+	if(!d_tiles)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_render_tiles_device: d_tiles is null");
+	}
+	Plan pl;
+	int rc = make_plan(ctx, opt, pl);
+	if(rc)
+	{
+		return rc;
+	}
+	pl.fp.tiles8 = static_cast<uint8_t *>(d_tiles);
+	return render_common(ctx, opt, pl, stats);
+}
+
+int skr_deinterleave_device(skr_ctx *ctx, const skr_options *opt, const void *d_gathered, void *d_rgb8)
+{
+	REQUIRE_CTX();
+	Plan pl;
+	int rc = make_plan(ctx, opt, pl);
+	if(rc)
+	{
+		return rc;
+	}
+	if(!d_gathered || !d_rgb8)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_deinterleave_device: null buffer");
+	}
+	const long long n = (long long) opt->width * opt->height;
+	deinterleave_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_gathered), static_cast<uint8_t *>(d_rgb8),
+																			   opt->width, opt->height, pl.fp.tile, pl.fp.tiles_x, pl.fp.world, pl.tiles_local);
+	CK(cudaGetLastError());
+	return SKR_OK;
+}
+
+double skr_measure_fp32_peak(skr_ctx *ctx, int iters)
+{
+	if(!ctx || cudaSetDevice(ctx->device) != cudaSuccess)
+	{
+		return -1.0;
+	}
+	if(iters <= 0)
+	{
+		iters = 2048;
+	}
+	const int blocks = ctx->sm_count * 8, threads = 256;
+	float *d_out = nullptr;
+	if(cudaMalloc(&d_out, sizeof(float) * (size_t) blocks * threads) != cudaSuccess)
+	{
+		return -1.0;
+	}
+	double best = 0.0;
+	for(int rep = 0; rep < 5; rep++)
+	{
+		cudaEventRecord(ctx->ev_x0, ctx->stream);
+		fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 1.0000001f, 1.0e-7f);
+		cudaEventRecord(ctx->ev_x1, ctx->stream);
+		if(cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+		{
+			cudaFree(d_out);
+			return -1.0;
+		}
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev_x0, ctx->ev_x1);
+		const double flops = 2.0 * 8.0 * 16.0 * (double) iters * (double) blocks * threads;
+		const double tf	   = flops / (ms * 1e-3) / 1e12;
+		if(rep > 0 && tf > best)
+		{
+			best = tf;
+		}
+	}
+	cudaFree(d_out);
+	return best;
+}
+
+} // extern "C"

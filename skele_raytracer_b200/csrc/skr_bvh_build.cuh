@@ -1,0 +1,434 @@
+// skr_bvh_build.cuh -- device-side LBVH construction at scene upload.
+//
+//   1. tri_bounds_kernel   : bounds of each MIRRORED triangle (v0, 2*v0-v1, v2) (see skr_bvh.cuh), slightly inflated,
+//                            and the scene bounds (block reduce in shared memory + float atomics).
+//   2. morton_kernel       : 63-bit Morton code (21 bits/axis) of each box centre.  30-bit codes are not enough:
+//                            dragon.scn's ground quad stretches the scene box to +-20 while the model is 0.2 wide.
+//   3. radix sort          : LSD, 8 bits/pass, 8 passes over the 64-bit keys, values = triangle ids.
+//                            Per pass: per-warp digit histograms (shared-memory counters) -> exclusive scan of the
+//                            [digit][warp] table -> stable scatter (warp match + shared-memory running counters).
+//   4. karras_kernel       : Karras 2012 "Maximizing Parallelism in the Construction of BVHs": every internal node
+//                            finds its key range and split from common-prefix lengths (ties broken by index).
+//   5. refit_kernel        : bottom-up; the second thread to reach a node (atomic counter) merges the child boxes
+//                            and writes the 64-byte node with both child boxes in it.
+//   6. gather_kernel       : triangles re-laid in leaf order as 3 x float4 (128-bit loads in the leaf test).
+#pragma once
+#include "skr_math.cuh"
+
+namespace bvhb
+{
+constexpr int SORT_THREADS		  = 256;
+constexpr int SORT_WARPS		  = SORT_THREADS / 32;
+constexpr int SORT_ITEMS_PER_WARP = 32 * 32; // each warp owns 1024 consecutive keys
+
+struct Box
+{
+	float3 lo, hi;
+};
+
+__device__ __forceinline__ void atomic_min_f(float *addr, float v)
+{
+	// valid for any sign: ints order like floats for >= 0, reversed for < 0
+	if(v >= 0.0f)
+	{
+		atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+	}
+	else
+	{
+		atomicMax(reinterpret_cast<unsigned *>(addr), __float_as_uint(v));
+	}
+}
+__device__ __forceinline__ void atomic_max_f(float *addr, float v)
+{
+	if(v >= 0.0f)
+	{
+		atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+	}
+	else
+	{
+		atomicMin(reinterpret_cast<unsigned *>(addr), __float_as_uint(v));
+	}
+}
+
+// tris: [T][9] floats as uploaded.  box_lo/box_hi: float4 per triangle.  scene_box: 6 floats (lo, hi), pre-set to +-FLT_MAX.
+__global__ void tri_bounds_kernel(const float *__restrict__ tris, int T, float4 *__restrict__ box_lo, float4 *__restrict__ box_hi, float *scene_box)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	float3 lo = f3(3.0e38f, 3.0e38f, 3.0e38f), hi = f3(-3.0e38f, -3.0e38f, -3.0e38f);
+	if(i < T)
+	{
+		const float *t	= tris + 9 * (size_t) i;
+		const float3 v0 = f3(t[0], t[1], t[2]), v1 = f3(t[3], t[4], t[5]), v2 = f3(t[6], t[7], t[8]);
+		const float3 m1 = f3(2.0f * v0.x - v1.x, 2.0f * v0.y - v1.y, 2.0f * v0.z - v1.z); // mirrored vertex
+		lo				= f3(fminf(fminf(v0.x, m1.x), v2.x), fminf(fminf(v0.y, m1.y), v2.y), fminf(fminf(v0.z, m1.z), v2.z));
+		hi				= f3(fmaxf(fmaxf(v0.x, m1.x), v2.x), fmaxf(fmaxf(v0.y, m1.y), v2.y), fmaxf(fmaxf(v0.z, m1.z), v2.z));
+		// inflate: the reference's float u/v window can accept points a few ulps outside the exact triangle
+		const float diag = fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
+		const float mag	 = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+		const float pad	 = 1.0e-3f * diag + 4.0e-6f * mag + 1.0e-30f;
+		lo				 = f3(lo.x - pad, lo.y - pad, lo.z - pad);
+		hi				 = f3(hi.x + pad, hi.y + pad, hi.z + pad);
+		box_lo[i]		 = make_float4(lo.x, lo.y, lo.z, 0.0f);
+		box_hi[i]		 = make_float4(hi.x, hi.y, hi.z, 0.0f);
+	}
+	// block reduction of the scene box through shared memory, one atomic per block per component
+	__shared__ float red[6][32];
+	float v[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+#pragma unroll
+	for(int k = 0; k < 6; k++)
+	{
+#pragma unroll
+		for(int off = 16; off > 0; off >>= 1)
+		{
+			const float o = __shfl_xor_sync(0xffffffffu, v[k], off);
+			v[k]		  = k < 3 ? fminf(v[k], o) : fmaxf(v[k], o);
+		}
+		if((threadIdx.x & 31) == 0)
+		{
+			red[k][threadIdx.x >> 5] = v[k];
+		}
+	}
+	__syncthreads();
+	if(threadIdx.x < 6)
+	{
+		const int k = threadIdx.x;
+		float r		= red[k][0];
+		for(int w = 1; w < (int) (blockDim.x >> 5); w++)
+		{
+			r = k < 3 ? fminf(r, red[k][w]) : fmaxf(r, red[k][w]);
+		}
+		if(k < 3)
+		{
+			atomic_min_f(scene_box + k, r);
+		}
+		else
+		{
+			atomic_max_f(scene_box + k, r);
+		}
+	}
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned v) // spread 21 bits to every third bit
+{
+	unsigned long long x = v & 0x1fffffull;
+	x					 = (x | x << 32) & 0x1f00000000ffffull;
+	x					 = (x | x << 16) & 0x1f0000ff0000ffull;
+	x					 = (x | x << 8) & 0x100f00f00f00f00full;
+	x					 = (x | x << 4) & 0x10c30c30c30c30c3ull;
+	x					 = (x | x << 2) & 0x1249249249249249ull;
+	return x;
+}
+
+__global__ void morton_kernel(const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, const float *__restrict__ scene_box, int T,
+							  unsigned long long *__restrict__ keys, unsigned *__restrict__ vals)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= T)
+	{
+		return;
+	}
+	const float3 slo = f3(scene_box[0], scene_box[1], scene_box[2]);
+	const float3 shi = f3(scene_box[3], scene_box[4], scene_box[5]);
+	const float4 lo = box_lo[i], hi = box_hi[i];
+	const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+	const float ex = fmaxf(shi.x - slo.x, 1e-30f), ey = fmaxf(shi.y - slo.y, 1e-30f), ez = fmaxf(shi.z - slo.z, 1e-30f);
+	// quantise in double: 21 bits exceed the float mantissa's headroom near the top of the range
+	const unsigned qx = (unsigned) fmin(fmax((double) (cx - slo.x) / (double) ex * 2097152.0, 0.0), 2097151.0);
+	const unsigned qy = (unsigned) fmin(fmax((double) (cy - slo.y) / (double) ey * 2097152.0, 0.0), 2097151.0);
+	const unsigned qz = (unsigned) fmin(fmax((double) (cz - slo.z) / (double) ez * 2097152.0, 0.0), 2097151.0);
+	keys[i]			  = expand21(qx) << 2 | expand21(qy) << 1 | expand21(qz);
+	vals[i]			  = (unsigned) i;
+}
+
+// ---- radix sort -------------------------------------------------------------------------------
+// Table layout: hist[digit * nwarps + warp].  Warp w owns keys [w*1024, (w+1)*1024).
+
+__global__ void sort_hist_kernel(const unsigned long long *__restrict__ keys, int n, int shift, unsigned *__restrict__ hist, int nwarps)
+{
+	__shared__ unsigned cnt[SORT_WARPS][256];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int warp = blockIdx.x * SORT_WARPS + wib;
+	for(int d = lane; d < 256; d += 32)
+	{
+		cnt[wib][d] = 0;
+	}
+	__syncwarp();
+	if(warp < nwarps)
+	{
+		const int base = warp * SORT_ITEMS_PER_WARP;
+		for(int it = 0; it < 32; it++)
+		{
+			const int i = base + it * 32 + lane;
+			if(i < n)
+			{
+				atomicAdd(&cnt[wib][(unsigned) (keys[i] >> shift) & 255u], 1u);
+			}
+		}
+		__syncwarp();
+		for(int d = lane; d < 256; d += 32)
+		{
+			hist[(size_t) d * nwarps + warp] = cnt[wib][d];
+		}
+	}
+}
+
+// single-block exclusive scan over `len` entries (len = 256 * nwarps), in place
+__global__ void sort_scan_kernel(unsigned *__restrict__ data, int len)
+{
+	__shared__ unsigned warp_sums[32];
+	__shared__ unsigned carry;
+	if(threadIdx.x == 0)
+	{
+		carry = 0;
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	for(int base = 0; base < len; base += blockDim.x)
+	{
+		const int i		 = base + threadIdx.x;
+		const unsigned v = i < len ? data[i] : 0u;
+		unsigned s		 = v;
+#pragma unroll
+		for(int off = 1; off < 32; off <<= 1)
+		{
+			const unsigned o = __shfl_up_sync(0xffffffffu, s, off);
+			if(lane >= off)
+			{
+				s += o;
+			}
+		}
+		if(lane == 31)
+		{
+			warp_sums[wib] = s;
+		}
+		__syncthreads();
+		if(wib == 0)
+		{
+			unsigned ws = lane < nw ? warp_sums[lane] : 0u;
+#pragma unroll
+			for(int off = 1; off < 32; off <<= 1)
+			{
+				const unsigned o = __shfl_up_sync(0xffffffffu, ws, off);
+				if(lane >= off)
+				{
+					ws += o;
+				}
+			}
+			warp_sums[lane] = ws; // inclusive
+		}
+		__syncthreads();
+		const unsigned prefix = carry + (wib > 0 ? warp_sums[wib - 1] : 0u) + s - v;
+		if(i < len)
+		{
+			data[i] = prefix;
+		}
+		__syncthreads();
+		if(threadIdx.x == blockDim.x - 1)
+		{
+			carry = prefix + v;
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void sort_scatter_kernel(const unsigned long long *__restrict__ keys_in, const unsigned *__restrict__ vals_in, int n, int shift,
+									const unsigned *__restrict__ offs, int nwarps, unsigned long long *__restrict__ keys_out,
+									unsigned *__restrict__ vals_out)
+{
+	__shared__ unsigned run[SORT_WARPS][256]; // running output cursor per digit for this warp
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int warp = blockIdx.x * SORT_WARPS + wib;
+	if(warp >= nwarps)
+	{
+		return;
+	}
+	for(int d = lane; d < 256; d += 32)
+	{
+		run[wib][d] = offs[(size_t) d * nwarps + warp];
+	}
+	__syncwarp();
+	const int base			 = warp * SORT_ITEMS_PER_WARP;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	for(int it = 0; it < 32; it++)
+	{
+		const int i				   = base + it * 32 + lane;
+		const bool valid		   = i < n;
+		const unsigned long long k = valid ? keys_in[i] : 0ull;
+		const unsigned v		   = valid ? vals_in[i] : 0u;
+		const unsigned digit	   = valid ? ((unsigned) (k >> shift) & 255u) : 256u + (unsigned) lane; // invalid lanes never match
+		const unsigned peers	   = __match_any_sync(0xffffffffu, digit);
+		const unsigned rank		   = __popc(peers & lt_mask);
+		unsigned pos			   = 0;
+		if(valid)
+		{
+			pos = run[wib][digit] + rank;
+		}
+		__syncwarp();
+		if(valid && rank == 0)
+		{
+			run[wib][digit] += __popc(peers);
+		}
+		__syncwarp();
+		if(valid)
+		{
+			keys_out[pos] = k;
+			vals_out[pos] = v;
+		}
+	}
+}
+
+// ---- Karras hierarchy --------------------------------------------------------------------------
+
+__device__ __forceinline__ int delta(const unsigned long long *__restrict__ keys, int n, int i, int j)
+{
+	if(j < 0 || j >= n)
+	{
+		return -1;
+	}
+	const unsigned long long a = keys[i], b = keys[j];
+	if(a == b)
+	{
+		return 64 + __clz(i ^ j);
+	}
+	return __clzll((long long) (a ^ b));
+}
+
+// parent[0 .. n-2] for internal nodes, parent[n-1 .. 2n-2] for leaves; child < 0 means leaf ~idx
+__global__ void karras_kernel(const unsigned long long *__restrict__ keys, int n, int2 *__restrict__ children, int *__restrict__ parent)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n - 1)
+	{
+		return;
+	}
+	const int d		= (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+	const int dmin	= delta(keys, n, i, i - d);
+	int lmax		= 2;
+	while(delta(keys, n, i, i + lmax * d) > dmin)
+	{
+		lmax <<= 1;
+	}
+	int l = 0;
+	for(int t = lmax >> 1; t >= 1; t >>= 1)
+	{
+		if(delta(keys, n, i, i + (l + t) * d) > dmin)
+		{
+			l += t;
+		}
+	}
+	const int j		= i + l * d;
+	const int dnode = delta(keys, n, i, j);
+	int s			= 0;
+	int t			= l;
+	do
+	{
+		t = (t + 1) >> 1;
+		if(delta(keys, n, i, i + (s + t) * d) > dnode)
+		{
+			s += t;
+		}
+	} while(t > 1);
+	const int gamma = i + s * d + min(d, 0);
+	const int lo = min(i, j), hi = max(i, j);
+	const int left	= (lo == gamma) ? ~gamma : gamma;
+	const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+	children[i]		= make_int2(left, right);
+	if(left < 0)
+	{
+		parent[n - 1 + gamma] = i;
+	}
+	else
+	{
+		parent[left] = i;
+	}
+	if(right < 0)
+	{
+		parent[n - 1 + gamma + 1] = i;
+	}
+	else
+	{
+		parent[right] = i;
+	}
+	if(i == 0)
+	{
+		parent[0] = -1;
+	}
+}
+
+// ---- refit -------------------------------------------------------------------------------------
+
+__global__ void refit_kernel(int n, const unsigned *__restrict__ sorted_ids, const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi,
+							 const int2 *__restrict__ children, const int *__restrict__ parent, float4 *node_lo, float4 *node_hi, int *flags,
+							 float4 *__restrict__ nodes)
+{
+	const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+	if(leaf >= n)
+	{
+		return;
+	}
+	int node = parent[n - 1 + leaf];
+	while(node >= 0)
+	{
+		__threadfence();
+		if(atomicAdd(&flags[node], 1) == 0)
+		{
+			return; // first to arrive: the sibling subtree is not finished yet
+		}
+		__threadfence();
+		const int2 ch = children[node];
+		float4 llo, lhi, rlo, rhi;
+		if(ch.x < 0)
+		{
+			const unsigned t = sorted_ids[~ch.x];
+			llo = box_lo[t], lhi = box_hi[t];
+		}
+		else
+		{
+			llo = __ldcg(node_lo + ch.x), lhi = __ldcg(node_hi + ch.x);
+		}
+		if(ch.y < 0)
+		{
+			const unsigned t = sorted_ids[~ch.y];
+			rlo = box_lo[t], rhi = box_hi[t];
+		}
+		else
+		{
+			rlo = __ldcg(node_lo + ch.y), rhi = __ldcg(node_hi + ch.y);
+		}
+		nodes[4 * node + 0] = make_float4(llo.x, llo.y, llo.z, lhi.x);
+		nodes[4 * node + 1] = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
+		nodes[4 * node + 2] = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
+		nodes[4 * node + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), 0.0f, 0.0f);
+		__stcg(node_lo + node, make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f));
+		__stcg(node_hi + node, make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f));
+		node = parent[node];
+	}
+}
+
+__global__ void gather_tris_kernel(const float *__restrict__ tris, const unsigned *__restrict__ sorted_ids, int n, float4 *__restrict__ tri_v)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n)
+	{
+		return;
+	}
+	const float *t	 = tris + 9 * (size_t) sorted_ids[i];
+	tri_v[3 * i + 0] = make_float4(t[0], t[1], t[2], 0.0f);
+	tri_v[3 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
+	tri_v[3 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
+}
+
+__global__ void iota_tris_kernel(const float *__restrict__ tris, int n, float4 *__restrict__ tri_v)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n)
+	{
+		return;
+	}
+	const float *t	 = tris + 9 * (size_t) i;
+	tri_v[3 * i + 0] = make_float4(t[0], t[1], t[2], 0.0f);
+	tri_v[3 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
+	tri_v[3 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
+}
+
+} // namespace bvhb

@@ -1,0 +1,425 @@
+// skr_kernels.cuh -- the frame kernels.
+//
+//   primary_kernel       reference src/main.cpp:33-86 (per-pixel loop: camera / jittered ray generation) fused with the
+//                        first half of shade() (closest sphere + triangle any-hit, src/raytrace.h:149-192).  Rays never
+//                        touch memory.  Without --gillum it also shades the hit inline (primary hits are image-coherent,
+//                        so warps stay converged) and writes the finished pixel; with --gillum it pushes each sphere hit
+//                        to wavefront queue level 0.
+//   shade_expand_kernel  one thread per queued hit: direct illumination (+ shadow rays) of that hit, then -- if the
+//                        reference would recurse (depth - 1 >= 1) -- the fan-out of montecarlo_global_illumination
+//                        (src/raytrace.h:107-136): n child rays generated from Philox draws, intersected, misses
+//                        folded into the local sum, sphere hits pushed (warp-aggregated) to the next queue level.
+//                        Every lane of a warp holds a hit, so shading never idles lanes on misses.
+//   resolve_kernel       accumulators -> float image and RGB8 ((unsigned char)(min(1,c)*255), src/main.cpp:96).
+//
+// Accumulation across kernels is in signed 64-bit fixed point (2^-32): integer atomics commute, so the image is
+// bit-identical from run to run and for any GPU count, whatever order the queues were filled in.
+#pragma once
+#include "skr_device.cuh"
+
+#define SKR_BLOCK 256
+#define SKR_FIX_SCALE 4294967296.0f
+
+struct Queue
+{
+	float4 *a;		 // (P.xyz, bits(global pixel id))
+	float4 *b;		 // (throughput.xyz, bits(node id))
+	uint32_t *c;	 // sample | sphere << 16
+	unsigned *count; // device counter
+	unsigned cap;
+};
+
+struct FrameParams
+{
+	int width, height;
+	int tile, tiles_x, tiles_total, rank, world, wpr; // wpr = tile / 8 (warps per tile row-block)
+	int grid, spp;
+	int max_depth, gi, n_gi, shadows;
+	float angle, aspect, inv_w, inv_h;
+	uint2 key;
+	uint32_t node_base, slot_gi;
+	uint8_t *rgb8;	 // row-major frame or null
+	float *rgb32;	 // row-major frame or null
+	uint8_t *tiles8; // compact tile-major buffer or null
+	long long *accum; // 3 per local pixel (gi only)
+	unsigned long long *counters; // 8 device counters (STATS)
+	int *err;
+};
+
+struct PixelId
+{
+	int x, y;
+	bool valid;
+};
+
+// local pixel index -> image coordinates.  Local order: tile by tile (local tile j = global tile j*world + rank),
+// inside a tile warp by warp, each warp an 8x4 pixel block (coherent primary rays).
+SKR_DEV PixelId decode_pixel(const FrameParams &fp, long long lp)
+{
+	const int tpix = fp.tile * fp.tile;
+	const int lt   = (int) (lp / tpix);
+	const int r	   = (int) (lp - (long long) lt * tpix);
+	const int w = r >> 5, lane = r & 31;
+	const int wx = w % fp.wpr, wy = w / fp.wpr;
+	const int px = wx * 8 + (lane & 7), py = wy * 4 + (lane >> 3);
+	const long long gt = (long long) lt * fp.world + fp.rank;
+	PixelId p;
+	p.valid = gt < fp.tiles_total;
+	const int tx = (int) (gt % fp.tiles_x), ty = (int) (gt / fp.tiles_x);
+	p.x = tx * fp.tile + px;
+	p.y = ty * fp.tile + py;
+	p.valid = p.valid && p.x < fp.width && p.y < fp.height;
+	return p;
+}
+// image coordinates -> local pixel index (inverse of the above; the pixel must belong to this rank)
+SKR_DEV long long encode_pixel(const FrameParams &fp, int x, int y)
+{
+	const int tx = x / fp.tile, ty = y / fp.tile;
+	const int px = x - tx * fp.tile, py = y - ty * fp.tile;
+	const long long gt = (long long) ty * fp.tiles_x + tx;
+	const long long lt = gt / fp.world;
+	const int w		   = (py >> 2) * fp.wpr + (px >> 3);
+	const int lane	   = ((py & 3) << 3) | (px & 7);
+	return lt * (long long) (fp.tile * fp.tile) + (w << 5) + lane;
+}
+
+SKR_DEV long long to_fixed(float v)
+{
+	v = (v != v) ? 1.0e9f : fminf(fmaxf(v, -1.0e9f), 1.0e9f); // NaN -> white, like std::min(float(1), NaN) = 1
+	return __float2ll_rn(v * SKR_FIX_SCALE);
+}
+SKR_DEV float from_fixed(long long a) { return (float) ((double) a * (1.0 / 4294967296.0)); }
+
+SKR_DEV uint8_t quantise(float c) // (unsigned char)(std::min(float(1), c) * 255), src/main.cpp:96
+{
+	const float m = c < 1.0f ? c : 1.0f;
+	return (uint8_t) (__float2int_rz(__fmul_rn(m, 255.0f)) & 0xff);
+}
+
+SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, float3 c)
+{
+	if(fp.rgb32)
+	{
+		float *o = fp.rgb32 + 3 * ((size_t) p.y * fp.width + p.x);
+		o[0]	 = c.x;
+		o[1]	 = c.y;
+		o[2]	 = c.z;
+	}
+	if(fp.rgb8)
+	{
+		uint8_t *o = fp.rgb8 + 3 * ((size_t) p.y * fp.width + p.x);
+		o[0]	   = quantise(c.x);
+		o[1]	   = quantise(c.y);
+		o[2]	   = quantise(c.z);
+	}
+	if(fp.tiles8)
+	{
+		const int tpix = fp.tile * fp.tile;
+		const long long lt = lp / tpix;
+		const int tx = p.x % fp.tile, ty = p.y % fp.tile;
+		uint8_t *o = fp.tiles8 + 3 * ((size_t) lt * tpix + (size_t) ty * fp.tile + tx);
+		o[0]	   = quantise(c.x);
+		o[1]	   = quantise(c.y);
+		o[2]	   = quantise(c.z);
+	}
+}
+
+// Stage the scene blob into shared memory (all threads of the CTA).  Returns the pointer the routines should read.
+SKR_DEV const float4 *stage_scene(const SceneView &sv, float4 *smem)
+{
+	if(!sv.blob_in_smem)
+	{
+		return sv.blob;
+	}
+	for(int i = threadIdx.x; i < sv.blob_f4; i += blockDim.x)
+	{
+		smem[i] = __ldg(sv.blob + i);
+	}
+	__syncthreads();
+	return smem;
+}
+
+template <bool STATS>
+SKR_DEV void flush_counters(const FrameParams &fp, Counters &c)
+{
+	if(!STATS)
+	{
+		return;
+	}
+	unsigned v[8] = {c.ch, c.sh, c.st, c.stp, c.tt, c.nv, c.hits, c.le};
+#pragma unroll
+	for(int k = 0; k < 8; k++)
+	{
+		unsigned s = v[k];
+#pragma unroll
+		for(int off = 16; off > 0; off >>= 1)
+		{
+			s += __shfl_xor_sync(0xffffffffu, s, off);
+		}
+		if((threadIdx.x & 31) == 0 && s)
+		{
+			atomicAdd(fp.counters + k, (unsigned long long) s);
+		}
+	}
+}
+
+// warp-aggregated push: one atomic per warp per call.  Must be called by all 32 lanes.
+SKR_DEV void queue_push(const Queue &q, bool want, float3 p, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, int *err)
+{
+	const unsigned mask = __ballot_sync(0xffffffffu, want);
+	if(mask == 0)
+	{
+		return;
+	}
+	const int lane	 = threadIdx.x & 31;
+	const int leader = __ffs(mask) - 1;
+	unsigned base	 = 0;
+	if(lane == leader)
+	{
+		base = atomicAdd(q.count, (unsigned) __popc(mask));
+	}
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if(want)
+	{
+		const unsigned idx = base + __popc(mask & ((1u << lane) - 1u));
+		if(idx < q.cap)
+		{
+			q.a[idx] = make_float4(p.x, p.y, p.z, u2f(pixel));
+			q.b[idx] = make_float4(thr.x, thr.y, thr.z, u2f(node));
+			q.c[idx] = (sample & 0xffffu) | ((uint32_t) sphere << 16);
+		}
+		else
+		{
+			atomicOr(err, 1); // cannot happen: the host sizes chunks so that a full fan-out fits
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// primary_kernel: local pixels [lp0, lp0 + npix)
+// ------------------------------------------------------------------------------------------------
+template <bool GI, bool STATS>
+__global__ void __launch_bounds__(SKR_BLOCK) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix)
+{
+	extern __shared__ float4 smem[];
+	const float4 *B = stage_scene(sv, smem);
+	Counters cnt;
+	zero(cnt);
+
+	const long long g  = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const long long lp = lp0 + g;
+	PixelId p		   = decode_pixel(fp, lp);
+	p.valid			   = p.valid && g < npix;
+
+	float3 sum = f3(0.0f, 0.0f, 0.0f);
+	RngCtx rng;
+	rng.pixel = (uint32_t) (p.y * fp.width + p.x);
+	rng.node  = 0;
+	rng.key	  = fp.key;
+
+	const int nsamples = fp.max_depth > 0 ? fp.spp : 0; // depth <= 0: shade() returns black (src/raytrace.h:142-145)
+	for(int s = 0; s < nsamples; s++)
+	{
+		rng.sample = (uint32_t) s;
+		float u, v;
+		if(fp.grid > 0)
+		{
+			// src/main.cpp:52-54: ONE draw for both axes, all-float arithmetic
+			const float r = rng_unit(rng_block(rng, 0u).x);
+			u = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn((float) p.x, r), fp.inv_w)), 1.0f), fp.angle), fp.aspect);
+			v = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(2.0f, __fmul_rn(__fadd_rn((float) p.y, r), fp.inv_h))), fp.angle);
+		}
+		else
+		{
+			// src/main.cpp:73-74: evaluated in double (x + 0.5 promotes), stored to float
+			u = (float) __dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(2.0, __dmul_rn((double) p.x + 0.5, (double) fp.inv_w)), 1.0), (double) fp.angle),
+								  (double) fp.aspect);
+			v = (float) __dmul_rn(__dsub_rn(1.0, __dmul_rn(2.0, __dmul_rn((double) p.y + 0.5, (double) fp.inv_h))), (double) fp.angle);
+		}
+		// src/main.cpp:76-77: D + u*R + v*U, never normalised
+		const float3 d = add_rn(add_rn(sv.cam_dir, muls_rn(sv.cam_right, u)), muls_rn(sv.cam_up, v));
+		const float3 o = sv.cam_pos;
+
+		float t = 0.0f;
+		int h	= -3;
+		if(p.valid)
+		{
+			h = closest_hit<true, STATS>(B, sv, o, d, t, cnt);
+		}
+		float3 hp = f3(0.0f, 0.0f, 0.0f);
+		if(h == -2)
+		{
+			sum += sv.background;
+		}
+		else if(h >= 0)
+		{
+			hp = add_rn(o, muls_rn(d, t)); // src/raytrace.h:204
+			if(!GI)
+			{
+				const float3 n = normalize_rn(sub_rn(hp, f3(B[sv.off_geom + h])));
+				sum += direct_light<STATS>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt);
+			}
+		}
+		if(GI)
+		{
+			queue_push(q0, h >= 0, hp, rng.pixel, f3(1.0f, 1.0f, 1.0f), 0u, (uint32_t) s, h, fp.err);
+		}
+	}
+
+	if(p.valid)
+	{
+		if(GI)
+		{
+			fp.accum[3 * lp + 0] = to_fixed(sum.x);
+			fp.accum[3 * lp + 1] = to_fixed(sum.y);
+			fp.accum[3 * lp + 2] = to_fixed(sum.z);
+		}
+		else
+		{
+			if(fp.grid > 0)
+			{
+				const float n2 = (float) fp.spp; // image[y][x] /= (grid*grid), src/main.cpp:68
+				sum			   = f3(__fdiv_rn(sum.x, n2), __fdiv_rn(sum.y, n2), __fdiv_rn(sum.z, n2));
+			}
+			write_pixel(fp, lp, p, sum);
+		}
+	}
+	flush_counters<STATS>(fp, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shade_expand_kernel: queue entries [start, start + count) of `in`
+// ------------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(SKR_BLOCK) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
+																  const Queue out, int expand)
+{
+	extern __shared__ float4 smem[];
+	const float4 *B = stage_scene(sv, smem);
+	Counters cnt;
+	zero(cnt);
+
+	const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = g < count;
+	const unsigned i = start + (valid ? g : 0u);
+
+	const float4 qa	  = in.a[i];
+	const float4 qb	  = in.b[i];
+	const uint32_t qc = in.c[i];
+	const float3 hp	  = f3(qa);
+	const float3 thr  = f3(qb);
+	const int sidx	  = (int) (qc >> 16);
+	RngCtx rng;
+	rng.pixel  = f2u(qa.w);
+	rng.sample = qc & 0xffffu;
+	rng.node   = f2u(qb.w);
+	rng.key	   = fp.key;
+
+	float3 contrib = f3(0.0f, 0.0f, 0.0f);
+	const float3 n = normalize_rn(sub_rn(hp, f3(B[sv.off_geom + sidx]))); // src/raytrace.h:205
+	const float3 kd = f3(B[sv.off_diff + sidx]);
+	if(valid)
+	{
+		const float3 direct = direct_light<STATS>(B, sv, fp.shadows != 0, rng, sidx, hp, n, cnt);
+		contrib				= thr * kd * (direct * 0.318309886183790672f); // (direct / pi) * kd, src/raytrace.h:213
+	}
+	if(expand)
+	{
+		// src/raytrace.h:107-136: acc += r1 * shade(child) / (1/pi); acc /= n; combine 2 * acc * kd
+		float3 nt, nb;
+		basis_from_normal(n, nt, nb);
+		const float3 tk = thr * kd * (6.28318530717958648f / (float) fp.n_gi);
+		const float3 o	= adds_rn(hp, 0.00001f);
+		for(int c = 0; c < fp.n_gi; c++)
+		{
+			const uint4 r  = rng_block(rng, fp.slot_gi + (uint32_t) c);
+			const float r1 = rng_unit(r.x), r2 = rng_unit(r.y);
+			const float3 d = gi_child_dir(r1, r2, n, nt, nb);
+			float t		   = 0.0f;
+			int h		   = -3;
+			if(valid)
+			{
+				h = closest_hit<false, STATS>(B, sv, o, d, t, cnt);
+			}
+			const float3 w = tk * r1;
+			if(h == -2)
+			{
+				contrib += w * sv.background;
+			}
+			const float3 cp = add_rn(o, muls_rn(d, t));
+			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, fp.err);
+		}
+	}
+	if(valid)
+	{
+		const int x = (int) (rng.pixel % (uint32_t) fp.width), y = (int) (rng.pixel / (uint32_t) fp.width);
+		const long long lp = encode_pixel(fp, x, y);
+		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 0), (unsigned long long) to_fixed(contrib.x));
+		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 1), (unsigned long long) to_fixed(contrib.y));
+		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 2), (unsigned long long) to_fixed(contrib.z));
+	}
+	flush_counters<STATS>(fp, cnt);
+}
+
+__global__ void __launch_bounds__(SKR_BLOCK) resolve_kernel(const FrameParams fp, long long lp0, long long npix)
+{
+	const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if(g >= npix)
+	{
+		return;
+	}
+	const long long lp = lp0 + g;
+	const PixelId p	   = decode_pixel(fp, lp);
+	if(!p.valid)
+	{
+		return;
+	}
+	float3 c = f3(from_fixed(fp.accum[3 * lp + 0]), from_fixed(fp.accum[3 * lp + 1]), from_fixed(fp.accum[3 * lp + 2]));
+	if(fp.grid > 0)
+	{
+		const float n2 = (float) fp.spp;
+		c			   = f3(__fdiv_rn(c.x, n2), __fdiv_rn(c.y, n2), __fdiv_rn(c.z, n2));
+	}
+	write_pixel(fp, lp, p, c);
+}
+
+// skr_deinterleave_device: gathered rank-major compact tiles -> row-major frame
+__global__ void deinterleave_kernel(const uint8_t *__restrict__ gathered, uint8_t *__restrict__ rgb8, int width, int height, int tile, int tiles_x,
+									int world, long long tiles_per_rank)
+{
+	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= (long long) width * height)
+	{
+		return;
+	}
+	const int x = (int) (i % width), y = (int) (i / width);
+	const int tx = x / tile, ty = y / tile;
+	const long long gt = (long long) ty * tiles_x + tx;
+	const long long r = gt % world, lt = gt / world;
+	const size_t src = ((size_t) (r * tiles_per_rank + lt) * tile * tile + (size_t) (y - ty * tile) * tile + (x - tx * tile)) * 3;
+	rgb8[3 * i + 0]	 = gathered[src + 0];
+	rgb8[3 * i + 1]	 = gathered[src + 1];
+	rgb8[3 * i + 2]	 = gathered[src + 2];
+}
+
+// FP32 FMA peak microbenchmark: 8 independent FFMA chains per thread, register resident.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float a, float b)
+{
+	float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+	for(int i = 0; i < iters; i++)
+	{
+#pragma unroll
+		for(int k = 0; k < 16; k++)
+		{
+			x0 = fmaf(x0, a, b);
+			x1 = fmaf(x1, a, b);
+			x2 = fmaf(x2, a, b);
+			x3 = fmaf(x3, a, b);
+			x4 = fmaf(x4, a, b);
+			x5 = fmaf(x5, a, b);
+			x6 = fmaf(x6, a, b);
+			x7 = fmaf(x7, a, b);
+		}
+	}
+	out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
