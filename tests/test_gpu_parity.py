@@ -1,0 +1,356 @@
+"""Parity tests proper: the CUDA path, through the C ABI (libskr.so), against the oracle on the same inputs.
+
+Oracle = oracle/skr_oracle.c (the C port), which tests/test_oracle_*.py pin bit-for-bit to the reference's golden
+vector and to the reference's own compiled code.  Nothing here reads /root/reference.
+"""
+import dataclasses
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import skele_raytracer_b200 as S
+from conftest import GOLDEN, ROOT, random_scene
+from make_cases import GOLDEN_CASES
+from oracle import oracle_lib as O
+from parity import assert_image_parity, assert_mean_parity, frac_pixels_within
+from test_oracle_ref import golden_testcpu
+
+pytestmark = pytest.mark.gpu
+
+
+def to_gpu_scene(s: O.Scene) -> S.Scene:
+    return S.Scene(s.spheres, s.tris, s.plights, s.dlights, s.fogs, s.camera, s.ambient, s.background)
+
+
+def opts(**kw):
+    """-> (oracle Options, GPU Options) from one kwargs dict"""
+    seed = kw.pop("seed", 0)
+    extra = {k: kw.pop(k) for k in ("rank", "world", "tile", "collect_stats", "queue_capacity") if k in kw}
+    return O.Options(**kw), S.Options(seed=seed, **extra, **kw)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    r = S.Renderer()
+    yield r
+    r.close()
+
+
+@pytest.fixture(scope="module")
+def gscenes(scenes):
+    return {k: to_gpu_scene(v) for k, v in scenes.items()}
+
+
+# ---- golden vectors ----------------------------------------------------------------------------
+
+def test_dragon_640x480_is_byte_identical_to_testcpu_ppm(gpu, gscenes):
+    """The reference's only golden render (renders/testcpu.ppm == dragon.scn @ 640x480)."""
+    img, sha = golden_testcpu()
+    gpu.upload(gscenes["dragon"])
+    _, rgb8, _ = gpu.render(S.Options(width=640, height=480, fov=60.0, max_depth=1), want_rgb32=False)
+    assert hashlib.sha256(O.ppm_bytes(rgb8)).hexdigest() == sha
+
+
+# (spheres2 is stochastic even without --gillum/--jsample: its fog record makes the shading draw random numbers)
+@pytest.mark.parametrize("key", sorted(k for k, (sc, kw, _) in GOLDEN_CASES.items()
+                                       if not kw.get("monte_carlo") and not kw.get("grid_size") and sc != "spheres2"))
+def test_deterministic_golden_images_from_the_reference(gpu, gscenes, ref_images, key):
+    scene, kw, _ = GOLDEN_CASES[key]
+    gpu.upload(gscenes[scene])
+    g32, _, _ = gpu.render(S.Options(**kw))
+    assert_image_parity(g32, ref_images[key], what=key)
+
+
+# ---- deterministic modes -----------------------------------------------------------------------
+
+@pytest.mark.parametrize("scene", ["spheres1", "spheres2_nofog", "bear", "test", "dragon"])
+@pytest.mark.parametrize("shadows", [False, True])
+def test_deterministic_parity_small(gpu, port, scenes, gscenes, scene, shadows):
+    oo, go = opts(width=480, height=270, max_depth=1 if not shadows else 3, use_shadows=shadows, collect_stats=True)
+    p32, p8, pst, _ = port.render(scenes[scene], oo)
+    gpu.upload(gscenes[scene])
+    g32, g8, gst = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, what=f"{scene} shadows={shadows}")
+    assert gst.closest_hit_rays == pst["closest_hit_rays"]
+    assert abs(int(gst.shadow_rays) - pst["shadow_rays"]) <= 1e-4 * max(1, pst["shadow_rays"])
+
+
+@pytest.mark.parametrize("scene,kw", [("spheres1", dict(max_depth=1)),                       # BASELINE config 1
+                                      ("dragon", dict(use_shadows=True)),                    # BASELINE config 4
+                                      ("bear", dict(use_shadows=True)), ("test", dict(use_shadows=True, fov=45.0))])
+def test_deterministic_parity_1920x1080(gpu, port, scenes, gscenes, scene, kw):
+    oo, go = opts(width=1920, height=1080, **kw)
+    p32, p8, _, _ = port.render(scenes[scene], oo)
+    gpu.upload(gscenes[scene])
+    g32, g8, _ = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, what=f"{scene} 1080p")
+
+
+# ---- stochastic modes, same keyed Philox stream on both sides ----------------------------------
+
+STOCH = [("spheres2", dict(width=240, height=135, grid_size=5, use_shadows=True, seed=1)),               # config 2 shape
+         ("spheres2", dict(width=96, height=54, max_depth=4, monte_carlo=True, num_path_traces=16, seed=2)),  # config 3 shape
+         ("bear", dict(width=64, height=36, monte_carlo=True, num_path_traces=64, grid_size=4, use_shadows=True, seed=3)),  # config 5 shape
+         ("spheres1", dict(width=128, height=72, max_depth=3, monte_carlo=True, num_path_traces=5, use_shadows=True, seed=4)),
+         ("test", dict(width=96, height=54, max_depth=2, monte_carlo=True, num_path_traces=3, grid_size=2, seed=5)),
+         ("spheres2_nofog", dict(width=128, height=72, grid_size=1, seed=6))]
+
+
+@pytest.mark.parametrize("scene,kw", STOCH)
+def test_stochastic_same_stream_parity(gpu, port, scenes, gscenes, scene, kw):
+    oo, go = opts(collect_stats=True, **dict(kw))
+    p32, p8, pst, _ = port.render(scenes[scene], oo, rng_mode=O.RNG_PHILOX, seed=go.seed)
+    gpu.upload(gscenes[scene])
+    g32, g8, gst = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, what=f"{scene} {kw}")
+    rays_p = pst["closest_hit_rays"] + pst["shadow_rays"]
+    rays_g = int(gst.closest_hit_rays + gst.shadow_rays)
+    assert abs(rays_g - rays_p) <= 2e-4 * rays_p
+
+
+def test_config2_full_size_same_stream(gpu, port, scenes, gscenes):
+    """BASELINE config 2 at its real size: spheres2 1920x1080 --jsample 5 --shadow."""
+    oo, go = opts(width=1920, height=1080, grid_size=5, use_shadows=True, seed=21)
+    p32, p8, _, _ = port.render(scenes["spheres2"], oo, rng_mode=O.RNG_PHILOX, seed=21)
+    gpu.upload(gscenes["spheres2"])
+    g32, g8, _ = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, what="config 2")
+
+
+@pytest.mark.parametrize("scene,kw,rows", [
+    ("spheres2", dict(width=1920, height=1080, max_depth=4, monte_carlo=True, num_path_traces=16, seed=31), (500, 540)),          # config 3
+    ("bear", dict(width=3840, height=2160, monte_carlo=True, num_path_traces=64, grid_size=4, use_shadows=True, seed=32), (1000, 1004))])  # config 5
+def test_full_size_gi_row_window(gpu, port, scenes, gscenes, scene, kw, rows):
+    """Configs 3 and 5 at full size: the oracle renders a window of rows of the SAME frame (it would need hours for all
+    of it); the GPU renders the whole frame."""
+    oo, go = opts(**dict(kw))
+    y0, y1 = rows
+    p32, _, _, _ = port.render(scenes[scene], oo, rng_mode=O.RNG_PHILOX, seed=go.seed, y0=y0, y1=y1, want_rgb8=False)
+    gpu.upload(gscenes[scene])
+    g32, _, _ = gpu.render(go, want_rgb8=False)
+    assert_image_parity(g32[y0:y1], p32[y0:y1], what=f"{scene} rows {rows}")
+
+
+# ---- stochastic modes vs the reference's own rand() stream: per-pixel mean, 3 sigma, N seeds ---
+
+@pytest.mark.parametrize("scene,kw,N", [
+    ("spheres2", dict(width=64, height=36, grid_size=5, use_shadows=True), 8),
+    ("spheres2", dict(width=48, height=27, max_depth=4, monte_carlo=True, num_path_traces=16), 16),
+    ("bear", dict(width=32, height=18, monte_carlo=True, num_path_traces=16, grid_size=2, use_shadows=True), 16)])
+def test_stochastic_mean_parity_vs_reference_rand_stream(gpu, port, scenes, gscenes, scene, kw, N):
+    oo, _ = opts(**dict(kw))
+    gpu.upload(gscenes[scene])
+    A = np.stack([gpu.render(S.Options(seed=i, **kw), want_rgb8=False)[0] for i in range(N)])
+    B = np.stack([port.render(scenes[scene], oo, rng_mode=O.RNG_LIBC, seed=1000 + i)[0] for i in range(N)])
+    assert_mean_parity(A, B, what=f"{scene} {kw}")
+
+
+# ---- edge cases ---------------------------------------------------------------------------------
+
+def test_empty_scene_is_background(gpu):
+    s = S.Scene(background=np.array([0.25, 0.5, 0.75], np.float32), camera=np.array([0, 0, 0, 0, 0, 1, 0, 1, 0, 1, 0, 0], np.float32))
+    gpu.upload(s)
+    g32, g8, _ = gpu.render(S.Options(width=37, height=23))
+    assert np.allclose(g32, [0.25, 0.5, 0.75]) and (g8 == [63, 127, 191]).all()
+
+
+def test_depth_zero_is_black(gpu, gscenes):
+    gpu.upload(gscenes["bear"])
+    g32, g8, _ = gpu.render(S.Options(width=64, height=36, max_depth=0))
+    assert not g32.any() and not g8.any()
+    g32, _, _ = gpu.render(S.Options(width=64, height=36, max_depth=0, monte_carlo=True, num_path_traces=4))
+    assert not g32.any()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (37, 23), (33, 65), (8, 4), (257, 3)])
+def test_ragged_sizes(gpu, port, scenes, gscenes, w, h):
+    oo, go = opts(width=w, height=h, use_shadows=True)
+    p32, p8, _, _ = port.render(scenes["spheres1"], oo)
+    gpu.upload(gscenes["spheres1"])
+    g32, g8, _ = gpu.render(go)
+    assert frac_pixels_within(g32, p32) >= 1.0 - 2.0 / (w * h) - 0.001
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_scenes(gpu, port, seed):
+    """Spheres + triangles in front of / behind each other, directional lights, several fogs, odd --gillum counts."""
+    rng = np.random.default_rng(seed)
+    sc = random_scene(rng, nspheres=int(rng.integers(1, 12)), nplights=int(rng.integers(1, 4)), ntris=int(rng.integers(0, 60)),
+                      nfogs=int(rng.integers(0, 3)), ndlights=int(rng.integers(0, 3)))
+    gpu.upload(to_gpu_scene(sc))
+    for kw in [dict(width=160, height=100, use_shadows=True), dict(width=96, height=60, grid_size=2, use_shadows=bool(seed & 1), seed=seed),
+               dict(width=64, height=40, max_depth=3, monte_carlo=True, num_path_traces=int(rng.integers(1, 7)), use_shadows=True, seed=seed)]:
+        oo, go = opts(**dict(kw))
+        p32, p8, _, _ = port.render(sc, oo, rng_mode=O.RNG_PHILOX, seed=go.seed)
+        g32, g8, _ = gpu.render(go)
+        assert_image_parity(g32, p32, g8, p8, min_ok=0.998, what=f"random scene {seed} {kw}")
+
+
+def test_many_spheres_use_the_global_memory_path(gpu, port):
+    """More spheres than the shared-memory staging holds (blob > 64 KB)."""
+    rng = np.random.default_rng(5)
+    sc = random_scene(rng, nspheres=1200, nplights=2)
+    sc.spheres[:, 3] *= 0.2
+    oo, go = opts(width=96, height=54, use_shadows=True)
+    p32, p8, _, _ = port.render(sc, oo)
+    gpu.upload(to_gpu_scene(sc))
+    g32, g8, _ = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, min_ok=0.998, what="1200 spheres")
+
+
+# ---- BVH ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("ntris", [1, 2, 3, 33, 1000, 20000])
+def test_bvh_equals_brute_force(gpu, ntris):
+    rng = np.random.default_rng(ntris)
+    sc = random_scene(rng, nspheres=3, nplights=1, ntris=ntris)
+    if ntris >= 1000:
+        sc.tris = (sc.tris.reshape(-1, 3, 3)[:, :1] + 0.08 * (sc.tris.reshape(-1, 3, 3) - sc.tris.reshape(-1, 3, 3)[:, :1])).reshape(-1, 9)
+    if ntris == 33:
+        sc.tris[5:20] = sc.tris[5]  # duplicates -> identical Morton codes
+    g = to_gpu_scene(sc)
+    go = S.Options(width=200, height=120, use_shadows=True)
+    gpu.upload(g)
+    a32, _, _ = gpu.render(go)
+    os.environ["SKR_NO_BVH"] = "1"
+    try:
+        gpu.upload(g)
+        b32, _, _ = gpu.render(go)
+    finally:
+        del os.environ["SKR_NO_BVH"]
+    assert np.array_equal(a32, b32)
+
+
+def test_bvh_dragon_1080p_equals_brute_force_window(gpu, port, scenes, gscenes):
+    oo, go = opts(width=1920, height=1080)
+    gpu.upload(gscenes["dragon"])
+    g32, _, st = gpu.render(dataclasses.replace(go, collect_stats=True))
+    p32, _, _, _ = port.render(scenes["dragon"], oo, y0=500, y1=560)
+    assert np.array_equal(g32[500:560], p32[500:560])
+    # the hierarchy must actually prune: far fewer leaf tests than the reference's T per ray
+    assert st.tri_tests < 0.02 * 1920 * 1080 * 10002
+
+
+# ---- determinism, chunking, frame split ---------------------------------------------------------
+
+GI_KW = dict(width=160, height=96, max_depth=3, monte_carlo=True, num_path_traces=6, grid_size=2, use_shadows=True, seed=77)
+
+
+def test_run_to_run_bit_identical(gpu, gscenes):
+    gpu.upload(gscenes["spheres2"])
+    a, _, _ = gpu.render(S.Options(**GI_KW))
+    b, _, _ = gpu.render(S.Options(**GI_KW))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_queue_capacity_does_not_change_the_image(gpu, gscenes):
+    gpu.upload(gscenes["spheres2"])
+    a, _, sa = gpu.render(S.Options(**GI_KW))
+    b, _, sb = gpu.render(S.Options(queue_capacity=6 * 256, **GI_KW))
+    assert sb.queue_chunks > sa.queue_chunks
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("world,tile", [(2, 32), (3, 16), (8, 32)])
+def test_frame_split_is_bit_identical_for_any_world(gpu, gscenes, world, tile):
+    gpu.upload(gscenes["spheres2"])
+    full32, full8, _ = gpu.render(S.Options(**GI_KW))
+    acc32 = np.zeros_like(full32)
+    acc8 = np.zeros_like(full8)
+    from skele_raytracer_b200 import tiles as T
+    own = T.owner_map(GI_KW["width"], GI_KW["height"], world, tile)
+    for r in range(world):
+        p32, p8, _ = gpu.render(S.Options(rank=r, world=world, tile=tile, **GI_KW))
+        assert not p32[own != r].any()          # other ranks' pixels are left zero
+        acc32 += p32
+        acc8 += p8
+    assert np.array_equal(acc32.view(np.uint32), full32.view(np.uint32)) and np.array_equal(acc8, full8)
+
+
+@pytest.mark.parametrize("world,tile", [(1, 32), (2, 32), (4, 16)])
+def test_compact_tiles_and_deinterleave_on_device(gpu, gscenes, world, tile):
+    import torch
+    from skele_raytracer_b200 import tiles as T
+    kw = dict(width=150, height=70, use_shadows=True)
+    gpu.upload(gscenes["spheres1"])
+    _, full8, _ = gpu.render(S.Options(**kw), want_rgb32=False)
+    parts = []
+    for r in range(world):
+        o = S.Options(rank=r, world=world, tile=tile, **kw)
+        buf = torch.zeros(gpu.tiles_bytes(o), dtype=torch.uint8, device="cuda")
+        assert buf.numel() == T.tiles_bytes(kw["width"], kw["height"], world, tile)
+        gpu.render_tiles_device(o, buf.data_ptr())
+        parts.append(buf)
+        assert np.array_equal(buf.cpu().numpy() * (T.compact_from_frame(np.ones_like(full8), r, world, tile) > 0),
+                              T.compact_from_frame(full8, r, world, tile))
+    gathered = torch.cat(parts)
+    frame = torch.zeros((kw["height"], kw["width"], 3), dtype=torch.uint8, device="cuda")
+    o = S.Options(rank=0, world=world, tile=tile, **kw)
+    gpu.deinterleave_device(o, gathered.data_ptr(), frame.data_ptr())
+    gpu.sync()
+    assert np.array_equal(frame.cpu().numpy(), full8)
+
+
+def test_render_device_matches_host_render(gpu, gscenes):
+    import torch
+    gpu.upload(gscenes["bear"])
+    o = S.Options(width=320, height=180, use_shadows=True)
+    h32, h8, _ = gpu.render(o)
+    d8 = torch.zeros((180, 320, 3), dtype=torch.uint8, device="cuda")
+    d32 = torch.zeros((180, 320, 3), dtype=torch.float32, device="cuda")
+    gpu.render_device(o, d8.data_ptr(), d32.data_ptr())
+    assert np.array_equal(d8.cpu().numpy(), h8) and np.array_equal(d32.cpu().numpy(), h32)
+
+
+# ---- error behaviour ------------------------------------------------------------------------------
+
+def test_errors_are_reported_not_swallowed(gscenes):
+    r = S.Renderer()
+    try:
+        with pytest.raises(S.SkrError, match="skr_scene_upload must be called"):
+            r.render(S.Options(width=8, height=8))
+        r.upload(gscenes["spheres1"])
+        with pytest.raises(S.SkrError, match="width/height"):
+            r.render(S.Options(width=0, height=8))
+        with pytest.raises(S.SkrError, match="tile"):
+            r.render(S.Options(width=8, height=8, tile=12))
+        with pytest.raises(S.SkrError, match="rank"):
+            r.render(S.Options(width=8, height=8, rank=2, world=2))
+    finally:
+        r.close()
+
+
+# ---- the C++ front end ----------------------------------------------------------------------------
+
+def test_cli_writes_the_same_ppm(gpu, tmp_path):
+    exe = os.path.join(ROOT, "host", "raytracer")
+    scn = os.path.join(GOLDEN, "tiny.scn")
+    out = tmp_path / "tiny.ppm"
+    r = subprocess.run([exe, "--path", scn, "--output", str(out), "--width", "200", "--height", "120", "--shadow", "--parallel", "true", "--stats"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "WROTE TO PPM" in r.stdout and '"closest_hit_rays": 24000' in r.stdout
+    sc = S.parseScene(scn)
+    gpu.upload(sc)
+    _, g8, _ = gpu.render(S.Options(width=200, height=120, use_shadows=True), want_rgb32=False)
+    assert out.read_bytes() == O.ppm_bytes(g8)
+    # and the reference-interface mirror writes the same file
+    out2 = tmp_path / "tiny2.ppm"
+    S.generate_rays_parallel(sc, S.Options(width=200, height=120, use_shadows=True), str(out2), renderer=gpu)
+    assert out2.read_bytes() == out.read_bytes()
+
+
+def test_cli_on_reference_scene_files_if_present(port, scenes, tmp_path):
+    d = O.REF_SCENES
+    if not os.path.isdir(d):
+        pytest.skip("oracle/_ref/scenes not shipped")
+    exe = os.path.join(ROOT, "host", "raytracer")
+    out = tmp_path / "bear.ppm"
+    subprocess.run([exe, "--path", os.path.join(d, "bear.scn"), "--output", str(out), "--width", "320", "--height", "180", "--shadow"], check=True,
+                   capture_output=True, timeout=300)
+    _, p8, _, _ = port.render(scenes["bear"], O.Options(width=320, height=180, use_shadows=True))
+    got = np.frombuffer(out.read_bytes()[len(b"P6\n320 180\n255\n"):], np.uint8).reshape(180, 320, 3)
+    assert (np.abs(got.astype(int) - p8.astype(int)) <= 1).all(axis=2).mean() >= 0.999
