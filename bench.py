@@ -181,11 +181,14 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         tiles = torch.empty(r.tiles_bytes(base), dtype=torch.uint8, device=dev)
         cst = r.render_tiles_device(dataclasses.replace(base, collect_stats=True), tiles.data_ptr()).as_dict()
         keys = ["closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "tri_tests", "bvh_node_visits", "sphere_hits", "light_evals"]
+        cst_local = dict(cst)
         t = torch.tensor([float(cst[k]) for k in keys], dtype=torch.float64, device=dev)
         dist.all_reduce(t)
         for k, v in zip(keys, t.tolist()):
             cst[k] = int(v)
         gathered = torch.empty(tiles.numel() * world, dtype=torch.uint8, device=dev)
+    else:
+        cst_local = dict(cst)
     frame = torch.empty((base.height, base.width, 3), dtype=torch.uint8, device=dev)
     rays = cst["closest_hit_rays"] + cst["shadow_rays"]
 
@@ -202,6 +205,7 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
     kernel_ms = {"primary": 0.0, "bounce": 0.0, "resolve": 0.0}
     with torch.cuda.stream(ext):
         for _ in range(warmup):
+            flush_buf.zero_()  # (also pays torch's lazy load of its fill kernel before the timed region)
             step()
         torch.cuda.synchronize()
         if world > 1:
@@ -228,7 +232,7 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
     out = {"desc": desc, "scene": scene_name, "kw": kw, "rays": rays, "ms_per_step": dev_ms / steps, "value": rays / (dev_ms / steps) / 1e3,
-           "wall_ms_per_step": (t_end - t_begin) * 1e3 / steps, "launches": launches, "stats": cst, "t_begin": t_begin, "t_end": t_end,
+           "wall_ms_per_step": (t_end - t_begin) * 1e3 / steps, "launches": launches, "stats": cst, "stats_rank0": cst_local, "t_begin": t_begin, "t_end": t_end,
            "kernel_ms_per_step": {k: v / steps for k, v in kernel_ms.items()},
            "primary_samples": base.width * base.height * (base.grid_size ** 2 if base.grid_size else 1)}
 
@@ -317,7 +321,8 @@ def main_gpu(args, rank, world, local_rank):
     if rank == 0:
         peaks, peaks_src = load_peaks()
         st = m["stats"]
-        flops = algorithmic_flops(st, m["primary_samples"])
+        # roofline of the dominant kernel AS LAUNCHED ON RANK 0: its own share of the frame's work / its own duration
+        flops = algorithmic_flops(m["stats_rank0"], m["primary_samples"] / world)
         # the dominant kernel: primary_kernel without --gillum, shade_expand_kernel with it
         dom = "bounce" if m["kw"].get("monte_carlo") else "primary"
         dom_ms = m["kernel_ms_per_step"][dom] or m["ms_per_step"]
@@ -338,7 +343,7 @@ def main_gpu(args, rank, world, local_rank):
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "traffic": None, "kernel": "primary_kernel<false,false>" if dom == "primary" else "shade_expand_kernel<false>",
                          "kernel_ms_per_frame": dom_ms, "kernel_launches_per_frame": dom_launches,
-                         "flops_per_frame_algorithmic": flops,
+                         "flops_per_frame_algorithmic_this_rank": flops,
                          "peak_source": "FFMA microbenchmark measured live in this run (skr_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                          "note": "compute-bound FP32 CUDA-core path (no dense contraction -> tensor cores unused); algorithmic HBM traffic is the RGB8 frame only",
                          "hbm": {"algorithmic_bytes_per_frame": frame_bytes, "achieved_gbs": frame_bytes / (m["ms_per_step"] * 1e-3) / 1e9,
