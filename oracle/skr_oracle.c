@@ -106,32 +106,50 @@ typedef struct
 	uint32_t slot_gi;	/* first slot of the GI (r1,r2) draws */
 } ctx_t;
 
-/* Slot map of the keyed stream (identical in the CUDA path, csrc/skr_rng.cuh):
+/* Slot map of the keyed stream (identical in the CUDA path, csrc/skr_device.cuh).  Philox hands out 128 bits per
+ * call, so independent draws are packed into one block wherever the same thread needs them together:
  *   counter = (pixel, sample, node, slot), key = (seed_lo, seed_hi)
- *   slot 0                        : .x = jitter r of this primary sample (node 0 only)
- *   slot 1 + (call*L + i)*F + j   : fog draws for call (0 diffuse, 1 specular), light i, fog j:
- *                                   .x = xi, .y/.z/.w = scattering offsets
- *   slot 1 + 2*L*F + c            : .x = r1, .y = r2 of GI child c of this node
+ *   jitter   : counter (pixel, sample >> 2, 0, 0), word sample & 3          -> r of this primary sample (31 bits)
+ *   fog      : slot 1 + i*F + j (light i, fog j), shared by the diffuse and the specular call:
+ *                word 0 -> xi of the diffuse call (31 bits), word 1 -> xi of the specular call (31 bits),
+ *                word 2 -> the diffuse call's three scattering offsets, 10 bits each (bits 0-9, 10-19, 20-29),
+ *                word 3 -> the specular call's three offsets, same packing;  offset = -1 + (k + 0.5) / 512
+ *   GI child : slot 1 + L*F + (c >> 1): children 2m and 2m+1 share a block, (r1, r2) = words (0,1) / (2,3), 31 bits
+ * In SKRO_RNG_LIBC mode none of this applies: every draw is one rand() call in the reference's order.
  */
-static inline uint32_t draw_bits(const ctx_t *c, uint32_t node, uint32_t slot, int comp)
+static inline void philox_block(const ctx_t *c, uint32_t sample, uint32_t node, uint32_t slot, uint32_t out[4])
+{
+	uint32_t ctr[4] = {c->pixel, sample, node, slot};
+	skro_philox4x32_10(ctr, c->key, out);
+}
+/* static_cast<float>(rand()) / static_cast<float>(RAND_MAX)   (RAND_MAX = 2^31-1, as float 2^31) */
+static inline float unit_from_31(uint32_t k) { return (float) (int32_t) k / (float) 2147483647; }
+/* -1.0f + rand() / float(RAND_MAX / 2)   src/utils.h:219-221 */
+static inline float pm1_from_31(uint32_t k) { return -1.0f + (float) (int32_t) k / (float) (2147483647 / (1 + 1)); }
+static inline float pm1_from_10(uint32_t k) { return -1.0f + ((float) k + 0.5f) * (1.0f / 512.0f); }
+
+static inline float draw_jitter(const ctx_t *c)
 {
 	if(c->opt->rng_mode == SKRO_RNG_LIBC)
 	{
-		return (uint32_t) rand(); /* 31 bits */
+		return unit_from_31((uint32_t) rand());
 	}
-	uint32_t ctr[4] = {c->pixel, c->sample, node, slot}, out[4];
-	skro_philox4x32_10(ctr, c->key, out);
-	return out[comp] >> 1; /* 31 bits, like rand() */
+	uint32_t w[4];
+	philox_block(c, c->sample >> 2, 0, 0, w);
+	return unit_from_31(w[c->sample & 3] >> 1);
 }
-/* static_cast<float>(rand()) / static_cast<float>(RAND_MAX)   (RAND_MAX = 2^31-1, as float 2^31) */
-static inline float draw_unit(const ctx_t *c, uint32_t node, uint32_t slot, int comp)
+static inline void draw_gi(const ctx_t *c, uint32_t node, int child, float *r1, float *r2)
 {
-	return (float) (int32_t) draw_bits(c, node, slot, comp) / (float) 2147483647;
-}
-/* -1.0f + rand() / float(RAND_MAX / 2)   src/utils.h:219-221 */
-static inline float draw_pm1(const ctx_t *c, uint32_t node, uint32_t slot, int comp)
-{
-	return -1.0f + (float) (int32_t) draw_bits(c, node, slot, comp) / (float) (2147483647 / (1 + 1));
+	if(c->opt->rng_mode == SKRO_RNG_LIBC)
+	{
+		*r1 = unit_from_31((uint32_t) rand());
+		*r2 = unit_from_31((uint32_t) rand());
+		return;
+	}
+	uint32_t w[4];
+	philox_block(c, c->sample, node, c->slot_gi + ((uint32_t) child >> 1), w);
+	*r1 = unit_from_31(w[(child & 1) * 2] >> 1);
+	*r2 = unit_from_31(w[(child & 1) * 2 + 1] >> 1);
 }
 
 /* ----------------------------------------------------------- geometry ---- */
@@ -363,7 +381,7 @@ float skro_fresnel(const float *dir, const float *n, float ior)
 static vec3 shade(ctx_t *c, vec3 o, vec3 d, int depth, uint32_t node);
 
 /* src/blinn_phong.h:19-44 spherical_fog_shading + src/utils.h:216-224 */
-static vec3 spherical_fog_shading(ctx_t *c, uint32_t node, uint32_t slot, const float *light, const float *fog, const float *sphere, vec3 light_direction, vec3 p, vec3 norm)
+static vec3 spherical_fog_shading(ctx_t *c, uint32_t node, uint32_t slot, int call, const float *light, const float *fog, const float *sphere, vec3 light_direction, vec3 p, vec3 norm)
 {
 	vec3 lpos = ld3(light), lcol = ld3(light + 3);
 	float scattering = fog[0], absorption = fog[1], fog_radius = fog[5];
@@ -373,16 +391,22 @@ static vec3 spherical_fog_shading(ctx_t *c, uint32_t node, uint32_t slot, const 
 		distance = 2 * fog_radius;
 	}
 	float probability_no_interaction = (float) exp((double) (-1.0f * distance * (absorption + scattering)));
-	float random_num				 = draw_unit(c, node, slot, 0);
+	const int libc = c->opt->rng_mode == SKRO_RNG_LIBC;
+	uint32_t w[4]  = {0, 0, 0, 0};
+	if(!libc)
+	{
+		philox_block(c, c->sample, node, slot, w);
+	}
+	float random_num = unit_from_31(libc ? (uint32_t) rand() : w[call] >> 1);
 	if(random_num > probability_no_interaction)
 	{
 		distance		= length3(sub(lpos, p));
 		float intensity = 1.0f / (fabsf(distance) * fabsf(distance));
 		return muls(muls(mul(ld3(sphere + 7), lcol), intensity), fmaxf(0.0f, dot(norm, light_direction)));
 	}
-	float x = draw_pm1(c, node, slot, 1);
-	float y = draw_pm1(c, node, slot, 2);
-	float z = draw_pm1(c, node, slot, 3);
+	float x = libc ? pm1_from_31((uint32_t) rand()) : pm1_from_10(w[2 + call] & 1023u);
+	float y = libc ? pm1_from_31((uint32_t) rand()) : pm1_from_10((w[2 + call] >> 10) & 1023u);
+	float z = libc ? pm1_from_31((uint32_t) rand()) : pm1_from_10((w[2 + call] >> 20) & 1023u);
 	vec3 nd = v3(light_direction.x + x * scattering, light_direction.y + y * scattering, light_direction.z + z * scattering);
 	return muls(mul(ld3(fog + 2), lcol), fmaxf(0.0f, dot(norm, nd)));
 }
@@ -410,8 +434,8 @@ static vec3 diffuse_shading(ctx_t *c, uint32_t node, const float *sphere, vec3 p
 			{
 				for(int j = 0; j < s->nfogs; j++)
 				{
-					uint32_t slot = 1u + (uint32_t) ((0 * s->nplights + i) * s->nfogs + j);
-					colour		  = add(colour, spherical_fog_shading(c, node, slot, light, s->fogs + 9 * j, sphere, light_direction, p, norm));
+					uint32_t slot = 1u + (uint32_t) (i * s->nfogs + j);
+					colour		  = add(colour, spherical_fog_shading(c, node, slot, 0, light, s->fogs + 9 * j, sphere, light_direction, p, norm));
 				}
 			}
 			else
@@ -459,8 +483,8 @@ static vec3 specular_shading(ctx_t *c, uint32_t node, const float *sphere, vec3 
 			{
 				for(int j = 0; j < s->nfogs; j++)
 				{
-					uint32_t slot = 1u + (uint32_t) ((1 * s->nplights + i) * s->nfogs + j);
-					colour		  = add(colour, spherical_fog_shading(c, node, slot, light, s->fogs + 9 * j, sphere, light_direction, p, norm));
+					uint32_t slot = 1u + (uint32_t) (i * s->nfogs + j);
+					colour		  = add(colour, spherical_fog_shading(c, node, slot, 1, light, s->fogs + 9 * j, sphere, light_direction, p, norm));
 				}
 			}
 			else
@@ -535,9 +559,8 @@ static vec3 montecarlo_global_illumination(ctx_t *c, uint32_t node, vec3 p, vec3
 	float probability_dist = (float) (1 / (M_PI));
 	for(int i = 0; i < num_rays; i++)
 	{
-		uint32_t slot = c->slot_gi + (uint32_t) i;
-		float r1	  = draw_unit(c, node, slot, 0);
-		float r2	  = draw_unit(c, node, slot, 1);
+		float r1, r2;
+		draw_gi(c, node, i, &r1, &r2);
 		vec3 sample	  = uniform_sample_hemi(r1, r2);
 		vec3 world	  = v3(sample.x * perp_to_both.x + sample.y * n.x + sample.z * perp_to_normal.x,
 						   sample.x * perp_to_both.y + sample.y * n.y + sample.z * perp_to_both.y,
@@ -633,7 +656,7 @@ static void ctx_init(ctx_t *c, const skro_scene *scene, const skro_options *opt)
 	c->key[1]  = (uint32_t) (opt->seed >> 32);
 	uint32_t n = opt->monte_carlo ? (uint32_t) opt->num_path_traces : 0u;
 	c->node_base = n + 1u + (opt->fresnel ? 2u * (uint32_t) (scene->nplights + scene->ndlights) : 0u);
-	c->slot_gi	 = 1u + 2u * (uint32_t) scene->nplights * (uint32_t) scene->nfogs;
+	c->slot_gi	 = 1u + (uint32_t) scene->nplights * (uint32_t) scene->nfogs;
 }
 
 static void stats_add(skro_stats *a, const skro_stats *b)
@@ -687,7 +710,7 @@ double skro_render(const skro_scene *scene, const skro_options *opt, float *rgb3
 						for(int j = 0; j < opt->grid_size; j++)
 						{
 							c.sample	= (uint32_t) (i * opt->grid_size + j);
-							float r		= draw_unit(&c, 0, 0, 0);
+							float r		= draw_jitter(&c);
 							float u		= (2 * ((x + r) * inv_width) - 1) * angle * aspect_ratio;
 							float v		= (1 - 2 * ((y + r) * inv_height)) * angle;
 							vec3 ray_dir = add(add(cam_dir, muls(cam_right, u)), muls(cam_up, v)); /* never normalised, SURVEY F8 */

@@ -29,6 +29,8 @@ def lib_path() -> str:
 
 def _load(name: str) -> C.CDLL:
     path = os.path.join(_HERE, name)
+    if name == "libskr.so" and os.environ.get("SKR_LIB"):  # developer override: A/B-test a differently built library
+        path = os.environ["SKR_LIB"]
     if not os.path.exists(path):
         raise SkrError(f"{path} is missing: build it with `make -C host` (or __graft_entry__.build()). "
                        "There is no CPU fallback.")

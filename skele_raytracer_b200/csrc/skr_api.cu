@@ -36,7 +36,7 @@ struct Span
 };
 
 constexpr size_t SMEM_BLOB_LIMIT = 64 * 1024;
-constexpr unsigned DEFAULT_QUEUE_CAP = 4u << 20;
+constexpr unsigned DEFAULT_QUEUE_CAP = 32u << 20; // entries per level (36 B each): large enough that one chunk fills the GPU even at --gillum 64
 constexpr int DEFAULT_TILE = 32;
 } // namespace
 
@@ -167,12 +167,12 @@ int set_smem_attr(skr_ctx *ctx)
 	const int bytes = (int) ctx->smem_bytes;
 	if(bytes > 48 * 1024)
 	{
-		CK(cudaFuncSetAttribute(primary_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(primary_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(primary_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(primary_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(shade_expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(shade_expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(primary_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(primary_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(primary_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(primary_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(shade_expand_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(shade_expand_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	}
 	return SKR_OK;
 }
@@ -331,7 +331,7 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	fp.angle  = (float) tan(M_PI * 0.5 * o->fov / 180.);
 	fp.key	  = make_uint2((uint32_t) o->seed, (uint32_t) (o->seed >> 32));
 	fp.node_base = (uint32_t) fp.n_gi + 1u;
-	fp.slot_gi	 = 1u + 2u * (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
+	fp.slot_gi	 = 1u + (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
 	pl.tiles_local = (fp.tiles_total + world - 1) / world;
 	pl.npix_local  = pl.tiles_local * tile * tile;
 	pl.levels	   = (fp.gi && fp.max_depth > 0) ? fp.max_depth : 0;
@@ -397,7 +397,14 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 	if(!expand)
 	{
 		span_begin(ctx, CAT_BOUNCE);
-		shade_expand_kernel<STATS><<<(count + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, 0u, count, in, 0);
+		if(ctx->sv.blob_in_smem)
+		{
+			shade_expand_kernel<STATS, true><<<(count + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, 0u, count, in, 0);
+		}
+		else
+		{
+			shade_expand_kernel<STATS, false><<<(count + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, 0, ctx->stream>>>(ctx->sv, fp, in, 0u, count, in, 0);
+		}
 		span_end(ctx);
 		ctx->launches++;
 		CK(cudaGetLastError());
@@ -410,7 +417,14 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 		const unsigned m = count - s < chunk ? count - s : chunk;
 		CK(cudaMemsetAsync(out.count, 0, sizeof(unsigned), ctx->stream));
 		span_begin(ctx, CAT_BOUNCE);
-		shade_expand_kernel<STATS><<<(m + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, s, m, out, 1);
+		if(ctx->sv.blob_in_smem)
+		{
+			shade_expand_kernel<STATS, true><<<(m + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, s, m, out, 1);
+		}
+		else
+		{
+			shade_expand_kernel<STATS, false><<<(m + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, 0, ctx->stream>>>(ctx->sv, fp, in, s, m, out, 1);
+		}
 		span_end(ctx);
 		ctx->launches++;
 		ctx->chunks++;
@@ -439,6 +453,23 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	if(fp.gi)
 	{
 		unsigned cap = o->queue_capacity > 0 ? (unsigned) o->queue_capacity : DEFAULT_QUEUE_CAP;
+		if(o->queue_capacity <= 0)
+		{
+			// never take more than a quarter of the free memory for the queues
+			size_t free_b = 0, total_b = 0;
+			if(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && ctx->queue_cap != cap)
+			{
+				const size_t budget = free_b / 4 / (size_t) (pl.levels > 0 ? pl.levels : 1) / 36;
+				if(budget < cap)
+				{
+					cap = (unsigned) budget;
+				}
+			}
+			else if(ctx->queue_cap != 0 && ctx->n_levels_alloc >= pl.levels)
+			{
+				cap = ctx->queue_cap; // already allocated for an earlier frame
+			}
+		}
 		const unsigned need = (unsigned) (fp.n_gi > fp.spp ? fp.n_gi : fp.spp);
 		if(cap < need * SKR_BLOCK)
 		{
@@ -457,7 +488,14 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		span_begin(ctx, CAT_PRIMARY);
 		const unsigned blocks = (unsigned) ((pl.npix_local + SKR_BLOCK - 1) / SKR_BLOCK);
 		Queue none{};
-		primary_kernel<false, STATS><<<blocks, SKR_BLOCK, smem, st>>>(ctx->sv, fp, none, 0, pl.npix_local);
+		if(ctx->sv.blob_in_smem)
+		{
+			primary_kernel<false, STATS, true><<<blocks, SKR_BLOCK, smem, st>>>(ctx->sv, fp, none, 0, pl.npix_local);
+		}
+		else
+		{
+			primary_kernel<false, STATS, false><<<blocks, SKR_BLOCK, 0, st>>>(ctx->sv, fp, none, 0, pl.npix_local);
+		}
 		span_end(ctx);
 		ctx->launches++;
 		CK(cudaGetLastError());
@@ -470,7 +508,14 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		const long long n = pl.npix_local - lp0 < batch ? pl.npix_local - lp0 : batch;
 		CK(cudaMemsetAsync(q0.count, 0, sizeof(unsigned), st));
 		span_begin(ctx, CAT_PRIMARY);
-		primary_kernel<true, STATS><<<(unsigned) ((n + SKR_BLOCK - 1) / SKR_BLOCK), SKR_BLOCK, smem, st>>>(ctx->sv, fp, q0, lp0, n);
+		if(ctx->sv.blob_in_smem)
+		{
+			primary_kernel<true, STATS, true><<<(unsigned) ((n + SKR_BLOCK - 1) / SKR_BLOCK), SKR_BLOCK, smem, st>>>(ctx->sv, fp, q0, lp0, n);
+		}
+		else
+		{
+			primary_kernel<true, STATS, false><<<(unsigned) ((n + SKR_BLOCK - 1) / SKR_BLOCK), SKR_BLOCK, 0, st>>>(ctx->sv, fp, q0, lp0, n);
+		}
 		span_end(ctx);
 		ctx->launches++;
 		ctx->chunks++;
@@ -724,12 +769,13 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	}
 	ctx->have_scene = false;
 	const int S = sc->nspheres, T = sc->ntris, L = sc->nplights, D = sc->ndlights, F = sc->nfogs;
+	const int S4 = (S + 3) / 4 * 4;
 	SceneView &sv = ctx->sv;
 	memset(&sv, 0, sizeof sv);
-	sv.S = S, sv.T = T, sv.L = L, sv.D = D, sv.F = F;
+	sv.S = S, sv.S4 = S4, sv.T = T, sv.L = L, sv.D = D, sv.F = F;
 	int off		  = 0;
-	sv.off_geom	  = off, off += S;
-	sv.off_prim	  = off, off += S;
+	sv.off_geom	  = off, off += S4;
+	sv.off_prim	  = off, off += S4;
 	sv.off_amb	  = off, off += S;
 	sv.off_diff	  = off, off += S;
 	sv.off_spec	  = off, off += S;
@@ -752,12 +798,17 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		const V3 e			   = V3{cam.x - c.x, cam.y - c.y, cam.z - c.z};
 		const float ee		   = hdot(e, e);
 		const float cterm	   = ee - r * r;
-		blob[sv.off_geom + s]  = make_float4(c.x, c.y, c.z, r);
-		blob[sv.off_prim + s]  = make_float4(2 * e.x, 2 * e.y, 2 * e.z, cterm);
+		blob[sv.off_geom + s]  = make_float4(c.x, c.y, c.z, -(r * r));
+		blob[sv.off_prim + s]  = make_float4(e.x, e.y, e.z, cterm);
 		blob[sv.off_amb + s]   = make_float4(sc->ambient[0] * p[4], sc->ambient[1] * p[5], sc->ambient[2] * p[6], p[16]);
 		blob[sv.off_diff + s]  = make_float4(p[7], p[8], p[9], p[17]);
-		const bool has_spec	   = p[10] != 0.0f || p[11] != 0.0f || p[12] != 0.0f;
-		blob[sv.off_spec + s]  = make_float4(p[10], p[11], p[12], has_spec ? 1.0f : 0.0f);
+		blob[sv.off_spec + s]  = make_float4(p[10], p[11], p[12], r);
+	}
+	for(int s = S; s < S4; s++)
+	{
+		// padding spheres: e.e overflows to +inf, so h*h - a*cc is -inf (or NaN) and every `>= 0` test fails
+		blob[sv.off_geom + s] = make_float4(3.0e19f, 3.0e19f, 3.0e19f, 0.0f);
+		blob[sv.off_prim + s] = make_float4(0.0f, 0.0f, 0.0f, 3.0e38f);
 	}
 	for(int i = 0; i < L; i++)
 	{

@@ -12,11 +12,11 @@
 // ------------------------------------------------------------------------------------------------
 // Scene view.  All small per-scene arrays live in ONE float4 blob (built by skr_scene_upload) that each
 // CTA stages into shared memory; indices below are float4 offsets into it.
-//   geom [S]  (cx, cy, cz, r)
-//   prim [S]  (2*(cam-c).xyz, |cam-c|^2 - r^2)      the camera-origin constants of the quadratic
+//   geom [S4] (cx, cy, cz, -r*r)                    S4 = S rounded up to a multiple of 4; the padding spheres can
+//   prim [S4] ((cam-c).xyz, |cam-c|^2 - r^2)         never be hit, so the test loops run unguarded in groups of 4
 //   amb  [S]  (ambient_light (.) ka .xyz, phong power)
 //   diff [S]  (kd.xyz, ior)
-//   spec [S]  (ks.xyz, any(ks != 0))
+//   spec [S]  (ks.xyz, r)
 //   plpos[L]  (pos.xyz, 0)   plcol[L] (colour.xyz, 0)
 //   dldir[D]  (normalize(dir).xyz, 0)   dlcol[D] (colour.xyz, 0)
 //   foga [F]  (scattering, absorption, radius, 0)   fogalb[F] (albedo.xyz, 0)
@@ -25,7 +25,7 @@
 // ------------------------------------------------------------------------------------------------
 struct SceneView
 {
-	int S, T, L, D, F;
+	int S, S4, T, L, D, F;
 	int off_geom, off_prim, off_amb, off_diff, off_spec, off_plpos, off_plcol, off_dldir, off_dlcol, off_foga, off_fogalb, off_fogp;
 	int blob_f4;		 // blob size in float4
 	int blob_in_smem;	 // 1: kernels stage the blob in shared memory
@@ -43,11 +43,13 @@ struct Counters // per-thread, reduced at kernel exit when STATS
 SKR_DEV void zero(Counters &c) { c.ch = c.sh = c.st = c.stp = c.tt = c.nv = c.hits = c.le = 0; }
 
 // ------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. 2011).  Keying, identical to oracle/skr_oracle.c:
+// Philox4x32-10 (Salmon et al. 2011).  Keying, identical to oracle/skr_oracle.c.  One call yields 128 bits, so draws
+// the same thread needs together share a block:
 //   counter = (pixel, sample, node, slot), key = (seed_lo, seed_hi)
-//   slot 0                      : .x jitter r of the primary sample
-//   slot 1 + (call*L + i)*F + j : fog draws (xi, dx, dy, dz) for call (0 diffuse / 1 specular), light i, fog j
-//   slot 1 + 2*L*F + c          : (.x, .y) = (r1, r2) of GI child c
+//   jitter   : counter (pixel, sample >> 2, 0, 0), word sample & 3 -> r (31 bits): one call per 4 samples
+//   fog      : slot 1 + i*F + j, shared by the diffuse and the specular call: words 0/1 -> their xi (31 bits),
+//              words 2/3 -> their three scattering offsets, 10 bits each, offset = -1 + (k + 0.5) / 512
+//   GI child : slot 1 + L*F + (c >> 1): children 2m, 2m+1 share a block, (r1, r2) = words (0,1) / (2,3)
 // ------------------------------------------------------------------------------------------------
 SKR_DEV uint4 philox4x32_10(uint4 c, uint2 k)
 {
@@ -64,8 +66,8 @@ SKR_DEV uint4 philox4x32_10(uint4 c, uint2 k)
 }
 // float(rand()) / float(RAND_MAX) with a 31-bit draw: k * 2^-31 (RAND_MAX rounds to 2^31 as a float)
 SKR_DEV float rng_unit(uint32_t x) { return __fmul_rn(__int2float_rn((int) (x >> 1)), 4.6566128730773926e-10f); }
-// -1.0f + rand() / float(RAND_MAX / 2)    (src/utils.h:219-221)
-SKR_DEV float rng_pm1(uint32_t x) { return __fadd_rn(-1.0f, __fmul_rn(__int2float_rn((int) (x >> 1)), 9.3132257461547852e-10f)); }
+// -1.0f + rand() / float(RAND_MAX / 2) (src/utils.h:219-221) from a 10-bit draw: -1 + (k + 0.5) / 512
+SKR_DEV float rng_pm1_10(uint32_t k) { return fmaf(__uint2float_rn(k) + 0.5f, 1.0f / 512.0f, -1.0f); }
 
 struct RngCtx
 {
@@ -78,84 +80,116 @@ SKR_DEV uint4 rng_block(const RngCtx &r, uint32_t slot) { return philox4x32_10(m
 // Spheres
 // ------------------------------------------------------------------------------------------------
 
+// All sphere tests use the half-b form of the reference's quadratic (src/utils.h:87-121): with e = o - c,
+// h = d.e (= b/2), cc = e.e - r^2, a = d.d:   disc/4 = h^2 - a*cc,   t2 = (-h - sqrt(h^2 - a*cc)) / a.
+// Same roots, one multiply less per test; the winner's t is then recomputed with the reference's own expression.
+
 // Closest sphere along (o, d) with 1.0 < t < inf, strict minimum, first wins ties (src/raytrace.h:149-165).
-// PRIMARY: o is the camera position, use the precomputed (2e, c) constants.
+// PRIMARY: o is the camera position, e and cc come precomputed from the blob.
+// Branch-free selection on u = a*t2 = -h - sqrt(d4) (a > 0 is common to all spheres of a ray):
+//   t2 > 1        <=>  h < -a  and  d4 >= 0  and  cc + 2h > -a          (as in occluded())
+//   u < umin      <=>  m < 0  or  d4 > m*m,  m = -h - umin              (no sqrt)
+// so a square root is taken only when a sphere actually becomes the new closest (once or twice per ray), and lanes
+// whose rays graze different spheres do not diverge through sqrt/divide sequences.
 template <bool PRIMARY, bool STATS>
 SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt)
 {
 	const float a  = dot(d, d);
-	const float a4 = 4.0f * a;
-	const float a2 = 2.0f * a;
+	const float na = -a;
 	int best	   = -1;
-	tmin		   = CUDART_INF_F;
-	const int S	   = sv.S;
+	float umin	   = CUDART_INF_F;
+	const int S4   = sv.S4;
+	const float4 *__restrict__ G = B + (PRIMARY ? sv.off_prim : sv.off_geom);
 #pragma unroll 4
-	for(int s = 0; s < S; s++)
+	for(int s = 0; s < S4; s++)
 	{
-		float b, cc;
+		const float4 g = G[s];
+		float h, cc;
 		if(PRIMARY)
 		{
-			const float4 p = B[sv.off_prim + s];
-			b			   = dot(d, f3(p)); // = 2*dot(d, e): scaling by 2 is exact
-			cc			   = p.w;
+			h  = dot(d, f3(g));
+			cc = g.w;
 		}
 		else
 		{
-			const float4 g = B[sv.off_geom + s];
 			const float3 e = o - f3(g);
-			b			   = 2.0f * dot(d, e);
-			cc			   = dot(e, e) - g.w * g.w;
+			h			   = dot(d, e);
+			cc			   = fmaf(e.z, e.z, fmaf(e.y, e.y, fmaf(e.x, e.x, g.w)));
 		}
-		const float disc = b * b - a4 * cc;
+		const float d4	  = fmaf(h, h, na * cc);
+		const float w	  = fmaf(2.0f, h, cc);
+		const float m	  = -h - umin;
+		const bool cand	  = (h < na) & (d4 >= 0.0f) & (w > na);
+		const bool better = cand & ((m < 0.0f) | (d4 > m * m));
 		if(STATS)
 		{
-			cnt.st++;
+			cnt.st += s < sv.S;
+			cnt.stp += d4 >= 0.0f;
 		}
-		if(disc >= 0.0f)
+		if(better)
 		{
-			if(STATS)
-			{
-				cnt.stp++;
-			}
-			const float t2 = __fdiv_rn(-b - __fsqrt_rn(disc), a2); // the root smallest_root returns for a > 0
-			if(t2 > 1.0f && t2 < tmin)
-			{
-				tmin = t2;
-				best = s;
-			}
+			umin = -h - __fsqrt_rn(d4);
+			best = s;
 		}
 	}
+	tmin = best >= 0 ? __fdiv_rn(umin, a) : CUDART_INF_F;
 	return best;
 }
 
+// The reference's own expression for the winner's t (src/raytrace.h:197-201 -> src/utils.h:87-110), so that the hit
+// point is the reference's.  (Its sqrt/divide run in double and round to float; IEEE float ops here differ from
+// that by at most one ulp on rare inputs -- below every tolerance, cheaper than FP64 sequences.)
+SKR_DEV float sphere_t_ref(float3 o, float3 d, float3 c, float r, float t_fallback)
+{
+	const float3 e	 = sub_rn(o, c);
+	const float a	 = dot_rn(d, d);
+	const float b	 = __fmul_rn(2.0f, dot_rn(d, e));
+	const float cc	 = __fsub_rn(dot_rn(e, e), __fmul_rn(r, r));
+	const float disc = __fsub_rn(__fmul_rn(b, b), __fmul_rn(__fmul_rn(4.0f, a), cc));
+	if(!(disc >= 0.0f))
+	{
+		return t_fallback; // the two forms disagree about a grazing hit: keep the loop's value
+	}
+	return __fdiv_rn(__fsub_rn(-b, __fsqrt_rn(disc)), __fmul_rn(2.0f, a));
+}
+
 // shadow(): ANY sphere with 1.0 < t2 < inf along the normalised direction from p + 1e-6 occludes; no light-distance
-// bound, hits within 1.0 ignored (src/utils.h:42-58).  t2 > 1  <=>  q = -b - 2a > 0 and q*q > disc.
+// bound, hits within 1.0 ignored (src/utils.h:42-58).
+//   t2 > 1  <=>  disc >= 0  and  -h - a > 0  and  (h + a)^2 > h^2 - a*cc  <=>  ... and  cc + 2h + a > 0
+// (the last term is |o + d - c|^2 - r^2: the point at t = 1 lies outside the sphere) -- no sqrt, no divide.
 template <bool STATS>
 SKR_DEV bool occluded(const float4 *__restrict__ B, const SceneView &sv, float3 p, float3 dir, Counters &cnt)
 {
 	const float3 o = adds_rn(p, 0.000001f);
 	const float a  = dot(dir, dir);
-	const float a4 = 4.0f * a;
-	const float a2 = 2.0f * a;
-	const int S	   = sv.S;
+	const float na = -a;
+	const int S4   = sv.S4;
+	const float4 *__restrict__ G = B + sv.off_geom;
 	if(STATS)
 	{
 		cnt.sh++;
 	}
-	for(int s = 0; s < S; s++)
+	for(int s = 0; s < S4; s += 4)
 	{
-		const float4 g	 = B[sv.off_geom + s];
-		const float3 e	 = o - f3(g);
-		const float b	 = 2.0f * dot(dir, e);
-		const float cc	 = dot(e, e) - g.w * g.w;
-		const float disc = b * b - a4 * cc;
-		const float q	 = -b - a2;
-		if(STATS)
+		bool any = false;
+#pragma unroll
+		for(int k = 0; k < 4; k++)
 		{
-			cnt.st++;
-			cnt.stp += disc >= 0.0f;
+			const float4 g = G[s + k];
+			const float3 e = o - f3(g);
+			const float h  = dot(dir, e);
+			const float cc = fmaf(e.z, e.z, fmaf(e.y, e.y, fmaf(e.x, e.x, g.w)));
+			const float d4 = fmaf(h, h, na * cc);
+			const float w  = fmaf(2.0f, h, cc);
+			const bool occ = (h < na) & (d4 >= 0.0f) & (w > na);
+			if(STATS && !any) // count like the reference's loop: up to and including the first occluder
+			{
+				cnt.st += s + k < sv.S;
+				cnt.stp += d4 >= 0.0f;
+			}
+			any |= occ;
 		}
-		if(disc >= 0.0f && q > 0.0f && q * q > disc)
+		if(any)
 		{
 			return true;
 		}
@@ -205,19 +239,21 @@ SKR_DEV float pow_fast(float x, float p) // x >= 0
 	return p == 0.0f ? 1.0f : __powf(x, p);
 }
 
-// bp::spherical_fog_shading (src/blinn_phong.h:19-44) + scattering_phase_function (src/utils.h:216-224)
-SKR_DEV float3 fog_term(const float4 *__restrict__ B, const SceneView &sv, const RngCtx &rng, int call, int i, int j, int sidx, float3 kd, float3 lcol,
+// bp::spherical_fog_shading (src/blinn_phong.h:19-44) + scattering_phase_function (src/utils.h:216-224).
+// `r` is the Philox block of this (light, fog); call 0 = from diffuse_shading, 1 = from specular_shading.
+SKR_DEV float3 fog_term(const float4 *__restrict__ B, const SceneView &sv, const uint4 &r, int call, int i, int j, int sidx, float3 kd, float3 lcol,
 						float3 lhat, float inv_d2, float3 n)
 {
 	const float *fogp = reinterpret_cast<const float *>(B + sv.off_fogp);
 	const float p_no  = fogp[(sidx * sv.L + i) * sv.F + j];
-	const uint4 r	  = rng_block(rng, 1u + (uint32_t) ((call * sv.L + i) * sv.F + j));
-	if(rng_unit(r.x) > p_no)
+	if(rng_unit(call ? r.y : r.x) > p_no)
 	{
 		return kd * lcol * (inv_d2 * fmaxf(0.0f, dot(n, lhat)));
 	}
-	const float4 fa = B[sv.off_foga + j];
-	const float3 nd = f3(lhat.x + rng_pm1(r.y) * fa.x, lhat.y + rng_pm1(r.z) * fa.x, lhat.z + rng_pm1(r.w) * fa.x);
+	const uint32_t w = call ? r.w : r.z;
+	const float4 fa	 = B[sv.off_foga + j];
+	const float3 nd	 = f3(fmaf(rng_pm1_10(w & 1023u), fa.x, lhat.x), fmaf(rng_pm1_10((w >> 10) & 1023u), fa.x, lhat.y),
+						  fmaf(rng_pm1_10((w >> 20) & 1023u), fa.x, lhat.z));
 	return f3(B[sv.off_fogalb + j]) * lcol * fmaxf(0.0f, dot(n, nd));
 }
 
@@ -230,15 +266,15 @@ SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, b
 {
 	const float4 am = B[sv.off_amb + sidx];
 	const float3 kd = f3(B[sv.off_diff + sidx]);
-	const float4 sp = B[sv.off_spec + sidx];
-	const float3 ks = f3(sp);
+	const float3 ks		= f3(B[sv.off_spec + sidx]);
+	const bool has_spec = ks.x != 0.0f || ks.y != 0.0f || ks.z != 0.0f;
 	float3 col		= f3(am);
 	const float3 view = normalize_fast(sv.cam_pos - p);
 	for(int i = 0; i < sv.L; i++)
 	{
-		const float3 lv	 = f3(B[sv.off_plpos + i]) - p;
-		const float d2	 = dot(lv, lv);
-		const float3 lhat = normalize_rn(sub_rn(f3(B[sv.off_plpos + i]), p)); // also the shadow-ray direction
+		const float3 lv	  = f3(B[sv.off_plpos + i]) - p;
+		const float d2	  = dot(lv, lv);
+		const float3 lhat = lv * rsqrtf(d2); // also the shadow-ray direction
 		if(use_shadows && occluded<STATS>(B, sv, p, lhat, cnt))
 		{
 			continue;
@@ -253,14 +289,15 @@ SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, b
 		{
 			for(int j = 0; j < sv.F; j++)
 			{
-				col += fog_term(B, sv, rng, 0, i, j, sidx, kd, lcol, lhat, inv_d2, n);
-				col += fog_term(B, sv, rng, 1, i, j, sidx, kd, lcol, lhat, inv_d2, n);
+				const uint4 r = rng_block(rng, 1u + (uint32_t) (i * sv.F + j));
+				col += fog_term(B, sv, r, 0, i, j, sidx, kd, lcol, lhat, inv_d2, n);
+				col += fog_term(B, sv, r, 1, i, j, sidx, kd, lcol, lhat, inv_d2, n);
 			}
 		}
 		else
 		{
 			col += kd * lcol * (inv_d2 * fmaxf(0.0f, dot(n, lhat)));
-			if(sp.w != 0.0f)
+			if(has_spec)
 			{
 				const float3 h = normalize_fast(view + lhat);
 				col += ks * lcol * (inv_d2 * pow_fast(fmaxf(0.0f, dot(n, h)), am.w));
@@ -276,7 +313,7 @@ SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, b
 		}
 		const float3 lcol = f3(B[sv.off_dlcol + i]);
 		col += kd * lcol * fmaxf(0.0f, dot(n, lhat));
-		if(sp.w != 0.0f)
+		if(has_spec)
 		{
 			const float3 h = normalize_fast(view + lhat);
 			col += ks * lcol * pow_fast(fmaxf(0.0f, dot(n, h)), am.w);

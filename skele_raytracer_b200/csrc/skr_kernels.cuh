@@ -18,6 +18,9 @@
 #include "skr_device.cuh"
 
 #define SKR_BLOCK 256
+#ifndef SKR_MIN_BLOCKS
+#define SKR_MIN_BLOCKS 4 // <= 64 registers: 32 resident warps per SM
+#endif
 #define SKR_FIX_SCALE 4294967296.0f
 
 struct Queue
@@ -124,10 +127,12 @@ SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, 
 	}
 }
 
-// Stage the scene blob into shared memory (all threads of the CTA).  Returns the pointer the routines should read.
+// Stage the scene blob into shared memory (all threads of the CTA).  SMEM is a template parameter so that the test
+// loops compile to LDS (not generic loads) in the common case; scenes too big for shared memory read the blob in place.
+template <bool SMEM>
 SKR_DEV const float4 *stage_scene(const SceneView &sv, float4 *smem)
 {
-	if(!sv.blob_in_smem)
+	if(!SMEM)
 	{
 		return sv.blob;
 	}
@@ -198,11 +203,11 @@ SKR_DEV void queue_push(const Queue &q, bool want, float3 p, uint32_t pixel, flo
 // ------------------------------------------------------------------------------------------------
 // primary_kernel: local pixels [lp0, lp0 + npix)
 // ------------------------------------------------------------------------------------------------
-template <bool GI, bool STATS>
-__global__ void __launch_bounds__(SKR_BLOCK) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix)
+template <bool GI, bool STATS, bool SMEM>
+__global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix)
 {
 	extern __shared__ float4 smem[];
-	const float4 *B = stage_scene(sv, smem);
+	const float4 *B = stage_scene<SMEM>(sv, smem);
 	Counters cnt;
 	zero(cnt);
 
@@ -218,14 +223,21 @@ __global__ void __launch_bounds__(SKR_BLOCK) primary_kernel(const SceneView sv, 
 	rng.key	  = fp.key;
 
 	const int nsamples = fp.max_depth > 0 ? fp.spp : 0; // depth <= 0: shade() returns black (src/raytrace.h:142-145)
+	uint4 jit = make_uint4(0u, 0u, 0u, 0u);
 	for(int s = 0; s < nsamples; s++)
 	{
 		rng.sample = (uint32_t) s;
 		float u, v;
 		if(fp.grid > 0)
 		{
-			// src/main.cpp:52-54: ONE draw for both axes, all-float arithmetic
-			const float r = rng_unit(rng_block(rng, 0u).x);
+			// src/main.cpp:52-54: ONE draw for both axes, all-float arithmetic.  Four consecutive samples
+			// share one Philox block.
+			if((s & 3) == 0)
+			{
+				jit = philox4x32_10(make_uint4(rng.pixel, (uint32_t) s >> 2, 0u, 0u), rng.key);
+			}
+			const uint32_t jw = (s & 3) == 0 ? jit.x : (s & 3) == 1 ? jit.y : (s & 3) == 2 ? jit.z : jit.w;
+			const float r	  = rng_unit(jw);
 			u = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn((float) p.x, r), fp.inv_w)), 1.0f), fp.angle), fp.aspect);
 			v = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(2.0f, __fmul_rn(__fadd_rn((float) p.y, r), fp.inv_h))), fp.angle);
 		}
@@ -253,10 +265,12 @@ __global__ void __launch_bounds__(SKR_BLOCK) primary_kernel(const SceneView sv, 
 		}
 		else if(h >= 0)
 		{
-			hp = add_rn(o, muls_rn(d, t)); // src/raytrace.h:204
+			const float3 c = f3(B[sv.off_geom + h]);
+			t			   = sphere_t_ref(o, d, c, B[sv.off_spec + h].w, t);
+			hp			   = add_rn(o, muls_rn(d, t)); // src/raytrace.h:204
 			if(!GI)
 			{
-				const float3 n = normalize_rn(sub_rn(hp, f3(B[sv.off_geom + h])));
+				const float3 n = normalize_rn(sub_rn(hp, c));
 				sum += direct_light<STATS>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt);
 			}
 		}
@@ -290,12 +304,12 @@ __global__ void __launch_bounds__(SKR_BLOCK) primary_kernel(const SceneView sv, 
 // ------------------------------------------------------------------------------------------------
 // shade_expand_kernel: queue entries [start, start + count) of `in`
 // ------------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(SKR_BLOCK) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
+template <bool STATS, bool SMEM>
+__global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
 																  const Queue out, int expand)
 {
 	extern __shared__ float4 smem[];
-	const float4 *B = stage_scene(sv, smem);
+	const float4 *B = stage_scene<SMEM>(sv, smem);
 	Counters cnt;
 	zero(cnt);
 
@@ -330,10 +344,14 @@ __global__ void __launch_bounds__(SKR_BLOCK) shade_expand_kernel(const SceneView
 		basis_from_normal(n, nt, nb);
 		const float3 tk = thr * kd * (6.28318530717958648f / (float) fp.n_gi);
 		const float3 o	= adds_rn(hp, 0.00001f);
+		uint4 r = make_uint4(0u, 0u, 0u, 0u);
 		for(int c = 0; c < fp.n_gi; c++)
 		{
-			const uint4 r  = rng_block(rng, fp.slot_gi + (uint32_t) c);
-			const float r1 = rng_unit(r.x), r2 = rng_unit(r.y);
+			if((c & 1) == 0)
+			{
+				r = rng_block(rng, fp.slot_gi + ((uint32_t) c >> 1)); // children 2m and 2m+1 share a block
+			}
+			const float r1 = rng_unit((c & 1) ? r.z : r.x), r2 = rng_unit((c & 1) ? r.w : r.y);
 			const float3 d = gi_child_dir(r1, r2, n, nt, nb);
 			float t		   = 0.0f;
 			int h		   = -3;
@@ -345,6 +363,10 @@ __global__ void __launch_bounds__(SKR_BLOCK) shade_expand_kernel(const SceneView
 			if(h == -2)
 			{
 				contrib += w * sv.background;
+			}
+			if(h >= 0)
+			{
+				t = sphere_t_ref(o, d, f3(B[sv.off_geom + h]), B[sv.off_spec + h].w, t);
 			}
 			const float3 cp = add_rn(o, muls_rn(d, t));
 			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, fp.err);
