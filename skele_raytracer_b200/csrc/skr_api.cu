@@ -774,8 +774,9 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	memset(&sv, 0, sizeof sv);
 	sv.S = S, sv.S4 = S4, sv.T = T, sv.L = L, sv.D = D, sv.F = F;
 	int off		  = 0;
-	sv.off_geom	  = off, off += S4;
-	sv.off_prim	  = off, off += S4;
+	sv.off_geom	  = off, off += S;
+	sv.off_pgeom  = off, off += S4; // S4/2 pairs x 2 float4
+	sv.off_pprim  = off, off += S4;
 	sv.off_amb	  = off, off += S;
 	sv.off_diff	  = off, off += S;
 	sv.off_spec	  = off, off += S;
@@ -799,7 +800,14 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		const float ee		   = hdot(e, e);
 		const float cterm	   = ee - r * r;
 		blob[sv.off_geom + s]  = make_float4(c.x, c.y, c.z, -(r * r));
-		blob[sv.off_prim + s]  = make_float4(e.x, e.y, e.z, cterm);
+		{
+			// pair layout: element (s & 1) of pair s >> 1
+			float *g = reinterpret_cast<float *>(&blob[sv.off_pgeom + 2 * (s >> 1)]);
+			float *q = reinterpret_cast<float *>(&blob[sv.off_pprim + 2 * (s >> 1)]);
+			const int k = s & 1;
+			g[0 + k] = -c.x, g[2 + k] = -c.y, g[4 + k] = -c.z, g[6 + k] = -(r * r);
+			q[0 + k] = e.x, q[2 + k] = e.y, q[4 + k] = e.z, q[6 + k] = cterm;
+		}
 		blob[sv.off_amb + s]   = make_float4(sc->ambient[0] * p[4], sc->ambient[1] * p[5], sc->ambient[2] * p[6], p[16]);
 		blob[sv.off_diff + s]  = make_float4(p[7], p[8], p[9], p[17]);
 		blob[sv.off_spec + s]  = make_float4(p[10], p[11], p[12], r);
@@ -807,8 +815,11 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	for(int s = S; s < S4; s++)
 	{
 		// padding spheres: e.e overflows to +inf, so h*h - a*cc is -inf (or NaN) and every `>= 0` test fails
-		blob[sv.off_geom + s] = make_float4(3.0e19f, 3.0e19f, 3.0e19f, 0.0f);
-		blob[sv.off_prim + s] = make_float4(0.0f, 0.0f, 0.0f, 3.0e38f);
+		float *g = reinterpret_cast<float *>(&blob[sv.off_pgeom + 2 * (s >> 1)]);
+		float *q = reinterpret_cast<float *>(&blob[sv.off_pprim + 2 * (s >> 1)]);
+		const int k = s & 1;
+		g[0 + k] = -3.0e19f, g[2 + k] = -3.0e19f, g[4 + k] = -3.0e19f, g[6 + k] = 0.0f;
+		q[0 + k] = 0.0f, q[2 + k] = 0.0f, q[4 + k] = 0.0f, q[6 + k] = 3.0e38f;
 	}
 	for(int i = 0; i < L; i++)
 	{

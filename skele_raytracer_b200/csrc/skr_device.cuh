@@ -12,8 +12,11 @@
 // ------------------------------------------------------------------------------------------------
 // Scene view.  All small per-scene arrays live in ONE float4 blob (built by skr_scene_upload) that each
 // CTA stages into shared memory; indices below are float4 offsets into it.
-//   geom [S4] (cx, cy, cz, -r*r)                    S4 = S rounded up to a multiple of 4; the padding spheres can
-//   prim [S4] ((cam-c).xyz, |cam-c|^2 - r^2)         never be hit, so the test loops run unguarded in groups of 4
+//   geom [S]  (cx, cy, cz, -r*r)
+//   pgeom[S4/2][2]  spheres in PAIRS for the packed FP32x2 test loops: (-cx0,-cx1,-cy0,-cy1), (-cz0,-cz1,-r0^2,-r1^2)
+//   pprim[S4/2][2]  same for camera rays: (ex0,ex1,ey0,ey1), (ez0,ez1,cc0,cc1) with e = cam - c, cc = e.e - r^2
+//                   S4 = S rounded up to a multiple of 4; the padding spheres can never be hit, so the loops run
+//                   unguarded, two pairs per iteration
 //   amb  [S]  (ambient_light (.) ka .xyz, phong power)
 //   diff [S]  (kd.xyz, ior)
 //   spec [S]  (ks.xyz, r)
@@ -26,7 +29,7 @@
 struct SceneView
 {
 	int S, S4, T, L, D, F;
-	int off_geom, off_prim, off_amb, off_diff, off_spec, off_plpos, off_plcol, off_dldir, off_dlcol, off_foga, off_fogalb, off_fogp;
+	int off_geom, off_pgeom, off_pprim, off_amb, off_diff, off_spec, off_plpos, off_plcol, off_dldir, off_dlcol, off_foga, off_fogalb, off_fogp;
 	int blob_f4;		 // blob size in float4
 	int blob_in_smem;	 // 1: kernels stage the blob in shared memory
 	const float4 *blob;	 // device
@@ -86,11 +89,10 @@ SKR_DEV uint4 rng_block(const RngCtx &r, uint32_t slot) { return philox4x32_10(m
 
 // Closest sphere along (o, d) with 1.0 < t < inf, strict minimum, first wins ties (src/raytrace.h:149-165).
 // PRIMARY: o is the camera position, e and cc come precomputed from the blob.
-// Branch-free selection on u = a*t2 = -h - sqrt(d4) (a > 0 is common to all spheres of a ray):
+// Two spheres per step in packed FP32x2.  Selection on u = a*t2 = -h - sqrt(d4) (a > 0 is common to a ray's spheres):
 //   t2 > 1        <=>  h < -a  and  d4 >= 0  and  cc + 2h > -a          (as in occluded())
 //   u < umin      <=>  m < 0  or  d4 > m*m,  m = -h - umin              (no sqrt)
-// so a square root is taken only when a sphere actually becomes the new closest (once or twice per ray), and lanes
-// whose rays graze different spheres do not diverge through sqrt/divide sequences.
+// so a square root is taken only when a sphere actually becomes the new closest (once or twice per ray).
 template <bool PRIMARY, bool STATS>
 SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt)
 {
@@ -98,38 +100,49 @@ SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, fl
 	const float na = -a;
 	int best	   = -1;
 	float umin	   = CUDART_INF_F;
-	const int S4   = sv.S4;
-	const float4 *__restrict__ G = B + (PRIMARY ? sv.off_prim : sv.off_geom);
-#pragma unroll 4
-	for(int s = 0; s < S4; s++)
+	const int NP   = sv.S4 >> 1;
+	const float4 *__restrict__ G = B + (PRIMARY ? sv.off_pprim : sv.off_pgeom);
+	const float2 dx = splat2(d.x), dy = splat2(d.y), dz = splat2(d.z), na2 = splat2(na);
+	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
+#pragma unroll 2
+	for(int p = 0; p < NP; p++)
 	{
-		const float4 g = G[s];
-		float h, cc;
+		const float4 g0 = G[2 * p], g1 = G[2 * p + 1];
+		float2 h, cc;
 		if(PRIMARY)
 		{
-			h  = dot(d, f3(g));
-			cc = g.w;
+			h  = fma2(dz, f2(g1.x, g1.y), fma2(dy, f2(g0.z, g0.w), mul2(dx, f2(g0.x, g0.y))));
+			cc = f2(g1.z, g1.w);
 		}
 		else
 		{
-			const float3 e = o - f3(g);
-			h			   = dot(d, e);
-			cc			   = fmaf(e.z, e.z, fmaf(e.y, e.y, fmaf(e.x, e.x, g.w)));
+			const float2 ex = add2(ox, f2(g0.x, g0.y)), ey = add2(oy, f2(g0.z, g0.w)), ez = add2(oz, f2(g1.x, g1.y));
+			h  = fma2(dz, ez, fma2(dy, ey, mul2(dx, ex)));
+			cc = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, f2(g1.z, g1.w))));
 		}
-		const float d4	  = fmaf(h, h, na * cc);
-		const float w	  = fmaf(2.0f, h, cc);
-		const float m	  = -h - umin;
-		const bool cand	  = (h < na) & (d4 >= 0.0f) & (w > na);
-		const bool better = cand & ((m < 0.0f) | (d4 > m * m));
+		const float2 d4 = fma2(h, h, mul2(na2, cc));
 		if(STATS)
 		{
-			cnt.st += s < sv.S;
-			cnt.stp += d4 >= 0.0f;
+			cnt.st += (2 * p < sv.S) + (2 * p + 1 < sv.S);
+			cnt.stp += (d4.x >= 0.0f) + (d4.y >= 0.0f);
 		}
-		if(better)
+		if(d4.x >= 0.0f)
 		{
-			umin = -h - __fsqrt_rn(d4);
-			best = s;
+			const float w = fmaf(2.0f, h.x, cc.x), m = -h.x - umin;
+			if((h.x < na) & (w > na) & ((m < 0.0f) | (d4.x > m * m)))
+			{
+				umin = -h.x - __fsqrt_rn(d4.x);
+				best = 2 * p;
+			}
+		}
+		if(d4.y >= 0.0f)
+		{
+			const float w = fmaf(2.0f, h.y, cc.y), m = -h.y - umin;
+			if((h.y < na) & (w > na) & ((m < 0.0f) | (d4.y > m * m)))
+			{
+				umin = -h.y - __fsqrt_rn(d4.y);
+				best = 2 * p + 1;
+			}
 		}
 	}
 	tmin = best >= 0 ? __fdiv_rn(umin, a) : CUDART_INF_F;
@@ -163,31 +176,35 @@ SKR_DEV bool occluded(const float4 *__restrict__ B, const SceneView &sv, float3 
 	const float3 o = adds_rn(p, 0.000001f);
 	const float a  = dot(dir, dir);
 	const float na = -a;
-	const int S4   = sv.S4;
-	const float4 *__restrict__ G = B + sv.off_geom;
+	const int NP   = sv.S4 >> 1;
+	const float4 *__restrict__ G = B + sv.off_pgeom;
+	const float2 dx = splat2(dir.x), dy = splat2(dir.y), dz = splat2(dir.z), na2 = splat2(na), two = splat2(2.0f);
+	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
 	if(STATS)
 	{
 		cnt.sh++;
 	}
-	for(int s = 0; s < S4; s += 4)
+	for(int p2 = 0; p2 < NP; p2 += 2) // two pairs = four spheres per iteration, one exit test
 	{
 		bool any = false;
 #pragma unroll
-		for(int k = 0; k < 4; k++)
+		for(int k = 0; k < 2; k++)
 		{
-			const float4 g = G[s + k];
-			const float3 e = o - f3(g);
-			const float h  = dot(dir, e);
-			const float cc = fmaf(e.z, e.z, fmaf(e.y, e.y, fmaf(e.x, e.x, g.w)));
-			const float d4 = fmaf(h, h, na * cc);
-			const float w  = fmaf(2.0f, h, cc);
-			const bool occ = (h < na) & (d4 >= 0.0f) & (w > na);
+			const int pp	= p2 + k;
+			const float4 g0 = G[2 * pp], g1 = G[2 * pp + 1];
+			const float2 ex = add2(ox, f2(g0.x, g0.y)), ey = add2(oy, f2(g0.z, g0.w)), ez = add2(oz, f2(g1.x, g1.y));
+			const float2 h	= fma2(dz, ez, fma2(dy, ey, mul2(dx, ex)));
+			const float2 cc = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, f2(g1.z, g1.w))));
+			const float2 d4 = fma2(h, h, mul2(na2, cc));
+			const float2 w	= fma2(two, h, cc);
+			const bool occ0 = (h.x < na) & (d4.x >= 0.0f) & (w.x > na);
+			const bool occ1 = (h.y < na) & (d4.y >= 0.0f) & (w.y > na);
 			if(STATS && !any) // count like the reference's loop: up to and including the first occluder
 			{
-				cnt.st += s + k < sv.S;
-				cnt.stp += d4 >= 0.0f;
+				cnt.st += (2 * pp < sv.S) + ((2 * pp + 1 < sv.S) & !occ0);
+				cnt.stp += (d4.x >= 0.0f) + ((d4.y >= 0.0f) & !occ0);
 			}
-			any |= occ;
+			any |= occ0 | occ1;
 		}
 		if(any)
 		{

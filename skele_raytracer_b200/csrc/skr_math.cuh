@@ -55,5 +55,14 @@ SKR_DEV float3 normalize_rn(float3 v)
 // colour-path normalize: rsqrt approximation (rel. error ~2^-22), fine for shading terms
 SKR_DEV float3 normalize_fast(float3 v) { return v * rsqrtf(dot(v, v)); }
 
+// ---- packed FP32x2 (Blackwell FFMA2/FADD2/FMUL2): two lanes per issue slot.  Measured on B200
+// (scripts/micro/fma2_peak.cu): same FP32 peak as FFMA (74 vs 72 TFLOP/s) but half the issue slots, so an
+// issue-bound mix of FP and integer/control instructions runs ~1.45x faster.
+SKR_DEV float2 f2(float a, float b) { return make_float2(a, b); }
+SKR_DEV float2 splat2(float a) { return make_float2(a, a); }
+SKR_DEV float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+SKR_DEV float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+SKR_DEV float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 SKR_DEV float u2f(uint32_t u) { return __uint_as_float(u); }
 SKR_DEV uint32_t f2u(float f) { return __float_as_uint(f); }
