@@ -162,17 +162,101 @@ void span_end(skr_ctx *ctx)
 	ctx->spans_used++;
 }
 
+// ---- kernel dispatch over the template flags -----------------------------------------------------
+// SMEM variants exist for every (TRIS, FOG); the global-memory fallback (scene blob > 64 KB) only as the general one.
+template <bool GI, bool STATS>
+void launch_primary(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, const Queue &q, long long lp0, long long n)
+{
+	const SceneView &sv = ctx->sv;
+	cudaStream_t st		= ctx->stream;
+	const size_t sm		= ctx->smem_bytes;
+	if(!sv.blob_in_smem)
+	{
+		primary_kernel<GI, STATS, false, true, true><<<blocks, SKR_BLOCK, 0, st>>>(sv, fp, q, lp0, n);
+		return;
+	}
+	const bool tris = sv.T > 0, fog = sv.F > 0;
+	if(tris && fog)
+	{
+		primary_kernel<GI, STATS, true, true, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n);
+	}
+	else if(tris)
+	{
+		primary_kernel<GI, STATS, true, true, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n);
+	}
+	else if(fog)
+	{
+		primary_kernel<GI, STATS, true, false, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n);
+	}
+	else
+	{
+		primary_kernel<GI, STATS, true, false, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n);
+	}
+}
+
+template <bool STATS>
+void launch_shade_expand(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, const Queue &in, unsigned start, unsigned count, const Queue &out,
+						 int expand)
+{
+	const SceneView &sv = ctx->sv;
+	cudaStream_t st		= ctx->stream;
+	const size_t sm		= ctx->smem_bytes;
+	if(!sv.blob_in_smem)
+	{
+		shade_expand_kernel<STATS, false, true, true><<<blocks, SKR_BLOCK, 0, st>>>(sv, fp, in, start, count, out, expand);
+		return;
+	}
+	const bool tris = sv.T > 0, fog = sv.F > 0;
+	if(tris && fog)
+	{
+		shade_expand_kernel<STATS, true, true, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+	}
+	else if(tris)
+	{
+		shade_expand_kernel<STATS, true, true, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+	}
+	else if(fog)
+	{
+		shade_expand_kernel<STATS, true, false, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+	}
+	else
+	{
+		shade_expand_kernel<STATS, true, false, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+	}
+}
+
+template <bool GI, bool STATS, bool TRIS, bool FOG>
+cudaError_t smem_attr_one(int bytes)
+{
+	cudaError_t e = cudaFuncSetAttribute(primary_kernel<GI, STATS, true, TRIS, FOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if(e == cudaSuccess && GI)
+	{
+		e = cudaFuncSetAttribute(shade_expand_kernel<STATS, true, TRIS, FOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	}
+	return e;
+}
+
 int set_smem_attr(skr_ctx *ctx)
 {
 	const int bytes = (int) ctx->smem_bytes;
 	if(bytes > 48 * 1024)
 	{
-		CK(cudaFuncSetAttribute(primary_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(primary_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(primary_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(primary_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(shade_expand_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(shade_expand_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK((smem_attr_one<false, false, false, false>(bytes)));
+		CK((smem_attr_one<false, false, false, true>(bytes)));
+		CK((smem_attr_one<false, false, true, false>(bytes)));
+		CK((smem_attr_one<false, false, true, true>(bytes)));
+		CK((smem_attr_one<false, true, false, false>(bytes)));
+		CK((smem_attr_one<false, true, false, true>(bytes)));
+		CK((smem_attr_one<false, true, true, false>(bytes)));
+		CK((smem_attr_one<false, true, true, true>(bytes)));
+		CK((smem_attr_one<true, false, false, false>(bytes)));
+		CK((smem_attr_one<true, false, false, true>(bytes)));
+		CK((smem_attr_one<true, false, true, false>(bytes)));
+		CK((smem_attr_one<true, false, true, true>(bytes)));
+		CK((smem_attr_one<true, true, false, false>(bytes)));
+		CK((smem_attr_one<true, true, false, true>(bytes)));
+		CK((smem_attr_one<true, true, true, false>(bytes)));
+		CK((smem_attr_one<true, true, true, true>(bytes)));
 	}
 	return SKR_OK;
 }
@@ -397,14 +481,7 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 	if(!expand)
 	{
 		span_begin(ctx, CAT_BOUNCE);
-		if(ctx->sv.blob_in_smem)
-		{
-			shade_expand_kernel<STATS, true><<<(count + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, 0u, count, in, 0);
-		}
-		else
-		{
-			shade_expand_kernel<STATS, false><<<(count + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, 0, ctx->stream>>>(ctx->sv, fp, in, 0u, count, in, 0);
-		}
+		launch_shade_expand<STATS>(ctx, (count + SKR_BLOCK - 1) / SKR_BLOCK, fp, in, 0u, count, in, 0);
 		span_end(ctx);
 		ctx->launches++;
 		CK(cudaGetLastError());
@@ -417,14 +494,7 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 		const unsigned m = count - s < chunk ? count - s : chunk;
 		CK(cudaMemsetAsync(out.count, 0, sizeof(unsigned), ctx->stream));
 		span_begin(ctx, CAT_BOUNCE);
-		if(ctx->sv.blob_in_smem)
-		{
-			shade_expand_kernel<STATS, true><<<(m + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, s, m, out, 1);
-		}
-		else
-		{
-			shade_expand_kernel<STATS, false><<<(m + SKR_BLOCK - 1) / SKR_BLOCK, SKR_BLOCK, 0, ctx->stream>>>(ctx->sv, fp, in, s, m, out, 1);
-		}
+		launch_shade_expand<STATS>(ctx, (m + SKR_BLOCK - 1) / SKR_BLOCK, fp, in, s, m, out, 1);
 		span_end(ctx);
 		ctx->launches++;
 		ctx->chunks++;
@@ -488,14 +558,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		span_begin(ctx, CAT_PRIMARY);
 		const unsigned blocks = (unsigned) ((pl.npix_local + SKR_BLOCK - 1) / SKR_BLOCK);
 		Queue none{};
-		if(ctx->sv.blob_in_smem)
-		{
-			primary_kernel<false, STATS, true><<<blocks, SKR_BLOCK, smem, st>>>(ctx->sv, fp, none, 0, pl.npix_local);
-		}
-		else
-		{
-			primary_kernel<false, STATS, false><<<blocks, SKR_BLOCK, 0, st>>>(ctx->sv, fp, none, 0, pl.npix_local);
-		}
+		launch_primary<false, STATS>(ctx, blocks, fp, none, 0, pl.npix_local);
 		span_end(ctx);
 		ctx->launches++;
 		CK(cudaGetLastError());
@@ -508,14 +571,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		const long long n = pl.npix_local - lp0 < batch ? pl.npix_local - lp0 : batch;
 		CK(cudaMemsetAsync(q0.count, 0, sizeof(unsigned), st));
 		span_begin(ctx, CAT_PRIMARY);
-		if(ctx->sv.blob_in_smem)
-		{
-			primary_kernel<true, STATS, true><<<(unsigned) ((n + SKR_BLOCK - 1) / SKR_BLOCK), SKR_BLOCK, smem, st>>>(ctx->sv, fp, q0, lp0, n);
-		}
-		else
-		{
-			primary_kernel<true, STATS, false><<<(unsigned) ((n + SKR_BLOCK - 1) / SKR_BLOCK), SKR_BLOCK, 0, st>>>(ctx->sv, fp, q0, lp0, n);
-		}
+		launch_primary<true, STATS>(ctx, (unsigned) ((n + SKR_BLOCK - 1) / SKR_BLOCK), fp, q0, lp0, n);
 		span_end(ctx);
 		ctx->launches++;
 		ctx->chunks++;

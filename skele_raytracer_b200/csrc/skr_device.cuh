@@ -277,7 +277,7 @@ SKR_DEV float3 fog_term(const float4 *__restrict__ B, const SceneView &sv, const
 // direct_illumination as HEAD computes it (src/raytrace.h:36-44): ambient + diffuse + specular.  One shadow ray per
 // light serves both terms (the reference casts the same ray twice).  View direction is towards the CAMERA POSITION
 // even for bounce hits (src/blinn_phong.h:93).
-template <bool STATS>
+template <bool STATS, bool FOG>
 SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, bool use_shadows, const RngCtx &rng, int sidx, float3 p, float3 n,
 							Counters &cnt)
 {
@@ -302,7 +302,7 @@ SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, b
 		}
 		const float3 lcol  = f3(B[sv.off_plcol + i]);
 		const float inv_d2 = __fdividef(1.0f, d2);
-		if(sv.F > 0)
+		if(FOG && sv.F > 0)
 		{
 			for(int j = 0; j < sv.F; j++)
 			{
@@ -370,7 +370,7 @@ SKR_DEV float3 gi_child_dir(float r1, float r2, float3 n, float3 nt, float3 nb)
 // One closest-hit query = the first half of shade() (src/raytrace.h:149-192).
 // Returns: -2 background, -1 triangle (black), >= 0 sphere index with t in tmin.
 // ------------------------------------------------------------------------------------------------
-template <bool PRIMARY, bool STATS>
+template <bool PRIMARY, bool STATS, bool TRIS>
 SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt)
 {
 	if(STATS)
@@ -378,7 +378,7 @@ SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float
 		cnt.ch++;
 	}
 	const int s = closest_sphere<PRIMARY, STATS>(B, sv, o, d, tmin, cnt);
-	if(sv.T > 0 && tri_any_hit_line<STATS>(sv, o, d, tmin, cnt))
+	if(TRIS && sv.T > 0 && tri_any_hit_line<STATS>(sv, o, d, tmin, cnt))
 	{
 		return -1;
 	}

@@ -203,7 +203,10 @@ SKR_DEV void queue_push(const Queue &q, bool want, float3 p, uint32_t pixel, flo
 // ------------------------------------------------------------------------------------------------
 // primary_kernel: local pixels [lp0, lp0 + npix)
 // ------------------------------------------------------------------------------------------------
-template <bool GI, bool STATS, bool SMEM>
+// Template flags: GI (--gillum: push hits instead of shading), STATS (device counters), SMEM (scene blob staged in shared
+// memory), TRIS (scene has triangles: BVH code compiled in), FOG (scene has spherical fog: fog shading compiled in).
+// Sphere-only, fog-free scenes thus run a kernel without the traversal stack or the fog branch in its register budget.
+template <bool GI, bool STATS, bool SMEM, bool TRIS, bool FOG>
 __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix)
 {
 	extern __shared__ float4 smem[];
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		int h	= -3;
 		if(p.valid)
 		{
-			h = closest_hit<true, STATS>(B, sv, o, d, t, cnt);
+			h = closest_hit<true, STATS, TRIS>(B, sv, o, d, t, cnt);
 		}
 		float3 hp = f3(0.0f, 0.0f, 0.0f);
 		if(h == -2)
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			if(!GI)
 			{
 				const float3 n = normalize_rn(sub_rn(hp, c));
-				sum += direct_light<STATS>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt);
+				sum += direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt);
 			}
 		}
 		if(GI)
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 // ------------------------------------------------------------------------------------------------
 // shade_expand_kernel: queue entries [start, start + count) of `in`
 // ------------------------------------------------------------------------------------------------
-template <bool STATS, bool SMEM>
+template <bool STATS, bool SMEM, bool TRIS, bool FOG>
 __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
 																  const Queue out, int expand)
 {
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 	const float3 kd = f3(B[sv.off_diff + sidx]);
 	if(valid)
 	{
-		const float3 direct = direct_light<STATS>(B, sv, fp.shadows != 0, rng, sidx, hp, n, cnt);
+		const float3 direct = direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, sidx, hp, n, cnt);
 		contrib				= thr * kd * (direct * 0.318309886183790672f); // (direct / pi) * kd, src/raytrace.h:213
 	}
 	if(expand)
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			int h		   = -3;
 			if(valid)
 			{
-				h = closest_hit<false, STATS>(B, sv, o, d, t, cnt);
+				h = closest_hit<false, STATS, TRIS>(B, sv, o, d, t, cnt);
 			}
 			const float3 w = tk * r1;
 			if(h == -2)
