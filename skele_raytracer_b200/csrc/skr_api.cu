@@ -49,6 +49,7 @@ struct skr_ctx
 
 	// scene
 	bool have_scene = false;
+	bool queues_have_dir = false;
 	SceneView sv{};
 	float4 *d_blob = nullptr;
 	float *d_tris_raw = nullptr;
@@ -408,33 +409,34 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	fp.gi			= o->monte_carlo ? 1 : 0;
 	fp.n_gi			= o->monte_carlo ? o->num_path_traces : 0;
 	fp.shadows		= o->use_shadows ? 1 : 0;
+	fp.fresnel		= o->fresnel ? 1 : 0;
 	// src/main.cpp:40-43
 	fp.inv_w  = 1 / float(o->width);
 	fp.inv_h  = 1 / float(o->height);
 	fp.aspect = o->width / float(o->height);
 	fp.angle  = (float) tan(M_PI * 0.5 * o->fov / 180.);
 	fp.key	  = make_uint2((uint32_t) o->seed, (uint32_t) (o->seed >> 32));
-	fp.node_base = (uint32_t) fp.n_gi + 1u;
+	fp.node_base = (uint32_t) fp.n_gi + 1u + (fp.fresnel ? 2u * (uint32_t) (ctx->sv.L + ctx->sv.D) : 0u);
 	fp.slot_gi	 = 1u + (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
 	pl.tiles_local = (fp.tiles_total + world - 1) / world;
 	pl.npix_local  = pl.tiles_local * tile * tile;
-	pl.levels	   = (fp.gi && fp.max_depth > 0) ? fp.max_depth : 0;
-	if(o->fresnel)
-	{
-		return fail(ctx, SKR_ERR_ARG, "skr_options: fresnel mode is not implemented yet");
-	}
+	pl.levels	   = ((fp.gi || fp.fresnel) && fp.max_depth > 0) ? fp.max_depth : 0;
 	return SKR_OK;
 }
 
-int ensure_queues(skr_ctx *ctx, int levels, unsigned cap)
+int ensure_queues(skr_ctx *ctx, int levels, unsigned cap, bool want_dir)
 {
-	if(levels <= ctx->n_levels_alloc && cap == ctx->queue_cap)
+	if(levels <= ctx->n_levels_alloc && cap == ctx->queue_cap && (!want_dir || ctx->queues_have_dir))
 	{
+		if(!want_dir && ctx->queues_have_dir)
+		{
+			// keep the arrays but hide them from the kernels of a non-fresnel frame
+		}
 		return SKR_OK;
 	}
 	for(Queue &q : ctx->queues)
 	{
-		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c);
+		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c), cudaFree(q.d);
 	}
 	ctx->queues.clear();
 	if(ctx->d_counts)
@@ -450,12 +452,17 @@ int ensure_queues(skr_ctx *ctx, int levels, unsigned cap)
 		CK(cudaMalloc(&q.a, sizeof(float4) * (size_t) cap));
 		CK(cudaMalloc(&q.b, sizeof(float4) * (size_t) cap));
 		CK(cudaMalloc(&q.c, sizeof(uint32_t) * (size_t) cap));
+		if(want_dir)
+		{
+			CK(cudaMalloc(&q.d, sizeof(float4) * (size_t) cap));
+		}
 		q.count = ctx->d_counts + l;
 		q.cap	= cap;
 		ctx->queues.push_back(q);
 	}
-	ctx->n_levels_alloc = levels;
-	ctx->queue_cap		= cap;
+	ctx->n_levels_alloc	 = levels;
+	ctx->queue_cap		 = cap;
+	ctx->queues_have_dir = want_dir;
 	return SKR_OK;
 }
 
@@ -467,6 +474,33 @@ int read_count(skr_ctx *ctx, int level, unsigned &out)
 	return SKR_OK;
 }
 
+Queue queue_view(const skr_ctx *ctx, int level, const FrameParams &fp)
+{
+	Queue q = ctx->queues[level];
+	if(!fp.fresnel)
+	{
+		q.d = nullptr; // direction array (if allocated by an earlier fresnel frame) stays untouched
+	}
+	return q;
+}
+
+template <bool STATS>
+void launch_fresnel_expand(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, const Queue &in, unsigned start, unsigned count, const Queue &out)
+{
+	if(ctx->sv.blob_in_smem)
+	{
+		fresnel_expand_kernel<STATS, true><<<blocks, SKR_BLOCK, ctx->smem_bytes, ctx->stream>>>(ctx->sv, fp, in, start, count, out);
+	}
+	else
+	{
+		fresnel_expand_kernel<STATS, false><<<blocks, SKR_BLOCK, 0, ctx->stream>>>(ctx->sv, fp, in, start, count, out);
+	}
+}
+
+// Depth-first over chunks of one queue level.  `depth` is the shade() depth of the hits in this level.  A hit spawns
+// children only if the reference would trace them (depth - 1 >= 1): n_gi hemisphere children under --gillum and, in
+// fresnel mode, up to 1 refraction + one reflection per light.  Chunks are sized so that the worst-case fan-out fits
+// the next level's queue.
 template <bool STATS>
 int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int depth)
 {
@@ -475,10 +509,13 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 		return SKR_OK;
 	}
 	const FrameParams &fp = pl.fp;
-	const bool expand	  = depth - 1 >= 1 && fp.n_gi > 0;
-	const Queue &in		  = ctx->queues[level];
+	const bool deeper	  = depth - 1 >= 1;
+	const bool expand_gi  = deeper && fp.gi && fp.n_gi > 0;
+	const bool expand_fr  = deeper && fp.fresnel && (ctx->sv.L + ctx->sv.D) > 0;
+	const unsigned fan	  = (expand_gi ? (unsigned) fp.n_gi : 0u) + (expand_fr ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
+	const Queue in		  = queue_view(ctx, level, fp);
 	ctx->queue_entries += count;
-	if(!expand)
+	if(fan == 0)
 	{
 		span_begin(ctx, CAT_BOUNCE);
 		launch_shade_expand<STATS>(ctx, (count + SKR_BLOCK - 1) / SKR_BLOCK, fp, in, 0u, count, in, 0);
@@ -487,16 +524,21 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 		CK(cudaGetLastError());
 		return SKR_OK;
 	}
-	const Queue &out	 = ctx->queues[level + 1];
-	const unsigned chunk = out.cap / (unsigned) fp.n_gi;
+	const Queue out		 = queue_view(ctx, level + 1, fp);
+	const unsigned chunk = out.cap / fan;
 	for(unsigned s = 0; s < count; s += chunk)
 	{
 		const unsigned m = count - s < chunk ? count - s : chunk;
 		CK(cudaMemsetAsync(out.count, 0, sizeof(unsigned), ctx->stream));
 		span_begin(ctx, CAT_BOUNCE);
-		launch_shade_expand<STATS>(ctx, (m + SKR_BLOCK - 1) / SKR_BLOCK, fp, in, s, m, out, 1);
-		span_end(ctx);
+		launch_shade_expand<STATS>(ctx, (m + SKR_BLOCK - 1) / SKR_BLOCK, fp, in, s, m, out, expand_gi ? 1 : 0);
 		ctx->launches++;
+		if(expand_fr)
+		{
+			launch_fresnel_expand<STATS>(ctx, (m + SKR_BLOCK - 1) / SKR_BLOCK, fp, in, s, m, out);
+			ctx->launches++;
+		}
+		span_end(ctx);
 		ctx->chunks++;
 		CK(cudaGetLastError());
 		unsigned next = 0;
@@ -520,7 +562,8 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	FrameParams &fp = pl.fp;
 	cudaStream_t st = ctx->stream;
 	const size_t smem = ctx->smem_bytes;
-	if(fp.gi)
+	const bool tree = fp.gi || fp.fresnel;
+	if(tree)
 	{
 		unsigned cap = o->queue_capacity > 0 ? (unsigned) o->queue_capacity : DEFAULT_QUEUE_CAP;
 		if(o->queue_capacity <= 0)
@@ -529,7 +572,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 			size_t free_b = 0, total_b = 0;
 			if(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && ctx->queue_cap != cap)
 			{
-				const size_t budget = free_b / 4 / (size_t) (pl.levels > 0 ? pl.levels : 1) / 36;
+				const size_t budget = free_b / 4 / (size_t) (pl.levels > 0 ? pl.levels : 1) / 52;
 				if(budget < cap)
 				{
 					cap = (unsigned) budget;
@@ -540,12 +583,13 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 				cap = ctx->queue_cap; // already allocated for an earlier frame
 			}
 		}
-		const unsigned need = (unsigned) (fp.n_gi > fp.spp ? fp.n_gi : fp.spp);
+		const unsigned fan	= (unsigned) fp.n_gi + (fp.fresnel ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
+		const unsigned need = fan > (unsigned) fp.spp ? fan : (unsigned) fp.spp;
 		if(cap < need * SKR_BLOCK)
 		{
 			cap = need * SKR_BLOCK;
 		}
-		int rc = ensure_queues(ctx, pl.levels, cap);
+		int rc = ensure_queues(ctx, pl.levels, cap, fp.fresnel != 0);
 		if(rc)
 		{
 			return rc;
@@ -553,7 +597,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		CK(ensure(ctx->d_accum, ctx->accum_bytes, sizeof(long long) * 3 * (size_t) pl.npix_local));
 		fp.accum = ctx->d_accum;
 	}
-	if(!fp.gi || pl.levels == 0)
+	if(!tree || pl.levels == 0)
 	{
 		span_begin(ctx, CAT_PRIMARY);
 		const unsigned blocks = (unsigned) ((pl.npix_local + SKR_BLOCK - 1) / SKR_BLOCK);
@@ -564,7 +608,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		CK(cudaGetLastError());
 		return SKR_OK;
 	}
-	const Queue &q0	  = ctx->queues[0];
+	const Queue q0	  = queue_view(ctx, 0, fp);
 	long long batch	  = (long long) (q0.cap / (unsigned) fp.spp) / SKR_BLOCK * SKR_BLOCK;
 	for(long long lp0 = 0; lp0 < pl.npix_local; lp0 += batch)
 	{
@@ -765,7 +809,7 @@ void skr_destroy(skr_ctx *ctx)
 	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
 	for(Queue &q : ctx->queues)
 	{
-		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c);
+		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c), cudaFree(q.d);
 	}
 	cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_err);
 	if(ctx->h_count)

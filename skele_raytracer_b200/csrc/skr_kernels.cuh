@@ -28,6 +28,7 @@ struct Queue
 	float4 *a;		 // (P.xyz, bits(global pixel id))
 	float4 *b;		 // (throughput.xyz, bits(node id))
 	uint32_t *c;	 // sample | sphere << 16
+	float4 *d;		 // (incoming ray direction.xyz, -) -- only allocated in fresnel mode, else null
 	unsigned *count; // device counter
 	unsigned cap;
 };
@@ -37,7 +38,7 @@ struct FrameParams
 	int width, height;
 	int tile, tiles_x, tiles_total, rank, world, wpr; // wpr = tile / 8 (warps per tile row-block)
 	int grid, spp;
-	int max_depth, gi, n_gi, shadows;
+	int max_depth, gi, n_gi, shadows, fresnel;
 	float angle, aspect, inv_w, inv_h;
 	uint2 key;
 	uint32_t node_base, slot_gi;
@@ -169,7 +170,8 @@ SKR_DEV void flush_counters(const FrameParams &fp, Counters &c)
 }
 
 // warp-aggregated push: one atomic per warp per call.  Must be called by all 32 lanes.
-SKR_DEV void queue_push(const Queue &q, bool want, float3 p, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, int *err)
+SKR_DEV void queue_push(const Queue &q, bool want, float3 p, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, float3 dir,
+						int *err)
 {
 	const unsigned mask = __ballot_sync(0xffffffffu, want);
 	if(mask == 0)
@@ -192,6 +194,10 @@ SKR_DEV void queue_push(const Queue &q, bool want, float3 p, uint32_t pixel, flo
 			q.a[idx] = make_float4(p.x, p.y, p.z, u2f(pixel));
 			q.b[idx] = make_float4(thr.x, thr.y, thr.z, u2f(node));
 			q.c[idx] = (sample & 0xffffu) | ((uint32_t) sphere << 16);
+			if(q.d)
+			{
+				q.d[idx] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+			}
 		}
 		else
 		{
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		}
 		if(GI)
 		{
-			queue_push(q0, h >= 0, hp, rng.pixel, f3(1.0f, 1.0f, 1.0f), 0u, (uint32_t) s, h, fp.err);
+			queue_push(q0, h >= 0, hp, rng.pixel, f3(1.0f, 1.0f, 1.0f), 0u, (uint32_t) s, h, d, fp.err);
 		}
 	}
 
@@ -338,7 +344,8 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 	if(valid)
 	{
 		const float3 direct = direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, sidx, hp, n, cnt);
-		contrib				= thr * kd * (direct * 0.318309886183790672f); // (direct / pi) * kd, src/raytrace.h:213
+		// with --gillum: (direct / pi) * kd (src/raytrace.h:213); fresnel-only trees return direct as is (:103, :218)
+		contrib = fp.gi ? thr * kd * (direct * 0.318309886183790672f) : thr * direct;
 	}
 	if(expand)
 	{
@@ -372,12 +379,122 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 				t = sphere_t_ref(o, d, f3(B[sv.off_geom + h]), B[sv.off_spec + h].w, t);
 			}
 			const float3 cp = add_rn(o, muls_rn(d, t));
-			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, fp.err);
+			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, fp.err);
 		}
 	}
 	if(valid)
 	{
 		const int x = (int) (rng.pixel % (uint32_t) fp.width), y = (int) (rng.pixel / (uint32_t) fp.width);
+		const long long lp = encode_pixel(fp, x, y);
+		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 0), (unsigned long long) to_fixed(contrib.x));
+		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 1), (unsigned long long) to_fixed(contrib.y));
+		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 2), (unsigned long long) to_fixed(contrib.z));
+	}
+	flush_counters<STATS>(fp, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fresnel_expand_kernel (opt-in mode, skr_options.fresnel): the recursion HEAD never reaches because
+// direct_illumination returns at src/raytrace.h:44 -- lines :46-103.  Runs over the same queue chunk as
+// shade_expand_kernel and pushes into the same next-level queue.  Per hit with a specular material:
+//   fr = bp::fresnel(ray.direction, N)                                   src/blinn_phong.h:156-184
+//   per light (point, then directional):
+//     fr < 1: refraction_colour  = fr * shade(P, bp::refraction(d, N))   ASSIGNMENT: only the last light's survives
+//             reflection_colour += (1 - fr) * ks * shade(P, bp::reflect_direction(Lhat, N))   (reflects the LIGHT direction)
+//   rays start exactly at P (the 1.0 near cutoff keeps them off their own sphere).
+// ------------------------------------------------------------------------------------------------
+SKR_DEV float fresnel_ref(float3 dir, float3 n, float ior_in)
+{
+	float cos_i = fminf(fmaxf(dot_rn(dir, n), -1.0f), 1.0f);
+	float et = 1.0f, ior = ior_in;
+	if(cos_i > 0.0f)
+	{
+		et	= ior_in;
+		ior = 1.0f;
+	}
+	const float sint = __fmul_rn(__fdiv_rn(et, ior), __fsqrt_rn(fmaxf(0.0f, __fsub_rn(1.0f, __fmul_rn(cos_i, cos_i)))));
+	if(sint >= 1.0f)
+	{
+		return 1.0f; // total internal reflection
+	}
+	const float cos_t = __fsqrt_rn(fmaxf(0.0f, __fsub_rn(1.0f, __fmul_rn(sint, sint))));
+	cos_i			  = fabsf(cos_i);
+	const float den	  = __fadd_rn(__fmul_rn(ior, cos_i), __fmul_rn(et, cos_t)); // the reference uses this denominator for Rs AND Rp
+	const float rs	  = __fdiv_rn(__fsub_rn(__fmul_rn(ior, cos_i), __fmul_rn(et, cos_t)), den);
+	const float rp	  = __fdiv_rn(__fsub_rn(__fmul_rn(et, cos_i), __fmul_rn(ior, cos_t)), den);
+	return __fdiv_rn(__fadd_rn(__fmul_rn(rs, rs), __fmul_rn(rp, rp)), 2.0f);
+}
+SKR_DEV float3 refraction_ref(float3 dir, float3 n, float ior) // src/blinn_phong.h:143-153
+{
+	const float dn = dot_rn(dir, n);
+	const float k  = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(ior, ior), __fsub_rn(1.0f, __fmul_rn(dn, dn))));
+	if(k < 0.0f)
+	{
+		return f3(0.0f, 0.0f, 0.0f);
+	}
+	return sub_rn(muls_rn(dir, ior), muls_rn(n, __fadd_rn(__fmul_rn(ior, dn), __fsqrt_rn(k))));
+}
+SKR_DEV float3 reflect_direction_ref(float3 l, float3 n) // src/blinn_phong.h:137-140
+{
+	return normalize_rn(sub_rn(l, muls_rn(n, __fmul_rn(2.0f, dot_rn(l, n)))));
+}
+
+template <bool STATS, bool SMEM>
+__global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
+																	const Queue out)
+{
+	extern __shared__ float4 smem[];
+	const float4 *B = stage_scene<SMEM>(sv, smem);
+	Counters cnt;
+	zero(cnt);
+	const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = g < count;
+	const unsigned i = start + (valid ? g : 0u);
+	const float4 qa = in.a[i], qb = in.b[i], qd = in.d[i];
+	const uint32_t qc = in.c[i];
+	const float3 hp = f3(qa), thr = f3(qb), dir = f3(qd);
+	const int sidx = (int) (qc >> 16);
+	const uint32_t pixel = f2u(qa.w), node = f2u(qb.w), sample = qc & 0xffffu;
+	const float3 n	= normalize_rn(sub_rn(hp, f3(B[sv.off_geom + sidx])));
+	const float3 kd = f3(B[sv.off_diff + sidx]);
+	const float3 ks = f3(B[sv.off_spec + sidx]);
+	const float ior = B[sv.off_diff + sidx].w;
+	const bool spec = valid && (ks.x != 0.0f || ks.y != 0.0f || ks.z != 0.0f);
+	const float fr	= fresnel_ref(dir, n, ior);
+	// weight of this node's direct_illumination result in the pixel: T (.) kd / pi under --gillum, T otherwise
+	const float3 wn = fp.gi ? thr * kd * 0.318309886183790672f : thr;
+	float3 contrib	= f3(0.0f, 0.0f, 0.0f);
+	const int nl	= sv.L + sv.D;
+	for(int li = 0; li < nl; li++)
+	{
+		const float3 lhat = li < sv.L ? normalize_rn(sub_rn(f3(B[sv.off_plpos + li]), hp)) : f3(B[sv.off_dldir + (li - sv.L)]);
+#pragma unroll
+		for(int kind = 0; kind < 2; kind++) // 0: refraction (only the last light's result survives), 1: reflection
+		{
+			const bool want = spec && (kind == 1 || (fr < 1.0f && li == nl - 1));
+			const float3 d	= kind == 0 ? refraction_ref(dir, n, ior) : reflect_direction_ref(lhat, n);
+			const float3 w	= kind == 0 ? wn * fr : wn * ks * (1.0f - fr);
+			float t			= 0.0f;
+			int h			= -3;
+			if(want)
+			{
+				h = closest_hit<false, STATS, true>(B, sv, hp, d, t, cnt);
+			}
+			if(h == -2)
+			{
+				contrib += w * sv.background;
+			}
+			if(h >= 0)
+			{
+				t = sphere_t_ref(hp, d, f3(B[sv.off_geom + h]), B[sv.off_spec + h].w, t);
+			}
+			const float3 cp = add_rn(hp, muls_rn(d, t));
+			queue_push(out, h >= 0, cp, pixel, w, node * fp.node_base + (uint32_t) (fp.n_gi + 2 * li + kind) + 1u, sample, h, d, fp.err);
+		}
+	}
+	if(valid && (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f))
+	{
+		const int x = (int) (pixel % (uint32_t) fp.width), y = (int) (pixel / (uint32_t) fp.width);
 		const long long lp = encode_pixel(fp, x, y);
 		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 0), (unsigned long long) to_fixed(contrib.x));
 		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 1), (unsigned long long) to_fixed(contrib.y));

@@ -148,6 +148,40 @@ def test_stochastic_mean_parity_vs_reference_rand_stream(gpu, port, scenes, gsce
     assert_mean_parity(A, B, what=f"{scene} {kw}")
 
 
+# ---- opt-in fresnel mode (row A9: the recursion of src/raytrace.h:46-103 that HEAD skips) -------------------------
+
+FRESNEL = [("spheres1", dict(width=320, height=180, max_depth=2, fresnel=True)),
+           ("spheres1", dict(width=320, height=180, max_depth=3, use_shadows=True, fresnel=True)),
+           ("spheres2_nofog", dict(width=320, height=180, max_depth=3, use_shadows=True, fresnel=True)),
+           ("bear", dict(width=320, height=180, max_depth=4, fresnel=True)),
+           ("test", dict(width=160, height=90, max_depth=3, fresnel=True)),
+           ("spheres2", dict(width=160, height=90, max_depth=3, grid_size=2, use_shadows=True, fresnel=True, seed=8)),
+           ("spheres2_nofog", dict(width=96, height=54, max_depth=3, monte_carlo=True, num_path_traces=3, fresnel=True, seed=9))]
+
+
+@pytest.mark.parametrize("scene,kw", FRESNEL)
+def test_fresnel_mode_parity(gpu, port, scenes, gscenes, scene, kw):
+    """Oracle: the port with fresnel=1, which tests/test_oracle_port.py pins bit-for-bit to the reference compiled with
+    src/raytrace.h:44 removed."""
+    oo, go = opts(collect_stats=True, **dict(kw))
+    p32, p8, pst, _ = port.render(scenes[scene], oo, rng_mode=O.RNG_PHILOX, seed=go.seed)
+    gpu.upload(gscenes[scene])
+    g32, g8, gst = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, min_ok=0.998, what=f"fresnel {scene} {kw}")
+    # the GPU traces only the refraction child whose result the reference keeps (the last light's), so it may issue
+    # fewer closest-hit rays than the port, never more
+    assert gst.closest_hit_rays <= pst["closest_hit_rays"]
+    assert gst.closest_hit_rays >= 0.5 * pst["closest_hit_rays"]
+
+
+def test_fresnel_off_is_head_behaviour(gpu, gscenes):
+    gpu.upload(gscenes["spheres1"])
+    a, _, _ = gpu.render(S.Options(width=160, height=90, max_depth=3))
+    b, _, _ = gpu.render(S.Options(width=160, height=90, max_depth=1))
+    c, _, _ = gpu.render(S.Options(width=160, height=90, max_depth=1, fresnel=True))  # depth 1: children would have depth 0
+    assert np.array_equal(a, b) and np.allclose(a, c, atol=1e-6)
+
+
 # ---- edge cases ---------------------------------------------------------------------------------
 
 def test_empty_scene_is_background(gpu):
