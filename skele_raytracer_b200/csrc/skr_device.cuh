@@ -102,7 +102,7 @@ SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, fl
 	float umin	   = CUDART_INF_F;
 	const int NP   = sv.S4 >> 1;
 	const float4 *__restrict__ G = B + (PRIMARY ? sv.off_pprim : sv.off_pgeom);
-	const float2 dx = splat2(d.x), dy = splat2(d.y), dz = splat2(d.z), na2 = splat2(na);
+	const float2 dx = splat2(d.x), dy = splat2(d.y), dz = splat2(d.z), na2 = splat2(na), two = splat2(2.0f);
 	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
 #pragma unroll 2
 	for(int p = 0; p < NP; p++)
@@ -126,22 +126,44 @@ SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, fl
 			cnt.st += (2 * p < sv.S) + (2 * p + 1 < sv.S);
 			cnt.stp += (d4.x >= 0.0f) + (d4.y >= 0.0f);
 		}
-		if(d4.x >= 0.0f)
+		if(PRIMARY)
 		{
-			const float w = fmaf(2.0f, h.x, cc.x), m = -h.x - umin;
-			if((h.x < na) & (w > na) & ((m < 0.0f) | (d4.x > m * m)))
+			// camera rays are coherent: whole warps skip the selection of spheres their rays' lines miss
+			if(d4.x >= 0.0f)
 			{
-				umin = -h.x - __fsqrt_rn(d4.x);
-				best = 2 * p;
+				const float w = fmaf(2.0f, h.x, cc.x), m = -h.x - umin;
+				if((h.x < na) & (w > na) & ((m < 0.0f) | (d4.x > m * m)))
+				{
+					umin = -h.x - __fsqrt_rn(d4.x);
+					best = 2 * p;
+				}
+			}
+			if(d4.y >= 0.0f)
+			{
+				const float w = fmaf(2.0f, h.y, cc.y), m = -h.y - umin;
+				if((h.y < na) & (w > na) & ((m < 0.0f) | (d4.y > m * m)))
+				{
+					umin = -h.y - __fsqrt_rn(d4.y);
+					best = 2 * p + 1;
+				}
 			}
 		}
-		if(d4.y >= 0.0f)
+		else
 		{
-			const float w = fmaf(2.0f, h.y, cc.y), m = -h.y - umin;
-			if((h.y < na) & (w > na) & ((m < 0.0f) | (d4.y > m * m)))
+			// bounce rays are incoherent: some lane always passes d4 >= 0, so branch-free predicates are cheaper than
+			// divergent branches; only an actual new closest sphere (rare) takes a branch and a sqrt
+			const float2 w	= fma2(two, h, cc);
+			const float2 m	= add2(f2(-h.x, -h.y), splat2(-umin));
+			const float2 mm = mul2(m, m);
+			const bool bx	= (d4.x >= 0.0f) & (h.x < na) & (w.x > na) & ((m.x < 0.0f) | (d4.x > mm.x));
+			const bool by	= (d4.y >= 0.0f) & (h.y < na) & (w.y > na) & ((m.y < 0.0f) | (d4.y > mm.y));
+			if(bx | by)
 			{
-				umin = -h.y - __fsqrt_rn(d4.y);
-				best = 2 * p + 1;
+				const float ux = bx ? -h.x - __fsqrt_rn(d4.x) : CUDART_INF_F;
+				const float uy = by ? -h.y - __fsqrt_rn(d4.y) : CUDART_INF_F;
+				const bool sy  = uy < ux; // strict: the first sphere wins ties, as in the reference's loop
+				umin		   = sy ? uy : ux;
+				best		   = 2 * p + (sy ? 1 : 0);
 			}
 		}
 	}
