@@ -192,10 +192,15 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
     frame = torch.empty((base.height, base.width, 3), dtype=torch.uint8, device=dev)
     rays = cst["closest_hit_rays"] + cst["shadow_rays"]
 
-    def step():
+    tree = bool(kw.get("monte_carlo") or kw.get("fresnel"))  # wavefront frames are scheduled with host read-backs
+
+    def step(want_stats=False):
+        """One frame.  Single-kernel frames are enqueued asynchronously (stats=NULL): consecutive steps, the all-gather
+        and the de-interleave queue up on the library's stream without a host round trip in between."""
+        ws = want_stats or tree
         if world == 1:
-            return r.render_device(base, frame.data_ptr(), 0)
-        st = r.render_tiles_device(base, tiles.data_ptr())
+            return r.render_device(base, frame.data_ptr(), 0, want_stats=ws)
+        st = r.render_tiles_device(base, tiles.data_ptr(), want_stats=ws)
         dist.all_gather_into_tensor(gathered, tiles)
         r.deinterleave_device(base, gathered.data_ptr(), frame.data_ptr())
         return st
@@ -217,15 +222,22 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
             ev[i][0].record(ext)
             st = step()
             ev[i][1].record(ext)
-            launches += st.kernel_launches + (1 if world > 1 else 0)
-            kernel_ms["primary"] += st.ms_primary
-            kernel_ms["bounce"] += st.ms_bounce
-            kernel_ms["resolve"] += st.ms_resolve
+            launches += (st.kernel_launches if st is not None else 1) + (1 if world > 1 else 0)
+            if st is not None:
+                kernel_ms["primary"] += st.ms_primary
+                kernel_ms["bounce"] += st.ms_bounce
+                kernel_ms["resolve"] += st.ms_resolve
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t_end = time.time()
+        if not tree:
+            # the dominant kernel's own duration (CUDA events around the launch, on its stream), from extra untimed steps
+            for _ in range(steps):
+                st = step(want_stats=True)
+                kernel_ms["primary"] += st.ms_primary
+            torch.cuda.synchronize()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     if world > 1:
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -290,6 +302,8 @@ def main_gpu(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner to STDOUT; keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     r = S.Renderer(local_rank)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

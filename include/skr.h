@@ -134,10 +134,13 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *scene);
 /* Renders one frame (or this rank's tiles of it) and copies the result to HOST buffers.
  *   rgb8  : H*W*3 bytes, row-major top-down RGB, (unsigned char)(min(1,c)*255) as src/main.cpp:96; may be NULL
  *   rgb32 : H*W*3 floats, the pre-clamp image (for tests); may be NULL
- * With world > 1 only this rank's tiles are written; other pixels are left untouched. */
+ * With world > 1 only this rank's tiles are rendered; the other ranks' pixels are written as 0. */
 int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32, skr_stats *stats);
 
-/* Same, results left in DEVICE memory (pointers valid on ctx's device; either may be NULL). */
+/* Same, results left in DEVICE memory (pointers valid on ctx's device; either may be NULL).
+ * With stats == NULL, collect_stats == 0 and no --gillum/fresnel tree the call is ASYNCHRONOUS: the frame (one
+ * kernel) is enqueued on skr_stream() and the call returns at once; order later work on that stream or skr_sync().
+ * The same holds for skr_render_tiles_device and skr_deinterleave_device. */
 int skr_render_device(skr_ctx *ctx, const skr_options *opt, void *d_rgb8, void *d_rgb32, skr_stats *stats);
 
 /* Multi-GPU frame split.  skr_render_tiles_device renders this rank's tiles into a COMPACT tile-major

@@ -251,22 +251,23 @@ class Renderer:
                                         None if rgb32 is None else rgb32.ctypes.data, C.byref(st)), "skr_render")
         return rgb32, rgb8, st
 
-    def render_device(self, option: Options, d_rgb8: int = 0, d_rgb32: int = 0) -> Stats:
-        """skr_render_device: raw device pointers (ints), e.g. torch.Tensor.data_ptr()."""
-        st = Stats()
+    def render_device(self, option: Options, d_rgb8: int = 0, d_rgb32: int = 0, want_stats: bool = True):
+        """skr_render_device: raw device pointers (ints), e.g. torch.Tensor.data_ptr().
+        want_stats=False passes stats=NULL: asynchronous for single-kernel frames (see include/skr.h)."""
+        st = Stats() if want_stats else None
         o = option._c()
-        self._check(self.lib.skr_render_device(self.ctx, C.byref(o), d_rgb8 or None, d_rgb32 or None, C.byref(st)),
-                    "skr_render_device")
+        self._check(self.lib.skr_render_device(self.ctx, C.byref(o), d_rgb8 or None, d_rgb32 or None,
+                                               C.byref(st) if want_stats else None), "skr_render_device")
         return st
 
     def tiles_bytes(self, option: Options) -> int:
         o = option._c()
         return int(self.lib.skr_tiles_bytes(C.byref(o)))
 
-    def render_tiles_device(self, option: Options, d_tiles: int) -> Stats:
-        st = Stats()
+    def render_tiles_device(self, option: Options, d_tiles: int, want_stats: bool = True):
+        st = Stats() if want_stats else None
         o = option._c()
-        self._check(self.lib.skr_render_tiles_device(self.ctx, C.byref(o), d_tiles, C.byref(st)),
+        self._check(self.lib.skr_render_tiles_device(self.ctx, C.byref(o), d_tiles, C.byref(st) if want_stats else None),
                     "skr_render_tiles_device")
         return st
 

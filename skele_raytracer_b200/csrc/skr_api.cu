@@ -82,6 +82,7 @@ struct skr_ctx
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
 
 	unsigned launches = 0, chunks = 0;
+	bool timing = true; // false: fire-and-forget frame, no per-kernel events
 	unsigned long long queue_entries = 0;
 };
 
@@ -145,6 +146,10 @@ inline float hdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
 void span_begin(skr_ctx *ctx, int cat)
 {
+	if(!ctx->timing)
+	{
+		return;
+	}
 	if(ctx->spans_used == ctx->spans.size())
 	{
 		Span s;
@@ -159,6 +164,10 @@ void span_begin(skr_ctx *ctx, int cat)
 }
 void span_end(skr_ctx *ctx)
 {
+	if(!ctx->timing)
+	{
+		return;
+	}
 	cudaEventRecord(ctx->spans[ctx->spans_used].b, ctx->stream);
 	ctx->spans_used++;
 }
@@ -648,15 +657,29 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	ctx->launches = ctx->chunks = 0;
 	ctx->queue_entries = 0;
 	const bool want_stats = o->collect_stats != 0;
+	const bool tree		  = (pl.fp.gi || pl.fp.fresnel) && pl.levels > 0;
+	// Fire-and-forget: with no stats requested and no wavefront tree (whose scheduling reads queue counts back), the
+	// frame is ONE kernel; enqueue it and return without touching the host again.  The caller orders later work on
+	// skr_stream() or calls skr_sync().  This is what lets back-to-back frames (and the all-gather / de-interleave of
+	// the multi-GPU path) queue up behind each other instead of paying a host round trip per frame.
+	const bool async = !stats && !want_stats && !tree;
+	ctx->timing		 = !async;
 	pl.fp.counters = ctx->d_counters;
 	pl.fp.err	   = ctx->d_err;
-	CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, st));
-	CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
-	CK(cudaEventRecord(ctx->ev_begin, st));
+	if(!async)
+	{
+		CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, st));
+		CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
+		CK(cudaEventRecord(ctx->ev_begin, st));
+	}
 	int rc = want_stats ? render_frame<true>(ctx, o, pl) : render_frame<false>(ctx, o, pl);
 	if(rc)
 	{
 		return rc;
+	}
+	if(async)
+	{
+		return SKR_OK;
 	}
 	CK(cudaEventRecord(ctx->ev_end, st));
 	CK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
