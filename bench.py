@@ -43,6 +43,9 @@ WORKLOADS = {
            "scenes/bear.scn 3840x2160 --gillum 64 --jsample 4 --shadow"),
 }
 SEED = 1
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu capture
+# (bench.py cannot run ncu on itself): profiles/r01_prof_c2c_ncu_raw.txt
+NCU_TRAFFIC_BYTES = {"c2": (637184 + 9216, "profiles/r01_prof_c2c_ncu_raw.txt"), "c4": (613376 + 1024, "profiles/r01_prof_c4_ncu_raw.txt")}
 
 
 def algorithmic_flops(st, primary_samples):
@@ -355,7 +358,8 @@ def main_gpu(args, rank, world, local_rank):
             "e2e": m.get("e2e"),
             "gpu_launches": m["launches"],
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": None, "kernel": "primary_kernel<false,false>" if dom == "primary" else "shade_expand_kernel<false>",
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[0] if world == 1 else None,
+                         "traffic_source": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[1], "kernel": "primary_kernel" if dom == "primary" else "shade_expand_kernel",
                          "kernel_ms_per_frame": dom_ms, "kernel_launches_per_frame": dom_launches,
                          "flops_per_frame_algorithmic_this_rank": flops,
                          "peak_source": "FFMA microbenchmark measured live in this run (skr_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",

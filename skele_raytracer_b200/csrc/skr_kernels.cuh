@@ -17,7 +17,9 @@
 #pragma once
 #include "skr_device.cuh"
 
+#ifndef SKR_BLOCK
 #define SKR_BLOCK 256
+#endif
 #ifndef SKR_MIN_BLOCKS
 #define SKR_MIN_BLOCKS 4 // <= 64 registers: 32 resident warps per SM
 #endif
