@@ -93,15 +93,18 @@ SKR_DEV uint4 rng_block(const RngCtx &r, uint32_t slot) { return philox4x32_10(m
 //   t2 > 1        <=>  h < -a  and  d4 >= 0  and  cc + 2h > -a          (as in occluded())
 //   u < umin      <=>  m < 0  or  d4 > m*m,  m = -h - umin              (no sqrt)
 // so a square root is taken only when a sphere actually becomes the new closest (once or twice per ray).
-template <bool PRIMARY, bool STATS>
-SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt)
+// ORIGIN_TABLE: G is a pair table of (e, cc) for THIS ray's origin (camera rays: the blob's pprim; bounce rays of one
+// hit: the per-group table expand_kernel builds in shared memory) -- the test is then 3 + 2 packed operations.
+// Otherwise G is the blob's pgeom (-c, -r^2) and e, cc are formed per test from `o`.
+// COHERENT picks branches (whole warps skip) over predicates (no divergence) for the rare selection work.
+template <bool ORIGIN_TABLE, bool COHERENT, bool STATS>
+SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, float3 o, float3 d, float &tmin, Counters &cnt)
 {
+	constexpr bool PRIMARY = ORIGIN_TABLE;
 	const float a  = dot(d, d);
 	const float na = -a;
 	int best	   = -1;
 	float umin	   = CUDART_INF_F;
-	const int NP   = sv.S4 >> 1;
-	const float4 *__restrict__ G = B + (PRIMARY ? sv.off_pprim : sv.off_pgeom);
 	const float2 dx = splat2(d.x), dy = splat2(d.y), dz = splat2(d.z), na2 = splat2(na), two = splat2(2.0f);
 	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
 #pragma unroll 2
@@ -123,10 +126,10 @@ SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, fl
 		const float2 d4 = fma2(h, h, mul2(na2, cc));
 		if(STATS)
 		{
-			cnt.st += (2 * p < sv.S) + (2 * p + 1 < sv.S);
+			cnt.st += (2 * p < S) + (2 * p + 1 < S);
 			cnt.stp += (d4.x >= 0.0f) + (d4.y >= 0.0f);
 		}
-		if(PRIMARY)
+		if(COHERENT)
 		{
 			// camera rays are coherent: whole warps skip the selection of spheres their rays' lines miss
 			if(d4.x >= 0.0f)
@@ -150,25 +153,32 @@ SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, fl
 		}
 		else
 		{
-			// bounce rays are incoherent: some lane always passes d4 >= 0, so branch-free predicates are cheaper than
-			// divergent branches; only an actual new closest sphere (rare) takes a branch and a sqrt
-			const float2 w	= fma2(two, h, cc);
-			const float2 m	= add2(f2(-h.x, -h.y), splat2(-umin));
-			const float2 mm = mul2(m, m);
-			const bool bx	= (d4.x >= 0.0f) & (h.x < na) & (w.x > na) & ((m.x < 0.0f) | (d4.x > mm.x));
-			const bool by	= (d4.y >= 0.0f) & (h.y < na) & (w.y > na) & ((m.y < 0.0f) | (d4.y > mm.y));
-			if(bx | by)
+			// bounce rays are incoherent: in every warp some lane's line hits this sphere, so branches would only add
+			// divergence.  Rank candidates directly on u = -h - sqrt(d4) with an approximate MUFU square root (NaN for
+			// d4 < 0 fails both comparisons): 1.0 < t2 < tmin  <=>  a < u < umin.  No branch, no IEEE sqrt sequence;
+			// the caller recomputes the winner's t exactly (sphere_t_ref).
+			const float ux = -h.x - sqrt_approx(d4.x);
+			const float uy = -h.y - sqrt_approx(d4.y);
+			if((ux > a) & (ux < umin))
 			{
-				const float ux = bx ? -h.x - __fsqrt_rn(d4.x) : CUDART_INF_F;
-				const float uy = by ? -h.y - __fsqrt_rn(d4.y) : CUDART_INF_F;
-				const bool sy  = uy < ux; // strict: the first sphere wins ties, as in the reference's loop
-				umin		   = sy ? uy : ux;
-				best		   = 2 * p + (sy ? 1 : 0);
+				umin = ux;
+				best = 2 * p;
+			}
+			if((uy > a) & (uy < umin))
+			{
+				umin = uy;
+				best = 2 * p + 1;
 			}
 		}
 	}
 	tmin = best >= 0 ? __fdiv_rn(umin, a) : CUDART_INF_F;
 	return best;
+}
+
+template <bool PRIMARY, bool STATS>
+SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt)
+{
+	return closest_sphere_table<PRIMARY, PRIMARY, STATS>(B + (PRIMARY ? sv.off_pprim : sv.off_pgeom), sv.S4 >> 1, sv.S, o, d, tmin, cnt);
 }
 
 // The reference's own expression for the winner's t (src/raytrace.h:197-201 -> src/utils.h:87-110), so that the hit

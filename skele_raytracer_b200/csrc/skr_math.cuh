@@ -64,5 +64,14 @@ SKR_DEV float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 SKR_DEV float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 SKR_DEV float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
+// sqrt.approx (MUFU-based, ~2^-22 relative error, NaN for negative inputs): used only to RANK candidate hits; the
+// winner's distance is always recomputed with IEEE operations.
+SKR_DEV float sqrt_approx(float x)
+{
+	float r;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
 SKR_DEV float u2f(uint32_t u) { return __uint_as_float(u); }
 SKR_DEV uint32_t f2u(float f) { return __float_as_uint(f); }
