@@ -393,7 +393,7 @@ SKR_DEV float3 gi_child_dir(float r1, float r2, float3 n, float3 nt, float3 nb)
 {
 	const float s_theta = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(r1, r1)));
 	float sn, cs;
-	sincospif(2.0f * r2, &sn, &cs); // phi = 2*pi*r2
+	__sincosf(6.28318530717958648f * r2, &sn, &cs); // phi = 2*pi*r2 in [0, 2pi]: MUFU sin/cos, abs. error ~2^-21
 	const float sx = s_theta * cs, sy = r1, sz = s_theta * sn;
 	return f3(sx * nb.x + sy * n.x + sz * nt.x, sx * nb.y + sy * n.y + sz * nb.y, sx * nb.z + sy * n.z + sz * nb.z);
 }
