@@ -691,7 +691,7 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	CK(cudaStreamSynchronize(st));
 	if(*ctx->h_err)
 	{
-		return fail(ctx, SKR_ERR_CUDA, "internal: wavefront queue overflow (flag %d)", *ctx->h_err);
+		return fail(ctx, SKR_ERR_CUDA, "internal: %s (flag %d)", (*ctx->h_err & 2) ? "BVH traversal stack overflow" : "wavefront queue overflow", *ctx->h_err);
 	}
 	if(stats)
 	{
@@ -990,6 +990,7 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	sv.cam_up	  = make_float3(sc->camera[6], sc->camera[7], sc->camera[8]);
 	sv.cam_right  = make_float3(sc->camera[9], sc->camera[10], sc->camera[11]);
 	sv.background = make_float3(sc->background[0], sc->background[1], sc->background[2]);
+	sv.err		  = ctx->d_err;
 
 	if(ctx->d_blob)
 	{

@@ -112,6 +112,10 @@ SKR_DEV bool tri_any_hit_line(const SceneView &sv, float3 o, float3 d, float tma
 			{
 				stack[sp++] = cr;
 			}
+			else
+			{
+				atomicOr(sv.err, 2); // deeper than any LBVH over 63-bit codes + index bits can be; reported, never silent
+			}
 		}
 		if(next < 0)
 		{

@@ -36,6 +36,7 @@ struct SceneView
 	const float4 *tri_v; // 3 float4 per triangle (v0, v1, v2), LBVH leaf order
 	const float4 *bvh;	 // 4 float4 per internal node (see skr_bvh.cuh)
 	int bvh_root_is_leaf; // T == 1
+	int *err;			  // device error word (bit 1: BVH traversal stack overflow)
 	float3 cam_pos, cam_dir, cam_up, cam_right, background;
 };
 

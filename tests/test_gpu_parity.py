@@ -235,6 +235,29 @@ def test_many_spheres_use_the_global_memory_path(gpu, port):
     assert_image_parity(g32, p32, g8, p8, min_ok=0.998, what="1200 spheres")
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_random_scenes_everything_on(gpu, port, seed):
+    """fresnel + --gillum + --jsample + shadows + fog + directional lights + triangles at once."""
+    rng = np.random.default_rng(100 + seed)
+    sc = random_scene(rng, nspheres=int(rng.integers(2, 9)), nplights=int(rng.integers(1, 3)), ntris=int(rng.integers(1, 30)),
+                      nfogs=int(rng.integers(0, 2)), ndlights=int(rng.integers(0, 2)))
+    gpu.upload(to_gpu_scene(sc))
+    kw = dict(width=72, height=48, max_depth=3, monte_carlo=True, num_path_traces=int(rng.choice([2, 4, 7])), grid_size=int(rng.choice([0, 2, 3])),
+              use_shadows=True, fresnel=True, seed=seed)
+    oo, go = opts(**dict(kw))
+    p32, p8, _, _ = port.render(sc, oo, rng_mode=O.RNG_PHILOX, seed=go.seed)
+    g32, g8, _ = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, min_ok=0.997, what=f"everything-on scene {seed} {kw}")
+
+
+def test_gillum_64_single_sample(gpu, port, scenes, gscenes):
+    oo, go = opts(width=48, height=27, max_depth=3, monte_carlo=True, num_path_traces=64, use_shadows=True, seed=12)
+    p32, p8, _, _ = port.render(scenes["spheres1"], oo, rng_mode=O.RNG_PHILOX, seed=12)
+    gpu.upload(gscenes["spheres1"])
+    g32, g8, _ = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, what="gillum 64")
+
+
 # ---- BVH ------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("ntris", [1, 2, 3, 33, 1000, 20000])
@@ -245,6 +268,8 @@ def test_bvh_equals_brute_force(gpu, ntris):
         sc.tris = (sc.tris.reshape(-1, 3, 3)[:, :1] + 0.08 * (sc.tris.reshape(-1, 3, 3) - sc.tris.reshape(-1, 3, 3)[:, :1])).reshape(-1, 9)
     if ntris == 33:
         sc.tris[5:20] = sc.tris[5]  # duplicates -> identical Morton codes
+    if ntris == 20000:
+        sc.tris[1000:9000] = sc.tris[1000]  # 8000 identical triangles: ties broken by index, depth stays logarithmic
     g = to_gpu_scene(sc)
     go = S.Options(width=200, height=120, use_shadows=True)
     gpu.upload(g)
