@@ -13,12 +13,11 @@ r = S.Renderer()
 for w in ["c3", "c5"]:
     scene, kw, desc = WORKLOADS[w]
     r.upload(S.Scene.load(os.path.join(G, scene + ".npz")))
-    for cap in [1 << 20, 4 << 20, 16 << 20, 32 << 20, 64 << 20, 128 << 20]:
+    for cap in [32 << 20, 64 << 20, 128 << 20, 256 << 20, 512 << 20]:
         o = S.Options(seed=1, queue_capacity=cap, **kw)
-        best = None
-        for _ in range(3):
+        ts = []
+        for _ in range(5):
             st = r.render_device(o, 0, 0)
-            if best is None or st.ms_total < best.ms_total:
-                best = st
-        print(f"{w} cap={cap >> 20}M total={best.ms_total:.2f}ms primary={best.ms_primary:.2f} bounce={best.ms_bounce:.2f} launches={best.kernel_launches} "
-              f"chunks={best.queue_chunks} entries={best.queue_entries}", flush=True)
+            ts.append(st.ms_total)
+        print(f"{w} cap={cap >> 20}M min={min(ts):.2f} median={sorted(ts)[2]:.2f} max={max(ts):.2f} bounce={st.ms_bounce:.2f} launches={st.kernel_launches} "
+              f"chunks={st.queue_chunks}", flush=True)

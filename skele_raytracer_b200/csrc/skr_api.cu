@@ -36,7 +36,8 @@ struct Span
 };
 
 constexpr size_t SMEM_BLOB_LIMIT = 64 * 1024;
-constexpr unsigned DEFAULT_QUEUE_CAP = 32u << 20; // entries per level (36 B each): large enough that one chunk fills the GPU even at --gillum 64
+constexpr unsigned MAX_QUEUE_CAP = 128u << 20; // entries per level (36 B each, 4.6 GB): fewer, fuller chunks -- config 5: 228 ms at 32 M, 213 ms at 128 M
+constexpr unsigned MIN_QUEUE_CAP = 1u << 20;
 constexpr int DEFAULT_TILE = 32;
 } // namespace
 
@@ -574,22 +575,29 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	const bool tree = fp.gi || fp.fresnel;
 	if(tree)
 	{
-		unsigned cap = o->queue_capacity > 0 ? (unsigned) o->queue_capacity : DEFAULT_QUEUE_CAP;
+		const unsigned fan0 = (unsigned) fp.n_gi + (fp.fresnel ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
+		unsigned cap		= (unsigned) o->queue_capacity;
 		if(o->queue_capacity <= 0)
 		{
-			// never take more than a quarter of the free memory for the queues
-			size_t free_b = 0, total_b = 0;
-			if(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && ctx->queue_cap != cap)
+			// default: what one fan-out of all primary samples could need, between 1 M and 128 M entries, and never more
+			// than a quarter of the free memory over all levels; an allocation that is already big enough is kept
+			const unsigned long long want = (unsigned long long) pl.npix_local * (unsigned) fp.spp * (fan0 ? fan0 : 1u);
+			cap = want > MAX_QUEUE_CAP ? MAX_QUEUE_CAP : (want < MIN_QUEUE_CAP ? MIN_QUEUE_CAP : (unsigned) want);
+			if(ctx->queue_cap >= cap && ctx->n_levels_alloc >= pl.levels)
 			{
-				const size_t budget = free_b / 4 / (size_t) (pl.levels > 0 ? pl.levels : 1) / 52;
-				if(budget < cap)
-				{
-					cap = (unsigned) budget;
-				}
+				cap = ctx->queue_cap;
 			}
-			else if(ctx->queue_cap != 0 && ctx->n_levels_alloc >= pl.levels)
+			else
 			{
-				cap = ctx->queue_cap; // already allocated for an earlier frame
+				size_t free_b = 0, total_b = 0;
+				if(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+				{
+					const size_t budget = free_b / 4 / (size_t) (pl.levels > 0 ? pl.levels : 1) / 52;
+					if(budget < cap)
+					{
+						cap = (unsigned) budget;
+					}
+				}
 			}
 		}
 		const unsigned fan	= (unsigned) fp.n_gi + (fp.fresnel ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
