@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""scripts/gpu_check.py -- developer probe: GPU vs the C port on a grid of scene/flag combinations.
+"""tests/tools/gpu_check.py -- developer probe (uses the oracle as checker, hence under tests/): GPU vs the C port on a grid of scene/flag combinations.
 Prints one line per case (fraction of pixel-channels beyond 1/255, max abs diff, device ms)."""
 import os
 import sys
@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import skele_raytracer_b200 as S  # noqa: E402
 from oracle import oracle_lib as O  # noqa: E402
