@@ -29,6 +29,20 @@ def test_every_declared_symbol_is_exported():
     assert lib.skr_abi_version() == int(re.search(r"#define SKR_ABI_VERSION (\d+)", HEADER).group(1))
 
 
+def test_multi_gpu_library_exports_its_header():
+    path = os.path.join(ROOT, "skele_raytracer_b200", "libskr_mgpu.so")
+    if not os.path.exists(path):
+        pytest.skip("built without NCCL")
+    hdr = open(os.path.join(ROOT, "include", "skr_mgpu.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(skr_mgpu_[a-z0-9_]+)\s*\(", body)))
+    assert len(names) >= 6
+    C.CDLL(S.lib_path(), mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
 def test_struct_layouts_match_header():
     # field order of the ctypes mirrors == field order in the header
     for cname, ctype in (("skr_scene_desc", api._SceneDesc), ("skr_options", api._Options), ("skr_stats", api.Stats)):

@@ -402,6 +402,22 @@ def test_cli_writes_the_same_ppm(gpu, tmp_path):
     assert out2.read_bytes() == out.read_bytes()
 
 
+def test_cli_multi_gpu_front_end_on_all_visible_gpus(gpu, tmp_path):
+    """host/raytracer --gpus 0 = frame split over every visible GPU through libskr_mgpu.so (NCCL all-gather when there is
+    more than one); the PPM must be byte-identical to the single-GPU one."""
+    exe = os.path.join(ROOT, "host", "raytracer")
+    if not os.path.exists(os.path.join(ROOT, "skele_raytracer_b200", "libskr_mgpu.so")):
+        pytest.skip("built without NCCL")
+    scn = os.path.join(GOLDEN, "tiny.scn")
+    a, b = tmp_path / "a.ppm", tmp_path / "b.ppm"
+    common = ["--path", scn, "--width", "333", "--height", "187", "--shadow", "--gillum", "4", "--jsample", "2", "--depth", "3", "--seed", "5"]
+    subprocess.run([exe, "--output", str(a)] + common, check=True, capture_output=True, timeout=300)
+    r = subprocess.run([exe, "--output", str(b), "--gpus", "0", "--stats"] + common, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert '"gpus":' in r.stdout
+    assert a.read_bytes() == b.read_bytes()
+
+
 def test_cli_on_reference_scene_files_if_present(port, scenes, tmp_path):
     d = O.REF_SCENES
     if not os.path.isdir(d):
