@@ -293,6 +293,51 @@ def test_bvh_dragon_1080p_equals_brute_force_window(gpu, port, scenes, gscenes):
     assert st.tri_tests < 0.02 * 1920 * 1080 * 10002
 
 
+# ---- size-independent properties at full size ----------------------------------------------------
+
+def test_linearity_in_light_colour_1080p(gpu, scenes):
+    """Blinn-Phong is linear in the light colours: frame(2L) - frame(0) == 2 * (frame(L) - frame(0)) on the pre-clamp float
+    image, at BASELINE size, shadows on (shadowing does not depend on colour)."""
+    import copy
+    base = scenes["bear"]
+    imgs = []
+    for k in (0.0, 1.0, 2.0):
+        sc = copy.deepcopy(base)
+        sc.plights = sc.plights.copy()
+        sc.plights[:, 3:6] *= k
+        gpu.upload(to_gpu_scene(sc))
+        imgs.append(gpu.render(S.Options(width=1920, height=1080, use_shadows=True), want_rgb8=False)[0].astype(np.float64))
+    d1, d2 = imgs[1] - imgs[0], imgs[2] - imgs[0]
+    assert np.abs(d2 - 2 * d1).max() <= 1e-5 * max(1.0, np.abs(d2).max())
+    assert np.abs(d1).max() > 0.1
+
+
+def test_background_only_reaches_miss_pixels_1080p(gpu, scenes):
+    import copy
+    a = copy.deepcopy(scenes["spheres1"])
+    b = copy.deepcopy(scenes["spheres1"])
+    b.background = np.array([0.9, 0.1, 0.4], np.float32)
+    gpu.upload(to_gpu_scene(a))
+    ia = gpu.render(S.Options(width=1920, height=1080, use_shadows=True), want_rgb8=False)[0]
+    gpu.upload(to_gpu_scene(b))
+    ib = gpu.render(S.Options(width=1920, height=1080, use_shadows=True), want_rgb8=False)[0]
+    changed = (ia != ib).any(axis=2)
+    assert np.allclose(ia[changed], a.background) and np.allclose(ib[changed], b.background)
+    assert 0.3 < changed.mean() < 0.9   # spheres1 covers ~40 % of the frame (SURVEY 8e)
+
+
+def test_gi_energy_bookkeeping_matches_ray_counts(gpu, gscenes):
+    """Every queue entry is a sphere hit that gets shaded exactly once: queue entries == sphere hits, and closest-hit rays
+    == primary samples + n * (hits that the reference would expand)."""
+    gpu.upload(gscenes["bear"])
+    w, h, n, depth = 320, 180, 8, 3
+    st = gpu.render(S.Options(width=w, height=h, max_depth=depth, monte_carlo=True, num_path_traces=n, collect_stats=True, seed=4),
+                    want_rgb8=False, want_rgb32=False)[2]
+    assert st.queue_entries == st.sphere_hits
+    # hits at depth >= 2 expand into n children each; depth-1 hits do not.  With depth 3: levels 0 and 1 expand.
+    assert (st.closest_hit_rays - w * h) % n == 0
+
+
 # ---- determinism, chunking, frame split ---------------------------------------------------------
 
 GI_KW = dict(width=160, height=96, max_depth=3, monte_carlo=True, num_path_traces=6, grid_size=2, use_shadows=True, seed=77)
