@@ -233,6 +233,11 @@ def test_many_spheres_use_the_global_memory_path(gpu, port):
     gpu.upload(to_gpu_scene(sc))
     g32, g8, _ = gpu.render(go)
     assert_image_parity(g32, p32, g8, p8, min_ok=0.998, what="1200 spheres")
+    # the wavefront kernels on the same path (shade_expand / fresnel_expand without shared-memory staging)
+    oo, go = opts(width=48, height=27, max_depth=2, monte_carlo=True, num_path_traces=2, use_shadows=True, fresnel=True, seed=3)
+    p32, p8, _, _ = port.render(sc, oo, rng_mode=O.RNG_PHILOX, seed=3)
+    g32, g8, _ = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, min_ok=0.995, what="1200 spheres, gillum + fresnel")
 
 
 @pytest.mark.parametrize("seed", range(4))
