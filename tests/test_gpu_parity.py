@@ -468,14 +468,26 @@ def test_cli_multi_gpu_front_end_on_all_visible_gpus(gpu, tmp_path):
     assert a.read_bytes() == b.read_bytes()
 
 
-def test_cli_on_reference_scene_files_if_present(port, scenes, tmp_path):
+def test_cli_on_reference_scene_files_if_present(port, tmp_path):
+    """The whole front end (.scn text -> flags -> libskr.so -> PPM) on the reference's own scene files: dragon.scn at
+    640x480 must reproduce the reference's golden render byte for byte; the sphere scenes are compared with the oracle
+    fed the scene as host/scene_parser.cpp read it (spheres2's fog record is parsed as intended there)."""
     d = O.REF_SCENES
     if not os.path.isdir(d):
         pytest.skip("oracle/_ref/scenes not shipped")
     exe = os.path.join(ROOT, "host", "raytracer")
-    out = tmp_path / "bear.ppm"
-    subprocess.run([exe, "--path", os.path.join(d, "bear.scn"), "--output", str(out), "--width", "320", "--height", "180", "--shadow"], check=True,
-                   capture_output=True, timeout=300)
-    _, p8, _, _ = port.render(scenes["bear"], O.Options(width=320, height=180, use_shadows=True))
-    got = np.frombuffer(out.read_bytes()[len(b"P6\n320 180\n255\n"):], np.uint8).reshape(180, 320, 3)
-    assert (np.abs(got.astype(int) - p8.astype(int)) <= 1).all(axis=2).mean() >= 0.999
+    out = tmp_path / "dragon.ppm"
+    subprocess.run([exe, "--path", os.path.join(d, "dragon.scn"), "--output", str(out), "--width", "640", "--height", "480", "--depth", "1",
+                    "--parallel", "true"], check=True, capture_output=True, timeout=300)
+    assert hashlib.sha256(out.read_bytes()).hexdigest() == golden_testcpu()[1]
+    for name, flags, kw in [("bear", ["--shadow"], dict(use_shadows=True)), ("spheres1", ["--fov", "45"], dict(fov=45.0)),
+                            ("spheres2", ["--jsample", "2", "--shadow", "--seed", "4"], dict(grid_size=2, use_shadows=True)),
+                            ("test", ["--gillum", "2", "--depth", "2", "--seed", "4"], dict(monte_carlo=True, num_path_traces=2, max_depth=2))]:
+        out = tmp_path / (name + ".ppm")
+        subprocess.run([exe, "--path", os.path.join(d, name + ".scn"), "--output", str(out), "--width", "320", "--height", "180"] + flags, check=True,
+                       capture_output=True, timeout=300)
+        parsed = S.parseScene(os.path.join(d, name + ".scn"))
+        sc = O.Scene(parsed.spheres, parsed.tris, parsed.plights, parsed.dlights, parsed.fogs, parsed.camera, parsed.ambient, parsed.background)
+        _, p8, _, _ = port.render(sc, O.Options(width=320, height=180, **kw), rng_mode=O.RNG_PHILOX, seed=4)
+        got = np.frombuffer(out.read_bytes()[len(b"P6\n320 180\n255\n"):], np.uint8).reshape(180, 320, 3)
+        assert (np.abs(got.astype(int) - p8.astype(int)) <= 1).all(axis=2).mean() >= 0.999, name
