@@ -190,8 +190,11 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         for k, v in zip(keys, t.tolist()):
             cst[k] = int(v)
         gathered = torch.empty(tiles.numel() * world, dtype=torch.uint8, device=dev)
+        from skele_raytracer_b200.distributed import PeerFrames
+        peer_frames = None if os.environ.get("SKR_BENCH_NO_P2P") == "1" else PeerFrames.create(base.height, base.width, dev)
     else:
         cst_local = dict(cst)
+        peer_frames = None
     frame = torch.empty((base.height, base.width, 3), dtype=torch.uint8, device=dev)
     rays = cst["closest_hit_rays"] + cst["shadow_rays"]
 
@@ -203,6 +206,10 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         ws = want_stats or tree
         if world == 1:
             return r.render_device(base, frame.data_ptr(), 0, want_stats=ws)
+        if peer_frames is not None:
+            # collective-free: P2P stores of the finished pixels into every rank's frame + symmetric-memory barrier
+            step.frame, st = peer_frames.render(r, base, rank, world, want_stats=ws)
+            return st
         st = r.render_tiles_device(base, tiles.data_ptr(), want_stats=ws)
         dist.all_gather_into_tensor(gathered, tiles)
         r.deinterleave_device(base, gathered.data_ptr(), frame.data_ptr())
@@ -225,7 +232,7 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
             ev[i][0].record(ext)
             st = step()
             ev[i][1].record(ext)
-            launches += (st.kernel_launches if st is not None else 1) + (1 if world > 1 else 0)
+            launches += (st.kernel_launches if st is not None else 1) + (1 if (world > 1 and peer_frames is None) else 0)
             if st is not None:
                 kernel_ms["primary"] += st.ms_primary
                 kernel_ms["bounce"] += st.ms_bounce
@@ -246,7 +253,7 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
-    out = {"desc": desc, "scene": scene_name, "kw": kw, "rays": rays, "ms_per_step": dev_ms / steps, "value": rays / (dev_ms / steps) / 1e3,
+    out = {"desc": desc, "scene": scene_name, "kw": kw, "rays": rays, "p2p": world > 1 and peer_frames is not None, "ms_per_step": dev_ms / steps, "value": rays / (dev_ms / steps) / 1e3,
            "wall_ms_per_step": (t_end - t_begin) * 1e3 / steps, "launches": launches, "stats": cst, "stats_rank0": cst_local, "t_begin": t_begin, "t_end": t_end,
            "kernel_ms_per_step": {k: v / steps for k, v in kernel_ms.items()},
            "primary_samples": base.width * base.height * (base.grid_size ** 2 if base.grid_size else 1)}
@@ -272,7 +279,7 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
                 r.upload(scene)
                 step()
                 if rank == 0:
-                    torch.from_numpy(host).copy_(frame, non_blocking=False)
+                    torch.from_numpy(host).copy_(getattr(step, "frame", frame), non_blocking=False)
             with torch.cuda.stream(ext):
                 e2e_step()
                 torch.cuda.synchronize()
@@ -290,7 +297,7 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         out["e2e"] = {"value": full_rays * n_e2e / (t1 - t0) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(sc_bytes) * (world if world > 1 else 1),
                       "d2h_bytes_per_step": int(host.nbytes), "ms_per_step": (t1 - t0) * 1e3 / n_e2e, "steps": n_e2e,
                       "path": "skr_scene_upload + skr_render (host arrays in, pinned host RGB8 out), wall clock"
-                      if world == 1 else "per rank skr_scene_upload + skr_render_tiles_device, NCCL all-gather, de-interleave, D2H on rank 0; wall clock, max over ranks"}
+                      if world == 1 else "per rank skr_scene_upload + frame split (same exchange as `value`), D2H of the frame on rank 0; wall clock, max over ranks"}
     return out
 
 
@@ -343,7 +350,7 @@ def main_gpu(args, rank, world, local_rank):
         # the dominant kernel: primary_kernel without --gillum, shade_expand_kernel with it
         dom = "bounce" if m["kw"].get("monte_carlo") else "primary"
         dom_ms = m["kernel_ms_per_step"][dom] or m["ms_per_step"]
-        dom_launches = max(1, round((m["launches"] / steps) - (1 if world > 1 else 0)) if dom == "primary" else round(m["launches"] / steps))
+        dom_launches = 1 if dom == "primary" else max(1, round(m["launches"] / steps))
         achieved = flops / (dom_ms * 1e-3) / 1e12
         frame_bytes = m["kw"]["width"] * m["kw"]["height"] * 3
         line = {
@@ -352,7 +359,10 @@ def main_gpu(args, rank, world, local_rank):
             "config": {"workload": m["desc"], "scene": m["scene"] + " (snapshot of the reference parser's Scene, tests/golden/scenes)", **m["kw"], "seed": SEED,
                        "rays_per_frame": m["rays"], "closest_hit_rays": st["closest_hit_rays"], "shadow_rays": st["shadow_rays"],
                        "l2": "flushed between steps with a 256 MiB memset, outside the per-step CUDA events", "timing": "CUDA events per step on the library stream, summed; max over ranks",
-                       "frame_split": f"{world} ranks, interleaved 32x32 tiles, one NCCL all-gather of RGB8 tiles per frame" if world > 1 else "single GPU, whole frame",
+                       "frame_split": ("single GPU, whole frame" if world == 1 else
+                                       f"{world} ranks, interleaved 32x32 tiles; finished pixels stored straight into every rank's frame over NVLink "
+                                       "(skr_render_peers_device, torch symmetric memory), one symmetric-memory barrier per frame" if m["p2p"] else
+                                       f"{world} ranks, interleaved 32x32 tiles, one NCCL all-gather of RGB8 tiles per frame + de-interleave kernel"),
                        "wall_ms_per_step_incl_flush": m["wall_ms_per_step"]},
             "clocks": clocks,
             "e2e": m.get("e2e"),

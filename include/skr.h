@@ -152,6 +152,14 @@ int64_t skr_tiles_bytes(const skr_options *opt);
 int skr_render_tiles_device(skr_ctx *ctx, const skr_options *opt, void *d_tiles, skr_stats *stats);
 int skr_deinterleave_device(skr_ctx *ctx, const skr_options *opt, const void *d_gathered, void *d_rgb8);
 
+/* Frame split WITHOUT a collective: renders this rank's tiles and stores every finished pixel straight into n_frames
+ * row-major RGB8 frames (H*W*3 bytes each) -- typically one per GPU of the box, the peers' buffers mapped into this
+ * process (CUDA IPC, cuMem fabric handles, torch symmetric memory ...).  The stores to peer GPUs travel over NVLink
+ * while the kernel is still tracing, so no gather and no de-interleave pass remain; the caller runs the cross-rank
+ * barrier after the call (all ranks' kernels complete => every frame is whole) and double-buffers the frames if it
+ * reads one while the next is being rendered.  1 <= n_frames <= 8.  Asynchronous like skr_render_device. */
+int skr_render_peers_device(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, skr_stats *stats);
+
 /* The library's stream as a cudaStream_t (so that callers can order their own work / events after it),
  * and a blocking wait for it. */
 void *skr_stream(skr_ctx *ctx);

@@ -205,6 +205,7 @@ class Renderer:
         L.skr_tiles_bytes.argtypes = [C.POINTER(_Options)]
         L.skr_render_tiles_device.argtypes = [C.c_void_p, C.POINTER(_Options), C.c_void_p, C.POINTER(Stats)]
         L.skr_deinterleave_device.argtypes = [C.c_void_p, C.POINTER(_Options), C.c_void_p, C.c_void_p]
+        L.skr_render_peers_device.argtypes = [C.c_void_p, C.POINTER(_Options), C.POINTER(C.c_void_p), C.c_int, C.POINTER(Stats)]
         L.skr_stream.restype = C.c_void_p
         L.skr_stream.argtypes = [C.c_void_p]
         L.skr_sync.argtypes = [C.c_void_p]
@@ -269,6 +270,15 @@ class Renderer:
         o = option._c()
         self._check(self.lib.skr_render_tiles_device(self.ctx, C.byref(o), d_tiles, C.byref(st) if want_stats else None),
                     "skr_render_tiles_device")
+        return st
+
+    def render_peers_device(self, option: Options, d_frames, want_stats: bool = True):
+        """skr_render_peers_device: d_frames = device pointers (ints) of the row-major RGB8 frames to fill."""
+        st = Stats() if want_stats else None
+        o = option._c()
+        arr = (C.c_void_p * len(d_frames))(*[int(p) for p in d_frames])
+        self._check(self.lib.skr_render_peers_device(self.ctx, C.byref(o), arr, len(d_frames), C.byref(st) if want_stats else None),
+                    "skr_render_peers_device")
         return st
 
     def deinterleave_device(self, option: Options, d_gathered: int, d_rgb8: int) -> None:

@@ -1140,6 +1140,32 @@ int skr_render_tiles_device(skr_ctx *ctx, const skr_options *opt, void *d_tiles,
 	return render_common(ctx, opt, pl, stats);
 }
 
+int skr_render_peers_device(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, skr_stats *stats)
+{
+	REQUIRE_CTX();
+	REQUIRE_SCENE();
+	if(!d_frames || n_frames < 1 || n_frames > 8)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_render_peers_device: between 1 and 8 frame pointers are required (got %d)", n_frames);
+	}
+	Plan pl;
+	int rc = make_plan(ctx, opt, pl);
+	if(rc)
+	{
+		return rc;
+	}
+	for(int k = 0; k < n_frames; k++)
+	{
+		if(!d_frames[k])
+		{
+			return fail(ctx, SKR_ERR_ARG, "skr_render_peers_device: frame pointer %d is null", k);
+		}
+		pl.fp.peers[k] = static_cast<uint8_t *>(d_frames[k]);
+	}
+	pl.fp.n_peers = n_frames;
+	return render_common(ctx, opt, pl, stats);
+}
+
 int skr_deinterleave_device(skr_ctx *ctx, const skr_options *opt, const void *d_gathered, void *d_rgb8)
 {
 	REQUIRE_CTX();

@@ -49,6 +49,8 @@ struct FrameParams
 	uint8_t *rgb8;	 // row-major frame or null
 	float *rgb32;	 // row-major frame or null
 	uint8_t *tiles8; // compact tile-major buffer or null
+	uint8_t *peers[8]; // skr_render_peers_device: row-major RGB8 frames (one per GPU of the box, peer-mapped) or null
+	int n_peers;
 	long long *accum; // 3 per local pixel (gi only)
 	unsigned long long *counters; // 8 device counters (STATS)
 	int *err;
@@ -119,6 +121,20 @@ SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, 
 		o[0]	   = quantise(c.x);
 		o[1]	   = quantise(c.y);
 		o[2]	   = quantise(c.z);
+	}
+	if(fp.n_peers > 0)
+	{
+		// frame split without a collective: the finished pixel goes straight into every GPU's frame; the stores to the
+		// peers travel over NVLink while the rest of the kernel is still tracing
+		const uint8_t r = quantise(c.x), g = quantise(c.y), b = quantise(c.z);
+		const size_t at = 3 * ((size_t) p.y * fp.width + p.x);
+		for(int k = 0; k < fp.n_peers; k++)
+		{
+			uint8_t *o = fp.peers[k] + at;
+			o[0]	   = r;
+			o[1]	   = g;
+			o[2]	   = b;
+		}
 	}
 	if(fp.tiles8)
 	{

@@ -46,3 +46,41 @@ def gather_frame_cpu(local_compact: np.ndarray, width: int, height: int, rank: i
     dist.all_gather(outs, loc)
     gathered = torch.cat(outs).numpy()
     return T.deinterleave(gathered, width, height, world, tile)
+
+
+class PeerFrames:
+    """Frame split without a collective (skr_render_peers_device): every rank's kernel stores its finished pixels
+    straight into every rank's frame over NVLink; a symmetric-memory barrier (a few microseconds) ends the frame.
+    Two frames alternate so that one can be read while the next is rendered.  Needs torch symmetric memory (P2P);
+    `PeerFrames.create` returns None where that is unavailable and callers fall back to the all-gather path."""
+
+    def __init__(self, bufs, hdls):
+        self.bufs, self.hdls, self.i = bufs, hdls, 0
+
+    @staticmethod
+    def create(height: int, width: int, device, group=None):
+        try:
+            import torch
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+
+            group = group or dist.group.WORLD
+            bufs = [symm_mem.empty((height * width * 3,), dtype=torch.uint8, device=device) for _ in range(2)]
+            hdls = [symm_mem.rendezvous(b, group) for b in bufs]
+            if any(len(h.buffer_ptrs) != dist.get_world_size(group) for h in hdls):
+                return None
+            return PeerFrames(bufs, hdls)
+        except Exception:  # no P2P / symmetric memory in this environment
+            return None
+
+    def render(self, renderer, option, rank: int, world: int, want_stats: bool = False):
+        """Enqueue one frame; returns (frame tensor view HxWx3 that is whole once the current stream reaches this point,
+        Stats or None)."""
+        import dataclasses
+
+        k = self.i & 1
+        self.i += 1
+        opt = dataclasses.replace(option, rank=rank, world=world)
+        st = renderer.render_peers_device(opt, self.hdls[k].buffer_ptrs, want_stats=want_stats)
+        self.hdls[k].barrier()
+        return self.bufs[k].view(option.height, option.width, 3), st
