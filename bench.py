@@ -192,6 +192,10 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         gathered = torch.empty(tiles.numel() * world, dtype=torch.uint8, device=dev)
         from skele_raytracer_b200.distributed import PeerFrames
         peer_frames = None if os.environ.get("SKR_BENCH_NO_P2P") == "1" else PeerFrames.create(base.height, base.width, dev)
+        ok = torch.tensor([1 if peer_frames is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank takes the same path
+        if int(ok.item()) == 0:
+            peer_frames = None
     else:
         cst_local = dict(cst)
         peer_frames = None
