@@ -403,6 +403,31 @@ def test_compact_tiles_and_deinterleave_on_device(gpu, gscenes, world, tile):
     assert np.array_equal(frame.cpu().numpy(), full8)
 
 
+def test_render_peers_device_fills_every_frame(gpu, gscenes):
+    """skr_render_peers_device: each rank stores its pixels into every frame it is given (here: three local buffers
+    standing in for the GPUs of a box); after all ranks have rendered, every frame is the whole image."""
+    import torch
+    kw = dict(width=200, height=90, grid_size=2, use_shadows=True, seed=2)
+    gpu.upload(gscenes["spheres2"])
+    _, full8, _ = gpu.render(S.Options(**kw), want_rgb32=False)
+    frames = [torch.zeros((90, 200, 3), dtype=torch.uint8, device="cuda") for _ in range(3)]
+    for r in range(4):
+        gpu.render_peers_device(S.Options(rank=r, world=4, tile=16, **kw), [f.data_ptr() for f in frames])
+    gpu.sync()
+    for f in frames:
+        assert np.array_equal(f.cpu().numpy(), full8)
+    with pytest.raises(S.SkrError, match="between 1 and 8"):
+        gpu.render_peers_device(S.Options(**kw), [frames[0].data_ptr()] * 9)
+    # --gillum frames go through resolve_kernel -> same stores
+    kw = dict(width=96, height=54, max_depth=2, monte_carlo=True, num_path_traces=3, seed=2)
+    _, full8, _ = gpu.render(S.Options(**kw), want_rgb32=False)
+    frames = [torch.zeros((54, 96, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    for r in range(2):
+        gpu.render_peers_device(S.Options(rank=r, world=2, **kw), [f.data_ptr() for f in frames])
+    gpu.sync()
+    assert all(np.array_equal(f.cpu().numpy(), full8) for f in frames)
+
+
 def test_render_device_matches_host_render(gpu, gscenes):
     import torch
     gpu.upload(gscenes["bear"])
