@@ -252,12 +252,14 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
                 st = step(want_stats=True)
                 kernel_ms["primary"] += st.ms_primary
             torch.cuda.synchronize()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(per_step)
     if world > 1:
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
     out = {"desc": desc, "scene": scene_name, "kw": kw, "rays": rays, "p2p": world > 1 and peer_frames is not None, "ms_per_step": dev_ms / steps, "value": rays / (dev_ms / steps) / 1e3,
+           "ms_per_step_min": min(per_step), "ms_per_step_median": sorted(per_step)[len(per_step) // 2],
            "wall_ms_per_step": (t_end - t_begin) * 1e3 / steps, "launches": launches, "stats": cst, "stats_rank0": cst_local, "t_begin": t_begin, "t_end": t_end,
            "kernel_ms_per_step": {k: v / steps for k, v in kernel_ms.items()},
            "primary_samples": base.width * base.height * (base.grid_size ** 2 if base.grid_size else 1)}
@@ -338,7 +340,8 @@ def main_gpu(args, rank, world, local_rank):
             k = 3 if w == "c5" else 10
             o = measure_gpu(S, torch, dist, r, w, k, 3, rank, world, flush_buf, want_e2e=False)
             fl = algorithmic_flops(o["stats"], o["primary_samples"])
-            others[w] = {"workload": o["desc"], "ms_per_frame": o["ms_per_step"], "mrays_per_s": o["value"], "rays_per_frame": o["rays"],
+            others[w] = {"workload": o["desc"], "ms_per_frame": o["ms_per_step"], "ms_per_frame_median": o["ms_per_step_median"],
+                         "ms_per_frame_min": o["ms_per_step_min"], "mrays_per_s": o["value"], "rays_per_frame": o["rays"],
                          "fp32_tflops_algorithmic": fl / (o["ms_per_step"] * 1e-3) / 1e12, "frac_of_fp32_peak": fl / (o["ms_per_step"] * 1e-3) / 1e12 / fp32_peak,
                          "kernel_launches_per_frame": o["launches"] / k}
 
@@ -367,6 +370,7 @@ def main_gpu(args, rank, world, local_rank):
                                        f"{world} ranks, interleaved 32x32 tiles; finished pixels stored straight into every rank's frame over NVLink "
                                        "(skr_render_peers_device, torch symmetric memory), one symmetric-memory barrier per frame" if m["p2p"] else
                                        f"{world} ranks, interleaved 32x32 tiles, one NCCL all-gather of RGB8 tiles per frame + de-interleave kernel"),
+                       "ms_per_step_median_this_rank": m["ms_per_step_median"], "ms_per_step_min_this_rank": m["ms_per_step_min"],
                        "wall_ms_per_step_incl_flush": m["wall_ms_per_step"]},
             "clocks": clocks,
             "e2e": m.get("e2e"),
