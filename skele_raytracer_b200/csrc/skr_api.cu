@@ -571,7 +571,6 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 {
 	FrameParams &fp = pl.fp;
 	cudaStream_t st = ctx->stream;
-	const size_t smem = ctx->smem_bytes;
 	const bool tree = fp.gi || fp.fresnel;
 	if(tree)
 	{
@@ -760,7 +759,6 @@ const char *skr_last_error(const skr_ctx *ctx)
 
 int skr_init(int device, skr_ctx **out)
 {
-	skr_ctx *ctx = nullptr;
 	if(!out)
 	{
 		return fail(nullptr, SKR_ERR_ARG, "skr_init: out is null");
@@ -790,7 +788,6 @@ int skr_init(int device, skr_ctx **out)
 	}
 	skr_ctx *c = new skr_ctx();
 	c->device  = device;
-	ctx		   = c;
 	auto bail  = [&](cudaError_t err, const char *what) {
 		 fail(nullptr, SKR_ERR_CUDA, "skr_init: %s: %s", what, cudaGetErrorString(err));
 		 skr_destroy(c);

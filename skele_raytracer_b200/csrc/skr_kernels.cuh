@@ -153,16 +153,19 @@ SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, 
 template <bool SMEM>
 SKR_DEV const float4 *stage_scene(const SceneView &sv, float4 *smem)
 {
-	if(!SMEM)
+	if constexpr(!SMEM)
 	{
 		return sv.blob;
 	}
-	for(int i = threadIdx.x; i < sv.blob_f4; i += blockDim.x)
+	else
 	{
-		smem[i] = __ldg(sv.blob + i);
+		for(int i = threadIdx.x; i < sv.blob_f4; i += blockDim.x)
+		{
+			smem[i] = __ldg(sv.blob + i);
+		}
+		__syncthreads();
+		return smem;
 	}
-	__syncthreads();
-	return smem;
 }
 
 template <bool STATS>
