@@ -20,16 +20,135 @@ struct MaterialState // reference: src/material.h:9-26 defaults
 	float ior			  = 1.0f;
 };
 
+// strtof-equivalent fast path for the numbers scene files actually contain ("-12.5", ".043", "1e-3"): up to 15
+// significant digits and a small decimal exponent are converted exactly in double (mantissa and 10^k are both exact
+// doubles, one correctly rounded multiply or divide) and then rounded to float.  The only way that double rounding
+// can differ from strtof's single rounding is a double that sits within one ulp of a float rounding midpoint; that
+// case -- and anything unusual (hex, inf/nan, long mantissas, big exponents) -- goes to strtof itself.
+// tests/test_host_parser.py checks bit equality with strtof on random decimal strings and on the reference scenes.
+inline bool fast_strtof(const char *p, const char **end, float *out)
+{
+	static const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+	const char *q = p;
+	while(*q == ' ' || *q == '\t' || *q == '\n' || *q == '\r' || *q == '\v' || *q == '\f')
+	{
+		q++;
+	}
+	bool negative = false;
+	if(*q == '-' || *q == '+')
+	{
+		negative = *q == '-';
+		q++;
+	}
+	unsigned long long mant = 0;
+	int digits = 0, frac = 0;
+	bool any = false;
+	while(*q >= '0' && *q <= '9')
+	{
+		any = true;
+		if(mant || *q != '0')
+		{
+			if(++digits > 15)
+			{
+				return false;
+			}
+			mant = mant * 10 + (unsigned) (*q - '0');
+		}
+		q++;
+	}
+	if(*q == '.')
+	{
+		q++;
+		while(*q >= '0' && *q <= '9')
+		{
+			any = true;
+			if(mant || *q != '0')
+			{
+				if(++digits > 15)
+				{
+					return false;
+				}
+				mant = mant * 10 + (unsigned) (*q - '0');
+			}
+			frac++;
+			q++;
+		}
+	}
+	if(!any)
+	{
+		return false; // not a plain decimal (or not a number at all): let strtof decide
+	}
+	int e10 = 0;
+	if(*q == 'e' || *q == 'E')
+	{
+		const char *r = q + 1;
+		bool eneg	  = false;
+		if(*r == '-' || *r == '+')
+		{
+			eneg = *r == '-';
+			r++;
+		}
+		if(*r >= '0' && *r <= '9')
+		{
+			int ev = 0;
+			while(*r >= '0' && *r <= '9')
+			{
+				if(ev > 1000)
+				{
+					return false;
+				}
+				ev = ev * 10 + (*r - '0');
+				r++;
+			}
+			e10 = eneg ? -ev : ev;
+			q	= r;
+		}
+	}
+	if(*q == 'x' || *q == 'X' || ((*q | 32) >= 'a' && (*q | 32) <= 'z' && *q != 'e' && *q != 'E'))
+	{
+		return false; // "0x..", "inf", "nan", "1f"... : strtof's business
+	}
+	const int k = e10 - frac;
+	if(k < -22 || k > 22)
+	{
+		return false;
+	}
+	double d = (double) mant;
+	d		 = k < 0 ? d / P10[-k] : d * P10[k];
+	if(d > 3.0e38 || (d != 0.0 && d < 1.0e-37))
+	{
+		return false; // overflow / subnormal range: strtof sets errno and rounds specially
+	}
+	unsigned long long bits;
+	memcpy(&bits, &d, sizeof bits);
+	const unsigned low = (unsigned) (bits & 0x1fffffffu); // the 29 bits a float drops
+	if(low >= 0x0fffffffu && low <= 0x10000001u)
+	{
+		return false; // within one double ulp of a float midpoint
+	}
+	*out = (float) (negative ? -d : d);
+	*end = q;
+	return true;
+}
+
 // Reads up to `max` floats after the command word; returns how many were converted (sscanf %f semantics:
 // stops at the first token that is not a number).
-int read_floats(const char *p, float *out, int max)
+int read_floats_impl(const char *p, float *out, int max)
 {
 	int n = 0;
 	while(n < max)
 	{
+		const char *fend = nullptr;
+		float v;
+		if(fast_strtof(p, &fend, &v))
+		{
+			out[n++] = v;
+			p		 = fend;
+			continue;
+		}
 		char *end = nullptr;
 		errno	  = 0;
-		float v	  = strtof(p, &end);
+		v		  = strtof(p, &end);
 		if(end == p)
 		{
 			break;
@@ -40,6 +159,11 @@ int read_floats(const char *p, float *out, int max)
 	return n;
 }
 } // namespace
+
+int read_floats(const char *p, float *out, int max)
+{
+	return read_floats_impl(p, out, max);
+}
 
 skr_scene_desc HostScene::desc() const
 {
@@ -81,13 +205,24 @@ bool parse_scn(const std::string &path, HostScene &scene, std::string &error, co
 		{
 			continue; // src/scene.cpp:31-35: only a '#' in column 0 starts a comment
 		}
+		// first word of the line = the command (what the reference reads with sscanf("%s "))
 		char command[100];
-		int consumed = 0;
-		if(sscanf(line, "%99s%n", command, &consumed) < 1)
+		const char *c = line;
+		while(*c == ' ' || *c == '\t' || *c == '\r' || *c == '\n' || *c == '\v' || *c == '\f')
+		{
+			c++;
+		}
+		int clen = 0;
+		while(*c && !(*c == ' ' || *c == '\t' || *c == '\r' || *c == '\n' || *c == '\v' || *c == '\f') && clen < 99)
+		{
+			command[clen++] = *c++;
+		}
+		command[clen] = 0;
+		if(clen == 0)
 		{
 			continue; // blank line
 		}
-		const char *args = line + consumed;
+		const char *args = c;
 		float f[16];
 		for(float &v : f)
 		{
@@ -238,6 +373,15 @@ bool parse_scn(const std::string &path, HostScene &scene, std::string &error, co
 	return ok;
 }
 
+} // namespace skr_host
+
+extern "C" int skr_host_read_floats(const char *text, float *out, int max)
+{
+	return skr_host::read_floats(text, out, max);
+}
+
+namespace skr_host
+{
 bool write_ppm(const std::string &path, int width, int height, const unsigned char *rgb8, std::string &error)
 {
 	FILE *fp = fopen(path.c_str(), "wb");

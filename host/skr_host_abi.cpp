@@ -53,6 +53,9 @@ void skr_host_scene_free(skr_host_scene *h)
 	delete h;
 }
 
+// the reader's number conversion, exposed so that the tests can compare it with strtof bit for bit
+int skr_host_read_floats(const char *text, float *out, int max);
+
 int skr_host_write_ppm(const char *path, int width, int height, const unsigned char *rgb8)
 {
 	std::string err;

@@ -95,3 +95,40 @@ def test_write_ppm_bytes(tmp_path):
     img = np.arange(2 * 3 * 3, dtype=np.uint8).reshape(2, 3, 3)
     S.write_ppm(str(tmp_path / "o.ppm"), img)
     assert (tmp_path / "o.ppm").read_bytes() == b"P6\n3 2\n255\n" + img.tobytes()
+
+
+def test_number_conversion_is_strtof_bit_for_bit():
+    """The reader converts plain decimals on a fast exact path and hands everything else to strtof; either way the float
+    must be the one the reference's sscanf("%f") produces."""
+    import ctypes as C
+    import random
+    import struct
+
+    from skele_raytracer_b200 import api
+    L = api._host_lib()
+    L.skr_host_read_floats.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_int]
+    libc = C.CDLL("libc.so.6")
+    libc.strtof.restype = C.c_float
+    libc.strtof.argtypes = [C.c_char_p, C.c_void_p]
+    rnd = random.Random(7)
+    buf = (C.c_float * 4)()
+    cases = ["0", "-0", "0.0", ".5", "5.", "+3", "1e10", "1E-10", "1e38", "3.5e38", "1e-45", "16777217", "0.1", "1.0000000596046448",
+             "1.00000005960464478", "8.5e-46", "1e23", "123456789012345678", "0.000000000000000000001", "1e", "1e+", "0x10", "12abc"]
+    for _ in range(60000):
+        k = rnd.random()
+        if k < 0.4:
+            cases.append("%.*f" % (rnd.randint(0, 9), rnd.uniform(-100, 100)))
+        elif k < 0.6:
+            cases.append("%.*e" % (rnd.randint(0, 14), rnd.uniform(-1, 1) * 10 ** rnd.randint(-30, 30)))
+        elif k < 0.8:
+            cases.append(str(rnd.randint(-10 ** rnd.randint(1, 15), 10 ** rnd.randint(1, 15))))
+        else:
+            cases.append("%s%s.%s" % (rnd.choice(["", "-", "+"]), rnd.choice(["", "0", "12", "000"]),
+                                      "".join(rnd.choice("0123456789") for _ in range(rnd.randint(1, 12)))))
+    for sv in cases:
+        n = L.skr_host_read_floats(sv.encode(), buf, 1)
+        ref = libc.strtof(sv.encode(), None)
+        assert n == 1 and struct.pack("f", buf[0]) == struct.pack("f", ref), sv
+    # several numbers on a line, CRLF, trailing junk stops the scan like sscanf
+    assert L.skr_host_read_floats(b" 1 -2.5\t3e1 .25 x 7\r\n", buf, 4) == 4 and list(buf) == [1.0, -2.5, 30.0, 0.25]
+    assert L.skr_host_read_floats(b" 1 2 abc 3", buf, 4) == 2
