@@ -56,6 +56,8 @@ struct skr_ctx
 	float *d_tris_raw = nullptr;
 	float4 *d_tri_v = nullptr;
 	float4 *d_bvh = nullptr;
+	size_t blob_bytes = 0, tris_raw_bytes = 0, tri_v_bytes = 0, bvh_bytes = 0, scratch_bytes = 0;
+	char *d_scratch = nullptr; // LBVH build scratch, kept between uploads
 	size_t smem_bytes = 0;
 
 	// frame buffers
@@ -278,17 +280,8 @@ int build_bvh(skr_ctx *ctx, int T)
 	cudaStream_t st = ctx->stream;
 	const int B		= 256;
 	const int gridT = (T + B - 1) / B;
-	if(ctx->d_tri_v)
-	{
-		cudaFree(ctx->d_tri_v);
-		ctx->d_tri_v = nullptr;
-	}
-	if(ctx->d_bvh)
-	{
-		cudaFree(ctx->d_bvh);
-		ctx->d_bvh = nullptr;
-	}
-	CK(cudaMalloc(&ctx->d_tri_v, sizeof(float4) * 3 * (size_t) T));
+	// persistent buffers grow on demand and are reused by later uploads (an e2e loop re-uploads the same scene)
+	CK(ensure(ctx->d_tri_v, ctx->tri_v_bytes, sizeof(float4) * 3 * (size_t) T));
 	const char *nobvh = getenv("SKR_NO_BVH");
 	if((nobvh && nobvh[0] == '1') || T == 1)
 	{
@@ -298,49 +291,37 @@ int build_bvh(skr_ctx *ctx, int T)
 		ctx->sv.bvh_root_is_leaf = 0;
 		return SKR_OK;
 	}
-	float4 *box_lo = nullptr, *box_hi = nullptr, *node_lo = nullptr, *node_hi = nullptr;
-	float *scene_box = nullptr;
-	unsigned long long *keys[2] = {nullptr, nullptr};
-	unsigned *vals[2] = {nullptr, nullptr};
-	unsigned *hist = nullptr;
-	int2 *children = nullptr;
-	int *parent = nullptr, *flags = nullptr;
+	CK(ensure(ctx->d_bvh, ctx->bvh_bytes, sizeof(float4) * 4 * (size_t) (T - 1)));
 	const int nwarps  = (T + SORT_ITEMS_PER_WARP - 1) / SORT_ITEMS_PER_WARP;
 	const int sblocks = (nwarps + SORT_WARPS - 1) / SORT_WARPS;
-	int rc = SKR_OK;
-	auto cleanup = [&]() {
-		cudaFree(box_lo), cudaFree(box_hi), cudaFree(node_lo), cudaFree(node_hi), cudaFree(scene_box);
-		cudaFree(keys[0]), cudaFree(keys[1]), cudaFree(vals[0]), cudaFree(vals[1]), cudaFree(hist);
-		cudaFree(children), cudaFree(parent), cudaFree(flags);
+
+	// build scratch: one arena, carved with 256-byte alignment
+	size_t off = 0;
+	auto carve = [&off](size_t bytes) {
+		const size_t at = off;
+		off += (bytes + 255) & ~(size_t) 255;
+		return at;
 	};
-#define CKB(call)                                                                                                   \
-	do                                                                                                               \
-	{                                                                                                                \
-		cudaError_t e_ = (call);                                                                                     \
-		if(e_ != cudaSuccess)                                                                                        \
-		{                                                                                                            \
-			rc = fail(ctx, SKR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));          \
-			cleanup();                                                                                               \
-			return rc;                                                                                               \
-		}                                                                                                            \
-	} while(0)
-	CKB(cudaMalloc(&box_lo, sizeof(float4) * T));
-	CKB(cudaMalloc(&box_hi, sizeof(float4) * T));
-	CKB(cudaMalloc(&node_lo, sizeof(float4) * T));
-	CKB(cudaMalloc(&node_hi, sizeof(float4) * T));
-	CKB(cudaMalloc(&scene_box, sizeof(float) * 6));
-	CKB(cudaMalloc(&keys[0], sizeof(unsigned long long) * T));
-	CKB(cudaMalloc(&keys[1], sizeof(unsigned long long) * T));
-	CKB(cudaMalloc(&vals[0], sizeof(unsigned) * T));
-	CKB(cudaMalloc(&vals[1], sizeof(unsigned) * T));
-	CKB(cudaMalloc(&hist, sizeof(unsigned) * 256 * (size_t) nwarps));
-	CKB(cudaMalloc(&children, sizeof(int2) * T));
-	CKB(cudaMalloc(&parent, sizeof(int) * 2 * (size_t) T));
-	CKB(cudaMalloc(&flags, sizeof(int) * T));
-	CKB(cudaMalloc(&ctx->d_bvh, sizeof(float4) * 4 * (size_t) (T - 1)));
+	const size_t o_box_lo = carve(sizeof(float4) * T), o_box_hi = carve(sizeof(float4) * T);
+	const size_t o_node_lo = carve(sizeof(float4) * T), o_node_hi = carve(sizeof(float4) * T);
+	const size_t o_scene = carve(sizeof(float) * 6);
+	const size_t o_k0 = carve(sizeof(unsigned long long) * T), o_k1 = carve(sizeof(unsigned long long) * T);
+	const size_t o_v0 = carve(sizeof(unsigned) * T), o_v1 = carve(sizeof(unsigned) * T);
+	const size_t o_hist = carve(sizeof(unsigned) * 256 * (size_t) nwarps);
+	const size_t o_children = carve(sizeof(int2) * T), o_parent = carve(sizeof(int) * 2 * (size_t) T), o_flags = carve(sizeof(int) * T);
+	CK(ensure(ctx->d_scratch, ctx->scratch_bytes, off));
+	char *base = ctx->d_scratch;
+	float4 *box_lo = (float4 *) (base + o_box_lo), *box_hi = (float4 *) (base + o_box_hi);
+	float4 *node_lo = (float4 *) (base + o_node_lo), *node_hi = (float4 *) (base + o_node_hi);
+	float *scene_box = (float *) (base + o_scene);
+	unsigned long long *keys[2] = {(unsigned long long *) (base + o_k0), (unsigned long long *) (base + o_k1)};
+	unsigned *vals[2] = {(unsigned *) (base + o_v0), (unsigned *) (base + o_v1)};
+	unsigned *hist = (unsigned *) (base + o_hist);
+	int2 *children = (int2 *) (base + o_children);
+	int *parent = (int *) (base + o_parent), *flags = (int *) (base + o_flags);
 
 	const float init_box[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
-	CKB(cudaMemcpyAsync(scene_box, init_box, sizeof init_box, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(scene_box, init_box, sizeof init_box, cudaMemcpyHostToDevice, st));
 	tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box);
 	morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0]);
 	int cur = 0;
@@ -352,14 +333,11 @@ int build_bvh(skr_ctx *ctx, int T)
 		sort_scatter_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], T, shift, hist, nwarps, keys[cur ^ 1], vals[cur ^ 1]);
 		cur ^= 1;
 	}
-	CKB(cudaMemsetAsync(flags, 0, sizeof(int) * T, st));
+	CK(cudaMemsetAsync(flags, 0, sizeof(int) * T, st));
 	karras_kernel<<<gridT, B, 0, st>>>(keys[cur], T, children, parent);
 	refit_kernel<<<gridT, B, 0, st>>>(T, vals[cur], box_lo, box_hi, children, parent, node_lo, node_hi, flags, ctx->d_bvh);
 	gather_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, vals[cur], T, ctx->d_tri_v);
-	CKB(cudaGetLastError());
-	CKB(cudaStreamSynchronize(st));
-	cleanup();
-#undef CKB
+	CK(cudaGetLastError());
 	ctx->sv.bvh				 = ctx->d_bvh;
 	ctx->sv.bvh_root_is_leaf = 0;
 	return SKR_OK;
@@ -833,7 +811,7 @@ void skr_destroy(skr_ctx *ctx)
 	{
 		cudaStreamSynchronize(ctx->stream);
 	}
-	cudaFree(ctx->d_blob), cudaFree(ctx->d_tris_raw), cudaFree(ctx->d_tri_v), cudaFree(ctx->d_bvh);
+	cudaFree(ctx->d_blob), cudaFree(ctx->d_tris_raw), cudaFree(ctx->d_tri_v), cudaFree(ctx->d_bvh), cudaFree(ctx->d_scratch);
 	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
 	for(Queue &q : ctx->queues)
 	{
@@ -997,12 +975,9 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	sv.background = make_float3(sc->background[0], sc->background[1], sc->background[2]);
 	sv.err		  = ctx->d_err;
 
-	if(ctx->d_blob)
-	{
-		cudaFree(ctx->d_blob);
-		ctx->d_blob = nullptr;
-	}
-	CK(cudaMalloc(&ctx->d_blob, sizeof(float4) * blob.size()));
+	// an earlier asynchronous frame may still be reading the old blob on this stream: the copies below are
+	// stream-ordered behind it, and buffers are only ever re-allocated through ensure() (cudaFree synchronises)
+	CK(ensure(ctx->d_blob, ctx->blob_bytes, sizeof(float4) * blob.size()));
 	CK(cudaMemcpyAsync(ctx->d_blob, blob.data(), sizeof(float4) * blob.size(), cudaMemcpyHostToDevice, ctx->stream));
 	sv.blob			= ctx->d_blob;
 	const size_t bb = sizeof(float4) * blob.size();
@@ -1014,16 +989,11 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		return rc;
 	}
 
-	if(ctx->d_tris_raw)
-	{
-		cudaFree(ctx->d_tris_raw);
-		ctx->d_tris_raw = nullptr;
-	}
 	sv.tri_v = nullptr;
 	sv.bvh	 = nullptr;
 	if(T > 0)
 	{
-		CK(cudaMalloc(&ctx->d_tris_raw, sizeof(float) * 9 * (size_t) T));
+		CK(ensure(ctx->d_tris_raw, ctx->tris_raw_bytes, sizeof(float) * 9 * (size_t) T));
 		CK(cudaMemcpyAsync(ctx->d_tris_raw, sc->tris, sizeof(float) * 9 * (size_t) T, cudaMemcpyHostToDevice, ctx->stream));
 		rc = build_bvh(ctx, T);
 		if(rc)
