@@ -369,6 +369,12 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 		const float3 direct = direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, sidx, hp, n, cnt);
 		// with --gillum: (direct / pi) * kd (src/raytrace.h:213); fresnel-only trees return direct as is (:103, :218)
 		contrib = fp.gi ? thr * kd * (direct * 0.318309886183790672f) : thr * direct;
+		if(fp.gi && fp.n_gi == 0)
+		{
+			// `--gillum 0`: the reference divides its empty sum by zero paths (total_colour /= num_rays, src/raytrace.h:133),
+			// so every shaded hit is NaN and the pixel quantises to 255.  Reproduced as such.
+			contrib = f3(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+		}
 	}
 	if(expand)
 	{
@@ -540,6 +546,10 @@ __global__ void __launch_bounds__(SKR_BLOCK) resolve_kernel(const FrameParams fp
 		return;
 	}
 	float3 c = f3(from_fixed(fp.accum[3 * lp + 0]), from_fixed(fp.accum[3 * lp + 1]), from_fixed(fp.accum[3 * lp + 2]));
+	// to_fixed() parks NaN contributions at +1e9 (far above any radiance sum); hand them back as NaN
+	c.x = c.x > 4.0e8f ? CUDART_NAN_F : c.x;
+	c.y = c.y > 4.0e8f ? CUDART_NAN_F : c.y;
+	c.z = c.z > 4.0e8f ? CUDART_NAN_F : c.z;
 	if(fp.grid > 0)
 	{
 		const float n2 = (float) fp.spp;

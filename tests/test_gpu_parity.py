@@ -199,6 +199,16 @@ def test_depth_zero_is_black(gpu, gscenes):
     assert not g32.any()
 
 
+def test_gillum_zero_paths_is_nan_like_the_reference(gpu, port, scenes, gscenes):
+    """`--gillum 0`: the reference's empty Monte-Carlo sum is divided by 0 -> NaN on every sphere hit -> byte 255."""
+    oo, go = opts(width=64, height=36, max_depth=2, monte_carlo=True, num_path_traces=0)
+    p32, p8, _, _ = port.render(scenes["spheres1"], oo, rng_mode=O.RNG_PHILOX, seed=0)
+    gpu.upload(gscenes["spheres1"])
+    g32, g8, _ = gpu.render(go)
+    assert np.isnan(p32).any() and np.array_equal(np.isnan(g32), np.isnan(p32))
+    assert np.array_equal(g8, p8) and (g8[np.isnan(g32)] == 255).all()
+
+
 @pytest.mark.parametrize("w,h", [(1, 1), (37, 23), (33, 65), (8, 4), (257, 3)])
 def test_ragged_sizes(gpu, port, scenes, gscenes, w, h):
     oo, go = opts(width=w, height=h, use_shadows=True)
