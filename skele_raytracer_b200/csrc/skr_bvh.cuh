@@ -8,27 +8,36 @@
 //     -> the query is over the whole LINE t in (-inf, tmax), not a ray;
 //   * any accepted hit gives the same answer -> any-hit: stop at the first one.
 //
-// Node layout (built by skr_bvh_build.cuh), 4 x float4 = 64 B per internal node, children boxes in the parent:
-//   n0 = (Lmin.x, Lmin.y, Lmin.z, Lmax.x)  n1 = (Lmax.y, Lmax.z, Rmin.x, Rmin.y)
-//   n2 = (Rmin.z, Rmax.x, Rmax.y, Rmax.z)  n3 = (bits(left), bits(right), -, -)
+// Node layout (built by skr_bvh_build.cuh), 4 x float4 = 64 B per internal node, both child boxes in the parent,
+// interleaved Left/Right so that the slab arithmetic of the two boxes runs as packed FP32x2 (FADD2/FMUL2):
+//   n0 = (Lmin.x, Rmin.x, Lmin.y, Rmin.y)  n1 = (Lmin.z, Rmin.z, Lmax.x, Rmax.x)
+//   n2 = (Lmax.y, Rmax.y, Lmax.z, Rmax.z)  n3 = (bits(left), bits(right), -, -)
 // child index >= 0: internal node; < 0: leaf ~idx, whose triangle is tri_v[3*idx .. 3*idx+2] (leaf order).
 #pragma once
 
 #define SKR_BVH_STACK 96
 
-SKR_DEV bool line_hits_box(float3 o, float3 inv, float tmax, float bx0, float by0, float bz0, float bx1, float by1, float bz1)
+// Slab test of the LINE (no t >= 0 clamp) against the two child boxes of a node at once.  (b - o) * inv per plane, the
+// same two roundings as the scalar form, issued as FADD2 + FMUL2 with Left in .x and Right in .y.  fminf/fmaxf drop
+// NaNs (0 * inf when the origin sits on a slab plane of a zero direction component), which only widens the interval;
+// the interval is then widened by a few ulps so that rounding can never cull a box the exact test would keep.
+SKR_DEV void line_hits_boxes(float3 o, float3 inv, float tmax, const float4 &n0, const float4 &n1, const float4 &n2, bool &hl, bool &hr)
 {
-	// slab test without the t >= 0 clamp; fminf/fmaxf drop NaNs (0 * inf when the origin sits on a slab plane
-	// of a zero direction component), which only ever widens the interval
-	const float tx0 = (bx0 - o.x) * inv.x, tx1 = (bx1 - o.x) * inv.x;
-	const float ty0 = (by0 - o.y) * inv.y, ty1 = (by1 - o.y) * inv.y;
-	const float tz0 = (bz0 - o.z) * inv.z, tz1 = (bz1 - o.z) * inv.z;
-	float tn		= fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fminf(tz0, tz1));
-	float tf		= fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
-	// widen by a few ulps so that rounding in the slab arithmetic can never cull a box the exact test would keep
-	tn -= fabsf(tn) * 4.8e-7f;
-	tf += fabsf(tf) * 4.8e-7f;
-	return tn <= tf && tn < tmax;
+	const float2 nox = splat2(-o.x), noy = splat2(-o.y), noz = splat2(-o.z);
+	const float2 ix = splat2(inv.x), iy = splat2(inv.y), iz = splat2(inv.z);
+	const float2 tx0 = mul2(add2(f2(n0.x, n0.y), nox), ix), tx1 = mul2(add2(f2(n1.z, n1.w), nox), ix);
+	const float2 ty0 = mul2(add2(f2(n0.z, n0.w), noy), iy), ty1 = mul2(add2(f2(n2.x, n2.y), noy), iy);
+	const float2 tz0 = mul2(add2(f2(n1.x, n1.y), noz), iz), tz1 = mul2(add2(f2(n2.z, n2.w), noz), iz);
+	float tnl = fmaxf(fmaxf(fminf(tx0.x, tx1.x), fminf(ty0.x, ty1.x)), fminf(tz0.x, tz1.x));
+	float tfl = fminf(fminf(fmaxf(tx0.x, tx1.x), fmaxf(ty0.x, ty1.x)), fmaxf(tz0.x, tz1.x));
+	float tnr = fmaxf(fmaxf(fminf(tx0.y, tx1.y), fminf(ty0.y, ty1.y)), fminf(tz0.y, tz1.y));
+	float tfr = fminf(fminf(fmaxf(tx0.y, tx1.y), fmaxf(ty0.y, ty1.y)), fmaxf(tz0.y, tz1.y));
+	tnl -= fabsf(tnl) * 4.8e-7f;
+	tfl += fabsf(tfl) * 4.8e-7f;
+	tnr -= fabsf(tnr) * 4.8e-7f;
+	tfr += fabsf(tfr) * 4.8e-7f;
+	hl = tnl <= tfl && tnl < tmax;
+	hr = tnr <= tfr && tnr < tmax;
 }
 
 template <bool STATS>
@@ -77,8 +86,8 @@ SKR_DEV bool tri_any_hit_line(const SceneView &sv, float3 o, float3 d, float tma
 		{
 			cnt.nv++;
 		}
-		const bool hl = line_hits_box(o, inv, tmax, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-		const bool hr = line_hits_box(o, inv, tmax, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+		bool hl, hr;
+		line_hits_boxes(o, inv, tmax, n0, n1, n2, hl, hr);
 		const int cl = (int) f2u(n3.x), cr = (int) f2u(n3.y);
 		int next = -1; // next internal node to visit, if any
 		if(hl)

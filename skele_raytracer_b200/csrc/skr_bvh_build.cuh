@@ -395,9 +395,10 @@ __global__ void refit_kernel(int n, const unsigned *__restrict__ sorted_ids, con
 		{
 			rlo = __ldcg(node_lo + ch.y), rhi = __ldcg(node_hi + ch.y);
 		}
-		nodes[4 * node + 0] = make_float4(llo.x, llo.y, llo.z, lhi.x);
-		nodes[4 * node + 1] = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
-		nodes[4 * node + 2] = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
+		// Left/Right interleaved (skr_bvh.cuh)
+		nodes[4 * node + 0] = make_float4(llo.x, rlo.x, llo.y, rlo.y);
+		nodes[4 * node + 1] = make_float4(llo.z, rlo.z, lhi.x, rhi.x);
+		nodes[4 * node + 2] = make_float4(lhi.y, rhi.y, lhi.z, rhi.z);
 		nodes[4 * node + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), 0.0f, 0.0f);
 		__stcg(node_lo + node, make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f));
 		__stcg(node_hi + node, make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f));
