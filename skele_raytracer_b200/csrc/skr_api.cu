@@ -404,6 +404,18 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	fp.aspect = o->width / float(o->height);
 	fp.angle  = (float) tan(M_PI * 0.5 * o->fov / 180.);
 	fp.key	  = make_uint2((uint32_t) o->seed, (uint32_t) (o->seed >> 32));
+	{
+		// bundle culling (skr_device.cuh: cull_pairs).  A pixel's rays are d(r) = D + u(r) R + v(r) U with ONE draw r in
+		// [0, 1] for both axes (src/main.cpp:52-54): |d(r) - d(0.5)| <= 0.5 |du R - dv U| + rounding of the float chain.
+		const SceneView &sv = ctx->sv;
+		const double du = 2.0 * fp.angle * fp.aspect * fp.inv_w, dv = 2.0 * fp.angle * fp.inv_h;
+		const double ex = du * sv.cam_right.x - dv * sv.cam_up.x, ey = du * sv.cam_right.y - dv * sv.cam_up.y, ez = du * sv.cam_right.z - dv * sv.cam_up.z;
+		const auto len3 = [](float3 v) { return sqrt((double) v.x * v.x + (double) v.y * v.y + (double) v.z * v.z); };
+		const double span = len3(sv.cam_dir) + fabs((double) fp.angle * fp.aspect) * len3(sv.cam_right) + fabs((double) fp.angle) * len3(sv.cam_up);
+		fp.cull_delta = (float) (0.5 * 1.01 * sqrt(ex * ex + ey * ey + ez * ez) + 4e-6 * span);
+		const char *nocull = getenv("SKR_NO_CULL");
+		fp.cull = (sv.off_cull >= 0 && fp.grid > 0 && fp.spp >= 4 && !(nocull && nocull[0] == '1') && std::isfinite(fp.cull_delta)) ? 1 : 0;
+	}
 	fp.node_base = (uint32_t) fp.n_gi + 1u + (fp.fresnel ? 2u * (uint32_t) (ctx->sv.L + ctx->sv.D) : 0u);
 	fp.slot_gi	 = 1u + (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
 	pl.tiles_local = (fp.tiles_total + world - 1) / world;
@@ -893,6 +905,13 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	sv.off_foga	  = off, off += F;
 	sv.off_fogalb = off, off += F;
 	sv.off_fogp	  = off, off += (S * L * F + 3) / 4;
+	const int NP  = S4 / 2;
+	sv.off_cull	  = -1;
+	if(S > 0 && NP <= 32)
+	{
+		sv.off_cull = off, off += 3 * NP * (1 + L);
+	}
+	sv.cull_shadow = (sv.off_cull >= 0 && L * NP <= 64) ? 1 : 0;
 	sv.blob_f4	  = off > 0 ? off : 1;
 	std::vector<float4> blob((size_t) sv.blob_f4, make_float4(0, 0, 0, 0));
 	const V3 cam = ld3(sc->camera);
@@ -940,6 +959,30 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		const float inv = 1.0f / sqrtf(d.x * d.x + d.y * d.y + d.z * d.z); // glm::normalize
 		blob[sv.off_dldir + i] = make_float4(d.x * inv, d.y * inv, d.z * inv, 0);
 		blob[sv.off_dlcol + i] = make_float4(p[3], p[4], p[5], 0);
+	}
+	if(sv.off_cull >= 0)
+	{
+		// bundle-culling tables (skr_device.cuh: cull_pairs): apex 0 = camera, 1 + i = point light i
+		for(int a = 0; a <= L; a++)
+		{
+			const V3 A = a == 0 ? cam : ld3(sc->plights + 6 * (size_t) (a - 1));
+			for(int s = 0; s < S4; s++)
+			{
+				float *q	= reinterpret_cast<float *>(&blob[sv.off_cull + 3 * ((size_t) a * NP + (s >> 1))]);
+				const int k = s & 1;
+				if(s >= S) // padding: always culled (dist^2 = 3e38 > any margin^2)
+				{
+					q[0 + k] = 0, q[2 + k] = 0, q[4 + k] = 0, q[6 + k] = 3.0e38f, q[8 + k] = 0, q[10 + k] = 0;
+					continue;
+				}
+				const float *p	= sc->spheres + 18 * (size_t) s;
+				const double ux = (double) p[0] - A.x, uy = (double) p[1] - A.y, uz = (double) p[2] - A.z, r = p[3];
+				const double uu = ux * ux + uy * uy + uz * uz;
+				const double R	= sqrt(r * r + 1e-4 * uu) + 1e-4 * (1.0 + fabs(A.x) + fabs(A.y) + fabs(A.z) + fabs(p[0]) + fabs(p[1]) + fabs(p[2]));
+				q[0 + k] = (float) ux, q[2 + k] = (float) uy, q[4 + k] = (float) uz, q[6 + k] = (float) uu;
+				q[8 + k] = (float) (R * (1.0 + 1e-6)), q[10 + k] = (float) (sqrt(uu) * (1.0 + 1e-6));
+			}
+		}
 	}
 	float *fogp = reinterpret_cast<float *>(blob.data() + sv.off_fogp);
 	for(int j = 0; j < F; j++)

@@ -25,11 +25,15 @@
 //   foga [F]  (scattering, absorption, radius, 0)   fogalb[F] (albedo.xyz, 0)
 //   fogp      float[S*L*F]: exp(-min(|c_s - Lp_i|, 2 r_j) * (abs_j + scat_j)), precomputed on the host with the
 //             reference's own expression (src/blinn_phong.h:22-29)
+//   cull [1+L][S4/2][3]  per apex A (0: camera, 1+i: point light i) and sphere pair, with u = c - A:
+//             (ux0,ux1,uy0,uy1), (uz0,uz1,|u0|^2,|u1|^2), (R0,R1,|u0|,|u1|), R = inflated radius (see cull_pairs)
 // ------------------------------------------------------------------------------------------------
 struct SceneView
 {
 	int S, S4, T, L, D, F;
 	int off_geom, off_pgeom, off_pprim, off_amb, off_diff, off_spec, off_plpos, off_plcol, off_dldir, off_dlcol, off_foga, off_fogalb, off_fogp;
+	int off_cull;		 // bundle-culling tables (see cull_pairs), or -1 when the scene has more than 64 spheres
+	int cull_shadow;	 // 1: L * (S4/2) <= 64, the per-light masks of a pixel fit one 64-bit word
 	int blob_f4;		 // blob size in float4
 	int blob_in_smem;	 // 1: kernels stage the blob in shared memory
 	const float4 *blob;	 // device
@@ -248,6 +252,153 @@ SKR_DEV bool occluded(const float4 *__restrict__ B, const SceneView &sv, float3 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bundle culling.  The jitter samples of one pixel (--jsample n: n*n rays through one pixel, src/main.cpp:47-66) are a
+// thin bundle of lines through one apex: the camera for the primary rays, a point light for the shadow rays of hit
+// points that lie close together.  One conservative test per (bundle, sphere) -- "could ANY line of the bundle pass the
+// sphere test?" -- replaces n*n exact tests for every sphere the bundle clearly misses; the exact tests then run over
+// the surviving pairs only.  The result is bit-identical to testing every sphere: a culled sphere is one whose exact
+// test (h*h - a*cc >= 0 in float) is guaranteed to fail, by the margins below.
+//
+// Lines through apex A with directions within angle beta of w.  Sphere (c, r), u = c - A.  Distance from c to a line of
+// the bundle >= |u| (sin(angle(u, w)) - beta) = dist_c - |u| beta  (sin is 1-Lipschitz), dist_c^2 = |u|^2 - (u.w)^2/|w|^2.
+// Cull iff dist_c^2 > (R + |u| beta + m)^2 with
+//   R = sqrt(r^2 + 1e-4 |u|^2) + 1e-4 (1 + |A|_1 + |c|_1): covers the rounding of the exact test (its disc/4 carries an
+//       error of ~1e-6 |o - c|^2: >= 80x margin), of this test, and lines that miss the apex by a few ulps of the coordinates;
+//   m = 0.01 |w| for shadow bundles, whose ray origins lie |w| away from the apex (|o - c| <= |u| + |w|).
+// Comparisons are written so that NaN keeps the sphere.  Returns one bit per sphere PAIR.
+// ------------------------------------------------------------------------------------------------
+SKR_DEV uint32_t cull_pairs(const float4 *__restrict__ C, int NP, float3 w, float beta, float m)
+{
+	const float2 ninv = splat2(-__fdividef(1.0f, dot(w, w)));
+	const float2 wx = splat2(w.x), wy = splat2(w.y), wz = splat2(w.z), b2 = splat2(beta), m2 = splat2(m);
+	uint32_t mask = 0;
+	for(int p = 0; p < NP; p++)
+	{
+		const float4 c0 = C[3 * p], c1 = C[3 * p + 1], c2 = C[3 * p + 2];
+		const float2 hw	 = fma2(wz, f2(c1.x, c1.y), fma2(wy, f2(c0.z, c0.w), mul2(wx, f2(c0.x, c0.y))));
+		const float2 lhs = fma2(mul2(hw, hw), ninv, f2(c1.z, c1.w));
+		const float2 X	 = fma2(f2(c2.z, c2.w), b2, add2(f2(c2.x, c2.y), m2));
+		const float2 X2	 = mul2(X, X);
+		const bool keep	 = !(lhs.x > X2.x) | !(lhs.y > X2.y);
+		mask |= (uint32_t) keep << p;
+	}
+	return mask;
+}
+
+// closest_sphere_table<ORIGIN_TABLE = true, COHERENT = true> over the pairs of `mask` only (ascending, so the first
+// sphere still wins ties).  `mask` is uniform across the warp: no divergence, broadcast shared-memory reads.
+template <bool STATS>
+SKR_DEV int closest_sphere_masked(const float4 *__restrict__ G, uint32_t mask, int S, float3 d, float &tmin, Counters &cnt)
+{
+	const float a  = dot(d, d);
+	const float na = -a;
+	int best	   = -1;
+	float umin	   = CUDART_INF_F;
+	const float2 dx = splat2(d.x), dy = splat2(d.y), dz = splat2(d.z), na2 = splat2(na);
+	if(STATS)
+	{
+		cnt.st += S; // the reference's count: it tests every sphere (the culled ones fail by construction)
+	}
+	for(uint32_t m = mask; m; m &= m - 1)
+	{
+		const int p		= __ffs(m) - 1;
+		const float4 g0 = G[2 * p], g1 = G[2 * p + 1];
+		const float2 h	= fma2(dz, f2(g1.x, g1.y), fma2(dy, f2(g0.z, g0.w), mul2(dx, f2(g0.x, g0.y))));
+		const float2 cc = f2(g1.z, g1.w);
+		const float2 d4 = fma2(h, h, mul2(na2, cc));
+		if(STATS)
+		{
+			cnt.stp += (d4.x >= 0.0f) + (d4.y >= 0.0f);
+		}
+		if(d4.x >= 0.0f)
+		{
+			const float w = fmaf(2.0f, h.x, cc.x), mm = -h.x - umin;
+			if((h.x < na) & (w > na) & ((mm < 0.0f) | (d4.x > mm * mm)))
+			{
+				umin = -h.x - __fsqrt_rn(d4.x);
+				best = 2 * p;
+			}
+		}
+		if(d4.y >= 0.0f)
+		{
+			const float w = fmaf(2.0f, h.y, cc.y), mm = -h.y - umin;
+			if((h.y < na) & (w > na) & ((mm < 0.0f) | (d4.y > mm * mm)))
+			{
+				umin = -h.y - __fsqrt_rn(d4.y);
+				best = 2 * p + 1;
+			}
+		}
+	}
+	tmin = best >= 0 ? __fdiv_rn(umin, a) : CUDART_INF_F;
+	return best;
+}
+
+// occluded() over the pairs of `mask` only (per-lane mask).
+template <bool STATS>
+SKR_DEV bool occluded_masked(const float4 *__restrict__ B, const SceneView &sv, uint32_t mask, float3 p, float3 dir, Counters &cnt)
+{
+	const float3 o = adds_rn(p, 0.000001f);
+	const float a  = dot(dir, dir);
+	const float na = -a;
+	const float4 *__restrict__ G = B + sv.off_pgeom;
+	const float2 dx = splat2(dir.x), dy = splat2(dir.y), dz = splat2(dir.z), na2 = splat2(na), two = splat2(2.0f);
+	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
+	if(STATS)
+	{
+		cnt.sh++;
+	}
+	for(uint32_t m = mask; m; m &= m - 1)
+	{
+		const int pp	= __ffs(m) - 1;
+		const float4 g0 = G[2 * pp], g1 = G[2 * pp + 1];
+		const float2 ex = add2(ox, f2(g0.x, g0.y)), ey = add2(oy, f2(g0.z, g0.w)), ez = add2(oz, f2(g1.x, g1.y));
+		const float2 h	= fma2(dz, ez, fma2(dy, ey, mul2(dx, ex)));
+		const float2 cc = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, f2(g1.z, g1.w))));
+		const float2 d4 = fma2(h, h, mul2(na2, cc));
+		const float2 w	= fma2(two, h, cc);
+		const bool occ0 = (h.x < na) & (d4.x >= 0.0f) & (w.x > na);
+		const bool occ1 = (h.y < na) & (d4.y >= 0.0f) & (w.y > na);
+		if(STATS)
+		{
+			cnt.stp += (d4.x >= 0.0f) + ((d4.y >= 0.0f) & !occ0);
+		}
+		if(occ0 | occ1)
+		{
+			if(STATS)
+			{
+				cnt.st += 2 * pp + (occ0 ? 1 : 2); // the reference stops at its first occluder
+			}
+			return true;
+		}
+	}
+	if(STATS)
+	{
+		cnt.st += sv.S;
+	}
+	return false;
+}
+
+// Shadow-ray masks of the hit points within `rho` of pc, one NP-bit field per point light (sv.cull_shadow).
+SKR_DEV uint64_t shadow_masks(const float4 *__restrict__ B, const SceneView &sv, float3 pc, float rho)
+{
+	const int NP		= sv.S4 >> 1;
+	const uint32_t full = NP >= 32 ? 0xffffffffu : (1u << NP) - 1u;
+	uint64_t all		= 0;
+	for(int i = 0; i < sv.L; i++)
+	{
+		const float3 w	= pc - f3(B[sv.off_plpos + i]);
+		const float len = sqrtf(dot(w, w));
+		uint32_t mk		= full;
+		if(rho <= 0.45f * len) // asin(x) <= 1.05 x there
+		{
+			mk = cull_pairs(B + sv.off_cull + 3 * NP * (1 + i), NP, w, __fdividef(1.07f * rho, len), 0.01f * len);
+		}
+		all |= (uint64_t) mk << (i * NP);
+	}
+	return all;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Triangles.  The leaf test is the reference's arithmetic verbatim in uncontracted float ops, so that the
 // `fabs(det) < 1e-5` rejection and the u/v window decide exactly as on the CPU.
 // ------------------------------------------------------------------------------------------------
@@ -312,8 +463,9 @@ SKR_DEV float3 fog_term(const float4 *__restrict__ B, const SceneView &sv, const
 // even for bounce hits (src/blinn_phong.h:93).
 template <bool STATS, bool FOG>
 SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, bool use_shadows, const RngCtx &rng, int sidx, float3 p, float3 n,
-							Counters &cnt)
+							Counters &cnt, bool masked = false, uint64_t smask = 0)
 {
+	const int NP = sv.S4 >> 1;
 	const float4 am = B[sv.off_amb + sidx];
 	const float3 kd = f3(B[sv.off_diff + sidx]);
 	const float3 ks		= f3(B[sv.off_spec + sidx]);
@@ -325,9 +477,13 @@ SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, b
 		const float3 lv	  = f3(B[sv.off_plpos + i]) - p;
 		const float d2	  = dot(lv, lv);
 		const float3 lhat = lv * rsqrtf(d2); // also the shadow-ray direction
-		if(use_shadows && occluded<STATS>(B, sv, p, lhat, cnt))
+		if(use_shadows)
 		{
-			continue;
+			if(masked ? occluded_masked<STATS>(B, sv, (uint32_t) (smask >> (i * NP)) & (uint32_t) ((1ull << NP) - 1ull), p, lhat, cnt)
+					  : occluded<STATS>(B, sv, p, lhat, cnt))
+			{
+				continue;
+			}
 		}
 		if(STATS)
 		{
@@ -404,13 +560,15 @@ SKR_DEV float3 gi_child_dir(float r1, float r2, float3 n, float3 nt, float3 nb)
 // Returns: -2 background, -1 triangle (black), >= 0 sphere index with t in tmin.
 // ------------------------------------------------------------------------------------------------
 template <bool PRIMARY, bool STATS, bool TRIS>
-SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt)
+SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt, bool masked = false,
+						uint32_t pmask = 0)
 {
 	if(STATS)
 	{
 		cnt.ch++;
 	}
-	const int s = closest_sphere<PRIMARY, STATS>(B, sv, o, d, tmin, cnt);
+	const int s = (PRIMARY && masked) ? closest_sphere_masked<STATS>(B + sv.off_pprim, pmask, sv.S, d, tmin, cnt)
+									  : closest_sphere<PRIMARY, STATS>(B, sv, o, d, tmin, cnt);
 	if(TRIS && sv.T > 0 && tri_any_hit_line<STATS>(sv, o, d, tmin, cnt))
 	{
 		return -1;

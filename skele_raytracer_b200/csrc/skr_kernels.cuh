@@ -44,6 +44,8 @@ struct FrameParams
 	int grid, spp;
 	int max_depth, gi, n_gi, shadows, fresnel;
 	float angle, aspect, inv_w, inv_h;
+	int cull;		  // 1: bundle culling (cull_pairs) for this frame: jittered, >= 4 samples per pixel, <= 64 spheres
+	float cull_delta; // bound on |d(r) - d(0.5)| over the jitter draw r of a pixel (ray directions are un-normalised)
 	uint2 key;
 	uint32_t node_base, slot_gi;
 	uint8_t *rgb8;	 // row-major frame or null
@@ -256,6 +258,28 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 
 	const int nsamples = fp.max_depth > 0 ? fp.spp : 0; // depth <= 0: shade() returns black (src/raytrace.h:142-145)
 	uint4 jit = make_uint4(0u, 0u, 0u, 0u);
+
+	// Bundle culling (skr_device.cuh, cull_pairs): the pixel's samples are lines through the camera within cull_delta of
+	// the ray of r = 0.5.  The warp tests the union of its 32 pixels' surviving pairs, so the loop stays uniform.
+	const bool cull	 = fp.cull != 0;
+	uint32_t pmask	 = 0;
+	float3 pc		 = f3(0.0f, 0.0f, 0.0f); // shadow bundle: hit points within sqrt(rho2) of pc use smask
+	float rho2		 = -1.0f;
+	uint64_t smask	 = 0;
+	if(cull)
+	{
+		const float uc = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn((float) p.x, 0.5f), fp.inv_w)), 1.0f), fp.angle), fp.aspect);
+		const float vc = __fmul_rn(__fsub_rn(1.0f, __fmul_rn(2.0f, __fmul_rn(__fadd_rn((float) p.y, 0.5f), fp.inv_h))), fp.angle);
+		const float3 dc = add_rn(add_rn(sv.cam_dir, muls_rn(sv.cam_right, uc)), muls_rn(sv.cam_up, vc));
+		const float len = sqrtf(dot(dc, dc));
+		const int NP	= sv.S4 >> 1;
+		uint32_t mk		= NP >= 32 ? 0xffffffffu : (1u << NP) - 1u;
+		if(fp.cull_delta <= 0.45f * len)
+		{
+			mk = cull_pairs(B + sv.off_cull, NP, dc, __fdividef(1.05f * fp.cull_delta, len), 0.0f);
+		}
+		pmask = __reduce_or_sync(0xffffffffu, p.valid ? mk : 0u);
+	}
 	for(int s = 0; s < nsamples; s++)
 	{
 		rng.sample = (uint32_t) s;
@@ -288,7 +312,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		int h	= -3;
 		if(p.valid)
 		{
-			h = closest_hit<true, STATS, TRIS>(B, sv, o, d, t, cnt);
+			h = closest_hit<true, STATS, TRIS>(B, sv, o, d, t, cnt, cull, pmask);
 		}
 		float3 hp = f3(0.0f, 0.0f, 0.0f);
 		if(h == -2)
@@ -302,8 +326,23 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			hp			   = add_rn(o, muls_rn(d, t)); // src/raytrace.h:204
 			if(!GI)
 			{
-				const float3 n = normalize_rn(sub_rn(hp, c));
-				sum += direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt);
+				const float3 n	  = normalize_rn(sub_rn(hp, c));
+				const bool smcull = cull && fp.shadows != 0 && sv.cull_shadow != 0;
+				if(smcull)
+				{
+					const float3 dp = hp - pc;
+					if(!(dot(dp, dp) <= rho2))
+					{
+						// new bundle around this hit.  Radius: the footprint of the pixel's jitter diagonal on the surface,
+						// t * 2 delta / cos(incidence), with slack; samples that still fall outside start another bundle.
+						const float ci	= fabsf(dot(n, d)) * rsqrtf(dot(d, d));
+						const float rho = __fdividef(2.5f * fp.cull_delta * t, fmaxf(ci, 0.05f));
+						pc				= hp;
+						rho2			= rho * rho;
+						smask			= shadow_masks(B, sv, hp, rho);
+					}
+				}
+				sum += direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt, smcull, smask);
 			}
 		}
 		if(GI)

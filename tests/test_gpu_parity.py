@@ -365,6 +365,50 @@ def test_run_to_run_bit_identical(gpu, gscenes):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+CULL_CASES = [("spheres2", dict(width=480, height=270, grid_size=5, use_shadows=True, seed=11)),                  # config 2 shape
+              ("spheres2", dict(width=317, height=201, grid_size=2, use_shadows=True, fov=120.0, seed=12)),      # wide pixels
+              ("spheres2_nofog", dict(width=64, height=36, grid_size=3, use_shadows=True, fov=170.0, seed=13)),  # huge pixels
+              ("bear", dict(width=480, height=270, grid_size=4, use_shadows=True, seed=14)),
+              ("spheres1", dict(width=320, height=180, grid_size=3, use_shadows=True, seed=15)),
+              ("test", dict(width=160, height=90, grid_size=2, use_shadows=True, seed=16)),
+              ("bear", dict(width=96, height=54, grid_size=2, monte_carlo=True, num_path_traces=4, use_shadows=True, seed=17))]
+
+
+@pytest.mark.parametrize("scene,kw", CULL_CASES)
+def test_bundle_culling_is_exact(gpu, gscenes, scene, kw):
+    """cull_pairs only ever skips spheres whose exact test fails: frame AND device counters (sphere tests with a
+    non-negative discriminant included) are identical with culling off (SKR_NO_CULL=1)."""
+    gpu.upload(gscenes[scene])
+    o = S.Options(collect_stats=True, **kw)
+    a32, a8, sa = gpu.render(o)
+    os.environ["SKR_NO_CULL"] = "1"
+    try:
+        b32, b8, sb = gpu.render(o)
+    finally:
+        del os.environ["SKR_NO_CULL"]
+    assert np.array_equal(a32.view(np.uint32), b32.view(np.uint32)) and np.array_equal(a8, b8)
+    for f in ("closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "sphere_hits", "light_evals"):
+        assert getattr(sa, f) == getattr(sb, f), f
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_bundle_culling_is_exact_random_scenes(gpu, seed):
+    rng = np.random.default_rng(900 + seed)
+    sc = to_gpu_scene(random_scene(rng, nspheres=int(rng.integers(1, 60)), nplights=int(rng.integers(1, 4))))
+    gpu.upload(sc)
+    o = S.Options(width=200, height=120, grid_size=int(rng.integers(2, 5)), use_shadows=True, fov=float(rng.uniform(20, 150)),
+                  seed=seed, collect_stats=True)
+    a32, a8, sa = gpu.render(o)
+    os.environ["SKR_NO_CULL"] = "1"
+    try:
+        b32, b8, sb = gpu.render(o)
+    finally:
+        del os.environ["SKR_NO_CULL"]
+    assert np.array_equal(a32.view(np.uint32), b32.view(np.uint32)) and np.array_equal(a8, b8)
+    for f in ("closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "sphere_hits", "light_evals"):
+        assert getattr(sa, f) == getattr(sb, f), f
+
+
 def test_queue_capacity_does_not_change_the_image(gpu, gscenes):
     gpu.upload(gscenes["spheres2"])
     a, _, sa = gpu.render(S.Options(**GI_KW))
