@@ -912,6 +912,14 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		sv.off_cull = off, off += 3 * NP * (1 + L);
 	}
 	sv.cull_shadow = (sv.off_cull >= 0 && L * NP <= 64) ? 1 : 0;
+	sv.off_rmask   = -1;
+	{
+		const char *nocull = getenv("SKR_NO_CULL");
+		if(sv.off_cull >= 0 && L > 0 && !(nocull && nocull[0] == '1'))
+		{
+			sv.off_rmask = off, off += (S * L + S + 3) / 4;
+		}
+	}
 	sv.blob_f4	  = off > 0 ? off : 1;
 	std::vector<float4> blob((size_t) sv.blob_f4, make_float4(0, 0, 0, 0));
 	const V3 cam = ld3(sc->camera);
@@ -981,6 +989,45 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 				const double R	= sqrt(r * r + 1e-4 * uu) + 1e-4 * (1.0 + fabs(A.x) + fabs(A.y) + fabs(A.z) + fabs(p[0]) + fabs(p[1]) + fabs(p[2]));
 				q[0 + k] = (float) ux, q[2 + k] = (float) uy, q[4 + k] = (float) uz, q[6 + k] = (float) uu;
 				q[8 + k] = (float) (R * (1.0 + 1e-6)), q[10 + k] = (float) (sqrt(uu) * (1.0 + 1e-6));
+			}
+		}
+	}
+	if(sv.off_rmask >= 0)
+	{
+		// static shadow masks: cull_pairs (skr_device.cuh) in double for the bundle "lines through light i and a point
+		// within rho of c_s", rho = r_s with slack for the rounding of the hit point; same margins as the device test
+		uint32_t *rm = reinterpret_cast<uint32_t *>(blob.data() + sv.off_rmask);
+		float *rchk	 = reinterpret_cast<float *>(rm + (size_t) S * L);
+		const uint32_t full = NP >= 32 ? 0xffffffffu : (1u << NP) - 1u;
+		for(int s = 0; s < S; s++)
+		{
+			const float *ps	 = sc->spheres + 18 * (size_t) s;
+			const double rho = fabs((double) ps[3]) * 1.001 + 1e-4 * (1.0 + fabs(ps[0]) + fabs(ps[1]) + fabs(ps[2]));
+			rchk[s]			 = (float) (rho * rho * (1.0 - 1e-5));
+			for(int i = 0; i < L; i++)
+			{
+				const float *pl = sc->plights + 6 * (size_t) i;
+				const double wx = (double) ps[0] - pl[0], wy = (double) ps[1] - pl[1], wz = (double) ps[2] - pl[2];
+				const double ww = wx * wx + wy * wy + wz * wz, len = sqrt(ww);
+				uint32_t mk		= full;
+				if(rho <= 0.45 * len)
+				{
+					mk					= 0;
+					const double beta	= 1.07 * rho / len, m = 0.01 * len;
+					const float *ctab	= reinterpret_cast<const float *>(&blob[sv.off_cull + 3 * (size_t) (1 + i) * NP]);
+					for(int k = 0; k < S; k++)
+					{
+						const float *q	= ctab + 12 * (size_t) (k >> 1);
+						const int e		= k & 1;
+						const double hw = wx * q[0 + e] + wy * q[2 + e] + wz * q[4 + e];
+						const double X	= (double) q[8 + e] + (double) q[10 + e] * beta + m;
+						if(!((double) q[6 + e] - hw * hw / ww > X * X))
+						{
+							mk |= 1u << (k >> 1);
+						}
+					}
+				}
+				rm[(size_t) s * L + i] = mk;
 			}
 		}
 	}

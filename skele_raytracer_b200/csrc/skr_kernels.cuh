@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 						smask			= shadow_masks(B, sv, hp, rho);
 					}
 				}
-				sum += direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt, smcull, smask);
+				sum += direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt, true, smcull, smask);
 			}
 		}
 		if(GI)

@@ -371,7 +371,11 @@ CULL_CASES = [("spheres2", dict(width=480, height=270, grid_size=5, use_shadows=
               ("bear", dict(width=480, height=270, grid_size=4, use_shadows=True, seed=14)),
               ("spheres1", dict(width=320, height=180, grid_size=3, use_shadows=True, seed=15)),
               ("test", dict(width=160, height=90, grid_size=2, use_shadows=True, seed=16)),
-              ("bear", dict(width=96, height=54, grid_size=2, monte_carlo=True, num_path_traces=4, use_shadows=True, seed=17))]
+              ("bear", dict(width=96, height=54, grid_size=2, monte_carlo=True, num_path_traces=4, use_shadows=True, seed=17)),
+              ("bear", dict(width=480, height=270, use_shadows=True)),                                            # static masks only
+              ("spheres2_nofog", dict(width=480, height=270, use_shadows=True)),
+              ("spheres1", dict(width=96, height=54, max_depth=3, monte_carlo=True, num_path_traces=6, use_shadows=True, seed=18)),
+              ("spheres2", dict(width=64, height=36, max_depth=3, monte_carlo=True, num_path_traces=5, use_shadows=True, fresnel=True, seed=19))]
 
 
 @pytest.mark.parametrize("scene,kw", CULL_CASES)
@@ -381,8 +385,9 @@ def test_bundle_culling_is_exact(gpu, gscenes, scene, kw):
     gpu.upload(gscenes[scene])
     o = S.Options(collect_stats=True, **kw)
     a32, a8, sa = gpu.render(o)
-    os.environ["SKR_NO_CULL"] = "1"
+    os.environ["SKR_NO_CULL"] = "1"          # read at upload (static per-receiver masks) and per frame (pixel bundles)
     try:
+        gpu.upload(gscenes[scene])
         b32, b8, sb = gpu.render(o)
     finally:
         del os.environ["SKR_NO_CULL"]
@@ -396,11 +401,12 @@ def test_bundle_culling_is_exact_random_scenes(gpu, seed):
     rng = np.random.default_rng(900 + seed)
     sc = to_gpu_scene(random_scene(rng, nspheres=int(rng.integers(1, 60)), nplights=int(rng.integers(1, 4))))
     gpu.upload(sc)
-    o = S.Options(width=200, height=120, grid_size=int(rng.integers(2, 5)), use_shadows=True, fov=float(rng.uniform(20, 150)),
-                  seed=seed, collect_stats=True)
+    o = S.Options(width=200, height=120, grid_size=int(rng.integers(0, 5)), use_shadows=True, fov=float(rng.uniform(20, 150)),
+                  monte_carlo=bool(seed & 1), num_path_traces=3, max_depth=2, seed=seed, collect_stats=True)
     a32, a8, sa = gpu.render(o)
     os.environ["SKR_NO_CULL"] = "1"
     try:
+        gpu.upload(sc)
         b32, b8, sb = gpu.render(o)
     finally:
         del os.environ["SKR_NO_CULL"]
