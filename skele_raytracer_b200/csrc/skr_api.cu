@@ -6,7 +6,10 @@
 // in this file or anywhere in the library: if CUDA is unavailable every entry point fails.
 #include "../../include/skr.h"
 
+#include <cuda.h> // types of the stream memory operations only; entry points come from cudaGetDriverEntryPoint
+#include <algorithm>
 #include <cmath>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +42,7 @@ constexpr size_t SMEM_BLOB_LIMIT = 64 * 1024;
 constexpr unsigned MAX_QUEUE_CAP = 128u << 20; // entries per level (36 B each, 4.6 GB): fewer, fuller chunks -- config 5: 228 ms at 32 M, 213 ms at 128 M
 constexpr unsigned MIN_QUEUE_CAP = 1u << 20;
 constexpr int DEFAULT_TILE = 32;
+constexpr int MAX_BANDS = 8;
 } // namespace
 
 struct skr_ctx
@@ -83,6 +87,13 @@ struct skr_ctx
 	std::vector<Span> spans;
 	size_t spans_used = 0;
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
+
+	// overlapped copy-out of skr_render (see FrameParams::band_flag)
+	cudaStream_t copy_stream = nullptr;
+	unsigned *d_band = nullptr; // [0, MAX_BANDS): counts, [MAX_BANDS, 2 MAX_BANDS): flags
+	unsigned band_seq = 0;
+	CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned) = nullptr;
+	CUresult (*write_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned) = nullptr;
 
 	unsigned launches = 0, chunks = 0;
 	bool timing = true; // false: fire-and-forget frame, no per-kernel events
@@ -647,7 +658,8 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 }
 
 // common driver: outputs already set in pl.fp
-int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats)
+// `after_launch` (optional) runs once the frame's kernels are enqueued, before anything waits for them.
+int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats, const std::function<int()> &after_launch = nullptr)
 {
 	cudaStream_t st = ctx->stream;
 	ctx->spans_used = 0;
@@ -671,6 +683,10 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	}
 	int rc = want_stats ? render_frame<true>(ctx, o, pl) : render_frame<false>(ctx, o, pl);
 	if(rc)
+	{
+		return rc;
+	}
+	if(after_launch && (rc = after_launch()) != 0)
 	{
 		return rc;
 	}
@@ -808,6 +824,20 @@ int skr_init(int device, skr_ctx **out)
 	cudaEventCreate(&c->ev_end);
 	cudaEventCreate(&c->ev_x0);
 	cudaEventCreate(&c->ev_x1);
+	// overlapped copy-out (optional: without stream memory operations skr_render copies after the kernel)
+	{
+		void *fw = nullptr, *fr = nullptr;
+		cudaDriverEntryPointQueryResult qw, qr;
+		if(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fw, cudaEnableDefault, &qw) == cudaSuccess && qw == cudaDriverEntryPointSuccess && fw &&
+		   cudaGetDriverEntryPoint("cuStreamWriteValue32", &fr, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess && fr &&
+		   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+		   cudaMalloc(&c->d_band, sizeof(unsigned) * 2 * MAX_BANDS) == cudaSuccess && cudaMemset(c->d_band, 0, sizeof(unsigned) * 2 * MAX_BANDS) == cudaSuccess)
+		{
+			c->wait_value32	 = reinterpret_cast<decltype(c->wait_value32)>(fw);
+			c->write_value32 = reinterpret_cast<decltype(c->write_value32)>(fr);
+		}
+		cudaGetLastError();
+	}
 	*out = c;
 	return SKR_OK;
 }
@@ -829,7 +859,11 @@ void skr_destroy(skr_ctx *ctx)
 	{
 		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c), cudaFree(q.d);
 	}
-	cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_err);
+	cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band);
+	if(ctx->copy_stream)
+	{
+		cudaStreamDestroy(ctx->copy_stream);
+	}
 	if(ctx->h_count)
 	{
 		cudaFreeHost(ctx->h_count);
@@ -1140,6 +1174,106 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 		{
 			CK(cudaMemsetAsync(ctx->d_rgb32, 0, npx * 3 * sizeof(float), ctx->stream));
 		}
+	}
+	// Copy-out overlapped with the kernel, for frames that are ONE kernel: the frame leaves in bands of whole tile rows; the
+	// copy of band b sits on a second stream behind a stream-ordered wait (cuStreamWaitValue32) on the flag that the last
+	// CTA of the band sets (primary_kernel), so all but the last band cross PCIe while the kernel is still tracing.
+	struct Band
+	{
+		size_t y0, y1;
+	} bands[MAX_BANDS];
+	int nb = 0;
+	{
+		const FrameParams &fp = pl.fp;
+		const char *no		  = getenv("SKR_NO_OVERLAP");
+		const int tpix		  = fp.tile * fp.tile;
+		// page-locked destinations only: a copy to pageable memory blocks the host until it is done, and it would be
+		// enqueued before the kernel it waits for
+		const auto pinned = [](const void *p) {
+			cudaPointerAttributes a;
+			if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+			{
+				cudaGetLastError();
+				return false;
+			}
+			return a.type == cudaMemoryTypeHost;
+		};
+		// (worth its ~0.04 ms of extra stream operations only when the kernel is long against the copy: jittered frames)
+		if(ctx->wait_value32 && pl.levels == 0 && fp.world == 1 && fp.spp >= 4 && tpix % SKR_BLOCK == 0 && npx * 3 >= (1u << 20) && !(no && no[0] == '1') &&
+		   (!rgb8 || pinned(rgb8)) && (!rgb32 || pinned(rgb32)) && (rgb8 || rgb32))
+		{
+			const int tile_rows = (opt->height + fp.tile - 1) / fp.tile;
+			const int rpb		= (tile_rows + 3) / 4;
+			nb					= (tile_rows + rpb - 1) / rpb;
+			for(int b = 0; b < nb; b++)
+			{
+				bands[b].y0 = (size_t) b * rpb * fp.tile;
+				bands[b].y1 = std::min((size_t) opt->height, (size_t) (b + 1) * rpb * fp.tile);
+			}
+			pl.fp.band_count = ctx->d_band;
+			pl.fp.band_flag	 = ctx->d_band + MAX_BANDS;
+			pl.fp.band_ctas	 = (unsigned) rpb * (unsigned) fp.tiles_x * (unsigned) (tpix / SKR_BLOCK);
+			pl.fp.band_seq	 = ++ctx->band_seq;
+		}
+	}
+	const size_t row8 = (size_t) opt->width * 3, row32 = row8 * sizeof(float);
+	if(nb > 0)
+	{
+		CK(cudaMemsetAsync(ctx->d_band, 0, sizeof(unsigned) * MAX_BANDS, ctx->stream));
+		// The waits are enqueued AFTER the kernel they wait for: should the two streams share a hardware queue, the copies
+		// then merely line up behind the kernel; a wait enqueued first could block the kernel behind it for ever.
+		bool enqueued		   = false;
+		const auto copy_bands = [&]() -> int {
+			enqueued = true;
+			for(int b = 0; b < nb; b++)
+			{
+				if(ctx->wait_value32((CUstream) ctx->copy_stream, (CUdeviceptr) (pl.fp.band_flag + b), pl.fp.band_seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+				{
+					return fail(ctx, SKR_ERR_CUDA, "skr_render: cuStreamWaitValue32 failed");
+				}
+				if(b == 0)
+				{
+					CK(cudaEventRecord(ctx->ev_x0, ctx->copy_stream));
+				}
+				const size_t y0 = bands[b].y0, rows = bands[b].y1 - bands[b].y0;
+				if(rgb8)
+				{
+					CK(cudaMemcpyAsync(rgb8 + y0 * row8, ctx->d_rgb8 + y0 * row8, rows * row8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+				}
+				if(rgb32)
+				{
+					CK(cudaMemcpyAsync((char *) rgb32 + y0 * row32, (char *) ctx->d_rgb32 + y0 * row32, rows * row32, cudaMemcpyDeviceToHost, ctx->copy_stream));
+				}
+			}
+			CK(cudaEventRecord(ctx->ev_x1, ctx->copy_stream));
+			return SKR_OK;
+		};
+		skr_stats local;
+		rc = render_common(ctx, opt, pl, &local, copy_bands);
+		if(enqueued)
+		{
+			// whatever happened above, nothing stays parked on the copy stream: publish every flag behind the frame
+			for(int b = 0; b < nb; b++)
+			{
+				ctx->write_value32((CUstream) ctx->stream, (CUdeviceptr) (pl.fp.band_flag + b), pl.fp.band_seq, 0);
+			}
+			cudaStreamSynchronize(ctx->stream);
+			const cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
+			if(!rc)
+			{
+				CK(ce);
+			}
+		}
+		if(rc)
+		{
+			return rc;
+		}
+		CK(cudaEventElapsedTime(&local.ms_d2h, ctx->ev_x0, ctx->ev_x1));
+		if(stats)
+		{
+			*stats = local;
+		}
+		return SKR_OK;
 	}
 	skr_stats local;
 	rc = render_common(ctx, opt, pl, &local);

@@ -184,6 +184,63 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 	return best;
 }
 
+// closest_sphere_table<false, false> for TWO rays from the same origin (a pair of GI children of one hit): e = o - c
+// and cc = e.e - r^2 of a sphere pair are formed once and serve both rays -- 8 of the 25 instructions per (pair, ray).
+// Per ray the operations and their order are those of the one-ray form: same winner, same t.
+template <bool STATS>
+SKR_DEV void closest_sphere_x2(const float4 *__restrict__ G, int NP, int S, float3 o, float3 d0, float3 d1, float &t0, int &s0, float &t1, int &s1,
+							   Counters &cnt)
+{
+	const float a0 = dot(d0, d0), a1 = dot(d1, d1);
+	int b0 = -1, b1 = -1;
+	float um0 = CUDART_INF_F, um1 = CUDART_INF_F;
+	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
+	const float2 d0x = splat2(d0.x), d0y = splat2(d0.y), d0z = splat2(d0.z), na0 = splat2(-a0);
+	const float2 d1x = splat2(d1.x), d1y = splat2(d1.y), d1z = splat2(d1.z), na1 = splat2(-a1);
+#pragma unroll 2
+	for(int p = 0; p < NP; p++)
+	{
+		const float4 g0 = G[2 * p], g1 = G[2 * p + 1];
+		const float2 ex = add2(ox, f2(g0.x, g0.y)), ey = add2(oy, f2(g0.z, g0.w)), ez = add2(oz, f2(g1.x, g1.y));
+		const float2 cc = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, f2(g1.z, g1.w))));
+		const float2 h0 = fma2(d0z, ez, fma2(d0y, ey, mul2(d0x, ex)));
+		const float2 h1 = fma2(d1z, ez, fma2(d1y, ey, mul2(d1x, ex)));
+		const float2 q0 = fma2(h0, h0, mul2(na0, cc));
+		const float2 q1 = fma2(h1, h1, mul2(na1, cc));
+		if(STATS)
+		{
+			cnt.st += 2 * ((2 * p < S) + (2 * p + 1 < S));
+			cnt.stp += (q0.x >= 0.0f) + (q0.y >= 0.0f) + (q1.x >= 0.0f) + (q1.y >= 0.0f);
+		}
+		const float u0x = -h0.x - sqrt_approx(q0.x), u0y = -h0.y - sqrt_approx(q0.y);
+		const float u1x = -h1.x - sqrt_approx(q1.x), u1y = -h1.y - sqrt_approx(q1.y);
+		if((u0x > a0) & (u0x < um0))
+		{
+			um0 = u0x;
+			b0	= 2 * p;
+		}
+		if((u0y > a0) & (u0y < um0))
+		{
+			um0 = u0y;
+			b0	= 2 * p + 1;
+		}
+		if((u1x > a1) & (u1x < um1))
+		{
+			um1 = u1x;
+			b1	= 2 * p;
+		}
+		if((u1y > a1) & (u1y < um1))
+		{
+			um1 = u1y;
+			b1	= 2 * p + 1;
+		}
+	}
+	t0 = b0 >= 0 ? __fdiv_rn(um0, a0) : CUDART_INF_F;
+	t1 = b1 >= 0 ? __fdiv_rn(um1, a1) : CUDART_INF_F;
+	s0 = b0;
+	s1 = b1;
+}
+
 template <bool PRIMARY, bool STATS>
 SKR_DEV int closest_sphere(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt)
 {
@@ -446,20 +503,20 @@ SKR_DEV float pow_fast(float x, float p) // x >= 0
 
 // bp::spherical_fog_shading (src/blinn_phong.h:19-44) + scattering_phase_function (src/utils.h:216-224).
 // `r` is the Philox block of this (light, fog); call 0 = from diffuse_shading, 1 = from specular_shading.
-SKR_DEV float3 fog_term(const float4 *__restrict__ B, const SceneView &sv, const uint4 &r, int call, int i, int j, int sidx, float3 kd, float3 lcol,
-						float3 lhat, float inv_d2, float3 n)
+SKR_DEV float3 fog_term(const float4 *__restrict__ B, const SceneView &sv, const uint4 &r, int call, float p_no, int j, float3 base, float3 alb_l,
+						float3 lhat, float3 n)
 {
-	const float *fogp = reinterpret_cast<const float *>(B + sv.off_fogp);
-	const float p_no  = fogp[(sidx * sv.L + i) * sv.F + j];
+	// base  = kd * lcol * (inv_d2 * max(0, n.lhat)): the no-interaction return, the same for both calls
+	// alb_l = albedo_j * lcol
 	if(rng_unit(call ? r.y : r.x) > p_no)
 	{
-		return kd * lcol * (inv_d2 * fmaxf(0.0f, dot(n, lhat)));
+		return base;
 	}
 	const uint32_t w = call ? r.w : r.z;
-	const float4 fa	 = B[sv.off_foga + j];
-	const float3 nd	 = f3(fmaf(rng_pm1_10(w & 1023u), fa.x, lhat.x), fmaf(rng_pm1_10((w >> 10) & 1023u), fa.x, lhat.y),
-						  fmaf(rng_pm1_10((w >> 20) & 1023u), fa.x, lhat.z));
-	return f3(B[sv.off_fogalb + j]) * lcol * fmaxf(0.0f, dot(n, nd));
+	const float fa	 = B[sv.off_foga + j].x;
+	const float3 nd	 = f3(fmaf(rng_pm1_10(w & 1023u), fa, lhat.x), fmaf(rng_pm1_10((w >> 10) & 1023u), fa, lhat.y),
+						  fmaf(rng_pm1_10((w >> 20) & 1023u), fa, lhat.z));
+	return alb_l * fmaxf(0.0f, dot(n, nd));
 }
 
 // direct_illumination as HEAD computes it (src/raytrace.h:36-44): ambient + diffuse + specular.  One shadow ray per
@@ -488,7 +545,8 @@ SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, b
 	const float3 ks		= f3(B[sv.off_spec + sidx]);
 	const bool has_spec = ks.x != 0.0f || ks.y != 0.0f || ks.z != 0.0f;
 	float3 col		= f3(am);
-	const float3 view = normalize_fast(sv.cam_pos - p);
+	const bool fog	= FOG && sv.F > 0;
+	const float3 view = (has_spec && (!fog || sv.D > 0)) ? normalize_fast(sv.cam_pos - p) : f3(0.0f, 0.0f, 0.0f); // specular terms only
 	for(int i = 0; i < sv.L; i++)
 	{
 		const float3 lv	  = f3(B[sv.off_plpos + i]) - p;
@@ -509,13 +567,17 @@ SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, b
 		}
 		const float3 lcol  = f3(B[sv.off_plcol + i]);
 		const float inv_d2 = __fdividef(1.0f, d2);
-		if(FOG && sv.F > 0)
+		if(fog)
 		{
+			const float3 base = kd * lcol * (inv_d2 * fmaxf(0.0f, dot(n, lhat)));
+			const float *fogp = reinterpret_cast<const float *>(B + sv.off_fogp) + (sidx * sv.L + i) * sv.F;
 			for(int j = 0; j < sv.F; j++)
 			{
-				const uint4 r = rng_block(rng, 1u + (uint32_t) (i * sv.F + j));
-				col += fog_term(B, sv, r, 0, i, j, sidx, kd, lcol, lhat, inv_d2, n);
-				col += fog_term(B, sv, r, 1, i, j, sidx, kd, lcol, lhat, inv_d2, n);
+				const uint4 r	   = rng_block(rng, 1u + (uint32_t) (i * sv.F + j));
+				const float3 alb_l = f3(B[sv.off_fogalb + j]) * lcol;
+				const float p_no   = fogp[j];
+				col += fog_term(B, sv, r, 0, p_no, j, base, alb_l, lhat, n);
+				col += fog_term(B, sv, r, 1, p_no, j, base, alb_l, lhat, n);
 			}
 		}
 		else
@@ -600,4 +662,33 @@ SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float
 		cnt.hits++;
 	}
 	return s;
+}
+
+// Two closest-hit queries from one origin (bounce rays; see closest_sphere_x2).
+template <bool STATS, bool TRIS>
+SKR_DEV void closest_hit_x2(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d0, float3 d1, float &t0, int &h0, float &t1, int &h1,
+							Counters &cnt)
+{
+	if(STATS)
+	{
+		cnt.ch += 2;
+	}
+	closest_sphere_x2<STATS>(B + sv.off_pgeom, sv.S4 >> 1, sv.S, o, d0, d1, t0, h0, t1, h1, cnt);
+	h0 = h0 < 0 ? -2 : h0; // no sphere: background, unless a triangle claims the ray
+	h1 = h1 < 0 ? -2 : h1;
+	if(TRIS && sv.T > 0)
+	{
+		if(tri_any_hit_line<STATS>(sv, o, d0, t0, cnt))
+		{
+			h0 = -1;
+		}
+		if(tri_any_hit_line<STATS>(sv, o, d1, t1, cnt))
+		{
+			h1 = -1;
+		}
+	}
+	if(STATS)
+	{
+		cnt.hits += (h0 >= 0) + (h1 >= 0);
+	}
 }

@@ -53,6 +53,11 @@ struct FrameParams
 	uint8_t *tiles8; // compact tile-major buffer or null
 	uint8_t *peers[8]; // skr_render_peers_device: row-major RGB8 frames (one per GPU of the box, peer-mapped) or null
 	int n_peers;
+	// Copy-out overlapped with the kernel (skr_render, single-kernel frames): CTAs are grouped by blockIdx into bands of
+	// `band_ctas` (whole tile rows); the CTA that completes a band publishes band_seq in band_flag[band], which a
+	// stream-ordered wait on the copy stream is parked on.  Null when unused.
+	unsigned *band_count, *band_flag;
+	unsigned band_ctas, band_seq;
 	long long *accum; // 3 per local pixel (gi only)
 	unsigned long long *counters; // 8 device counters (STATS)
 	int *err;
@@ -369,6 +374,22 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			write_pixel(fp, lp, p, sum);
 		}
 	}
+	if(!GI && fp.band_flag)
+	{
+		__syncthreads(); // every pixel store of this CTA is issued
+		if(threadIdx.x == 0)
+		{
+			__threadfence_system();
+			const unsigned b	= blockIdx.x / fp.band_ctas;
+			const unsigned left = gridDim.x - b * fp.band_ctas;
+			const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
+			if(atomicAdd(fp.band_count + b, 1u) + 1u == want)
+			{
+				__threadfence_system();
+				atomicExch(fp.band_flag + b, fp.band_seq);
+			}
+		}
+	}
 	flush_counters<STATS>(fp, cnt);
 }
 
@@ -422,21 +443,8 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 		basis_from_normal(n, nt, nb);
 		const float3 tk = thr * kd * (6.28318530717958648f / (float) fp.n_gi);
 		const float3 o	= adds_rn(hp, 0.00001f);
-		uint4 r = make_uint4(0u, 0u, 0u, 0u);
-		for(int c = 0; c < fp.n_gi; c++)
-		{
-			if((c & 1) == 0)
-			{
-				r = rng_block(rng, fp.slot_gi + ((uint32_t) c >> 1)); // children 2m and 2m+1 share a block
-			}
-			const float r1 = rng_unit((c & 1) ? r.z : r.x), r2 = rng_unit((c & 1) ? r.w : r.y);
-			const float3 d = gi_child_dir(r1, r2, n, nt, nb);
-			float t		   = 0.0f;
-			int h		   = -3;
-			if(valid)
-			{
-				h = closest_hit<false, STATS, TRIS>(B, sv, o, d, t, cnt);
-			}
+		// one child: weight, miss -> background, hit -> exact t and a push to the next level
+		const auto finish = [&](int c, float3 d, float r1, float t, int h) {
 			const float3 w = tk * r1;
 			if(h == -2)
 			{
@@ -448,6 +456,34 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			}
 			const float3 cp = add_rn(o, muls_rn(d, t));
 			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, fp.err);
+		};
+		// children 2m and 2m+1 share a Philox block AND the per-sphere origin terms of their intersection tests
+		for(int c = 0; c < fp.n_gi; c += 2)
+		{
+			const uint4 r	= rng_block(rng, fp.slot_gi + ((uint32_t) c >> 1));
+			const float r1a = rng_unit(r.x), r2a = rng_unit(r.y);
+			const float3 da = gi_child_dir(r1a, r2a, n, nt, nb);
+			float ta = 0.0f, tb = 0.0f;
+			int ha = -3, hb = -3;
+			if(c + 1 < fp.n_gi)
+			{
+				const float r1b = rng_unit(r.z), r2b = rng_unit(r.w);
+				const float3 db = gi_child_dir(r1b, r2b, n, nt, nb);
+				if(valid)
+				{
+					closest_hit_x2<STATS, TRIS>(B, sv, o, da, db, ta, ha, tb, hb, cnt);
+				}
+				finish(c, da, r1a, ta, ha);
+				finish(c + 1, db, r1b, tb, hb);
+			}
+			else
+			{
+				if(valid)
+				{
+					ha = closest_hit<false, STATS, TRIS>(B, sv, o, da, ta, cnt);
+				}
+				finish(c, da, r1a, ta, ha);
+			}
 		}
 	}
 	if(valid)

@@ -415,6 +415,33 @@ def test_bundle_culling_is_exact_random_scenes(gpu, seed):
         assert getattr(sa, f) == getattr(sb, f), f
 
 
+@pytest.mark.parametrize("scene,kw", [("spheres2", dict(width=1920, height=1080, grid_size=2, use_shadows=True, seed=5)),
+                                      ("dragon", dict(width=1000, height=700, grid_size=2, seed=6)),  # ragged tile columns / rows
+                                      ("bear", dict(width=1280, height=720, use_shadows=True, grid_size=3, seed=7))])
+def test_overlapped_copy_out_into_pinned_host_memory(gpu, gscenes, scene, kw):
+    """skr_render with page-locked destinations copies the frame out in bands while the kernel is still running
+    (stream-ordered waits on per-band flags); the bytes are those of the plain copy-after-kernel path."""
+    import torch
+    gpu.upload(gscenes[scene])
+    o = S.Options(**kw)
+    ref32, ref8, _ = gpu.render(o)                                   # pageable numpy buffers: copy after the kernel
+    for trial in range(3):
+        h8 = torch.full((o.height, o.width, 3), 77, dtype=torch.uint8).pin_memory()
+        h32 = torch.full((o.height, o.width, 3), -1.0, dtype=torch.float32).pin_memory()
+        gpu.render(o, rgb8=h8.numpy(), rgb32=h32.numpy())
+        assert np.array_equal(h8.numpy(), ref8) and np.array_equal(h32.numpy().view(np.uint32), ref32.view(np.uint32))
+        h8b = torch.zeros((o.height, o.width, 3), dtype=torch.uint8).pin_memory()
+        gpu.render(o, rgb8=h8b.numpy(), want_rgb32=False)
+        assert np.array_equal(h8b.numpy(), ref8)
+    os.environ["SKR_NO_OVERLAP"] = "1"
+    try:
+        h8 = torch.zeros((o.height, o.width, 3), dtype=torch.uint8).pin_memory()
+        gpu.render(o, rgb8=h8.numpy(), want_rgb32=False)
+    finally:
+        del os.environ["SKR_NO_OVERLAP"]
+    assert np.array_equal(h8.numpy(), ref8)
+
+
 def test_queue_capacity_does_not_change_the_image(gpu, gscenes):
     gpu.upload(gscenes["spheres2"])
     a, _, sa = gpu.render(S.Options(**GI_KW))
