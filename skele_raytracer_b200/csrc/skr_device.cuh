@@ -184,61 +184,60 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 	return best;
 }
 
-// closest_sphere_table<false, false> for TWO rays from the same origin (a pair of GI children of one hit): e = o - c
-// and cc = e.e - r^2 of a sphere pair are formed once and serve both rays -- 8 of the 25 instructions per (pair, ray).
+// closest_sphere_table<false, false> for K rays from the same origin (GI children of one hit): e = o - c and
+// cc = e.e - r^2 of a sphere pair are formed once and serve all K rays -- 8 of the 25 instructions per (pair, ray).
 // Per ray the operations and their order are those of the one-ray form: same winner, same t.
-template <bool STATS>
-SKR_DEV void closest_sphere_x2(const float4 *__restrict__ G, int NP, int S, float3 o, float3 d0, float3 d1, float &t0, int &s0, float &t1, int &s1,
-							   Counters &cnt)
+template <int K, bool STATS>
+SKR_DEV void closest_sphere_xk(const float4 *__restrict__ G, int NP, int S, float3 o, const float3 (&d)[K], float (&t)[K], int (&s)[K], Counters &cnt)
 {
-	const float a0 = dot(d0, d0), a1 = dot(d1, d1);
-	int b0 = -1, b1 = -1;
-	float um0 = CUDART_INF_F, um1 = CUDART_INF_F;
+	float a[K], um[K];
+	int b[K];
+#pragma unroll
+	for(int k = 0; k < K; k++)
+	{
+		a[k]  = dot(d[k], d[k]);
+		um[k] = CUDART_INF_F;
+		b[k]  = -1;
+	}
 	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
-	const float2 d0x = splat2(d0.x), d0y = splat2(d0.y), d0z = splat2(d0.z), na0 = splat2(-a0);
-	const float2 d1x = splat2(d1.x), d1y = splat2(d1.y), d1z = splat2(d1.z), na1 = splat2(-a1);
 #pragma unroll 2
 	for(int p = 0; p < NP; p++)
 	{
 		const float4 g0 = G[2 * p], g1 = G[2 * p + 1];
 		const float2 ex = add2(ox, f2(g0.x, g0.y)), ey = add2(oy, f2(g0.z, g0.w)), ez = add2(oz, f2(g1.x, g1.y));
 		const float2 cc = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, f2(g1.z, g1.w))));
-		const float2 h0 = fma2(d0z, ez, fma2(d0y, ey, mul2(d0x, ex)));
-		const float2 h1 = fma2(d1z, ez, fma2(d1y, ey, mul2(d1x, ex)));
-		const float2 q0 = fma2(h0, h0, mul2(na0, cc));
-		const float2 q1 = fma2(h1, h1, mul2(na1, cc));
 		if(STATS)
 		{
-			cnt.st += 2 * ((2 * p < S) + (2 * p + 1 < S));
-			cnt.stp += (q0.x >= 0.0f) + (q0.y >= 0.0f) + (q1.x >= 0.0f) + (q1.y >= 0.0f);
+			cnt.st += K * ((2 * p < S) + (2 * p + 1 < S));
 		}
-		const float u0x = -h0.x - sqrt_approx(q0.x), u0y = -h0.y - sqrt_approx(q0.y);
-		const float u1x = -h1.x - sqrt_approx(q1.x), u1y = -h1.y - sqrt_approx(q1.y);
-		if((u0x > a0) & (u0x < um0))
+#pragma unroll
+		for(int k = 0; k < K; k++)
 		{
-			um0 = u0x;
-			b0	= 2 * p;
-		}
-		if((u0y > a0) & (u0y < um0))
-		{
-			um0 = u0y;
-			b0	= 2 * p + 1;
-		}
-		if((u1x > a1) & (u1x < um1))
-		{
-			um1 = u1x;
-			b1	= 2 * p;
-		}
-		if((u1y > a1) & (u1y < um1))
-		{
-			um1 = u1y;
-			b1	= 2 * p + 1;
+			const float2 h = fma2(splat2(d[k].z), ez, fma2(splat2(d[k].y), ey, mul2(splat2(d[k].x), ex)));
+			const float2 q = fma2(h, h, mul2(splat2(-a[k]), cc));
+			if(STATS)
+			{
+				cnt.stp += (q.x >= 0.0f) + (q.y >= 0.0f);
+			}
+			const float ux = -h.x - sqrt_approx(q.x), uy = -h.y - sqrt_approx(q.y);
+			if((ux > a[k]) & (ux < um[k]))
+			{
+				um[k] = ux;
+				b[k]  = 2 * p;
+			}
+			if((uy > a[k]) & (uy < um[k]))
+			{
+				um[k] = uy;
+				b[k]  = 2 * p + 1;
+			}
 		}
 	}
-	t0 = b0 >= 0 ? __fdiv_rn(um0, a0) : CUDART_INF_F;
-	t1 = b1 >= 0 ? __fdiv_rn(um1, a1) : CUDART_INF_F;
-	s0 = b0;
-	s1 = b1;
+#pragma unroll
+	for(int k = 0; k < K; k++)
+	{
+		t[k] = b[k] >= 0 ? __fdiv_rn(um[k], a[k]) : CUDART_INF_F;
+		s[k] = b[k];
+	}
 }
 
 template <bool PRIMARY, bool STATS>
@@ -664,31 +663,26 @@ SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float
 	return s;
 }
 
-// Two closest-hit queries from one origin (bounce rays; see closest_sphere_x2).
-template <bool STATS, bool TRIS>
-SKR_DEV void closest_hit_x2(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d0, float3 d1, float &t0, int &h0, float &t1, int &h1,
-							Counters &cnt)
+// K closest-hit queries from one origin (bounce rays; see closest_sphere_xk).
+template <int K, bool STATS, bool TRIS>
+SKR_DEV void closest_hit_xk(const float4 *__restrict__ B, const SceneView &sv, float3 o, const float3 (&d)[K], float (&t)[K], int (&h)[K], Counters &cnt)
 {
 	if(STATS)
 	{
-		cnt.ch += 2;
+		cnt.ch += K;
 	}
-	closest_sphere_x2<STATS>(B + sv.off_pgeom, sv.S4 >> 1, sv.S, o, d0, d1, t0, h0, t1, h1, cnt);
-	h0 = h0 < 0 ? -2 : h0; // no sphere: background, unless a triangle claims the ray
-	h1 = h1 < 0 ? -2 : h1;
-	if(TRIS && sv.T > 0)
+	closest_sphere_xk<K, STATS>(B + sv.off_pgeom, sv.S4 >> 1, sv.S, o, d, t, h, cnt);
+#pragma unroll
+	for(int k = 0; k < K; k++)
 	{
-		if(tri_any_hit_line<STATS>(sv, o, d0, t0, cnt))
+		h[k] = h[k] < 0 ? -2 : h[k]; // no sphere: background, unless a triangle claims the ray
+		if(TRIS && sv.T > 0 && tri_any_hit_line<STATS>(sv, o, d[k], t[k], cnt))
 		{
-			h0 = -1;
+			h[k] = -1;
 		}
-		if(tri_any_hit_line<STATS>(sv, o, d1, t1, cnt))
+		if(STATS)
 		{
-			h1 = -1;
+			cnt.hits += h[k] >= 0;
 		}
-	}
-	if(STATS)
-	{
-		cnt.hits += (h0 >= 0) + (h1 >= 0);
 	}
 }

@@ -26,6 +26,9 @@
 #define SKR_MIN_BLOCKS 7
 #endif
 #define SKR_FIX_SCALE 4294967296.0f
+#ifndef SKR_GI_BATCH
+#define SKR_GI_BATCH 2 // GI children traced together (even)
+#endif
 
 struct Queue
 {
@@ -457,33 +460,51 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			const float3 cp = add_rn(o, muls_rn(d, t));
 			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, fp.err);
 		};
-		// children 2m and 2m+1 share a Philox block AND the per-sphere origin terms of their intersection tests
-		for(int c = 0; c < fp.n_gi; c += 2)
+		// children are traced SKR_GI_BATCH at a time: they share the per-sphere origin terms of their intersection tests
+		// (children 2m and 2m+1 also share a Philox block)
+		int c = 0;
+		for(; c + SKR_GI_BATCH <= fp.n_gi; c += SKR_GI_BATCH)
 		{
-			const uint4 r	= rng_block(rng, fp.slot_gi + ((uint32_t) c >> 1));
-			const float r1a = rng_unit(r.x), r2a = rng_unit(r.y);
-			const float3 da = gi_child_dir(r1a, r2a, n, nt, nb);
-			float ta = 0.0f, tb = 0.0f;
-			int ha = -3, hb = -3;
-			if(c + 1 < fp.n_gi)
+			float3 d[SKR_GI_BATCH];
+			float r1[SKR_GI_BATCH], t[SKR_GI_BATCH];
+			int h[SKR_GI_BATCH];
+#pragma unroll
+			for(int k = 0; k < SKR_GI_BATCH; k += 2)
 			{
-				const float r1b = rng_unit(r.z), r2b = rng_unit(r.w);
-				const float3 db = gi_child_dir(r1b, r2b, n, nt, nb);
-				if(valid)
-				{
-					closest_hit_x2<STATS, TRIS>(B, sv, o, da, db, ta, ha, tb, hb, cnt);
-				}
-				finish(c, da, r1a, ta, ha);
-				finish(c + 1, db, r1b, tb, hb);
+				const uint4 r = rng_block(rng, fp.slot_gi + ((uint32_t) (c + k) >> 1));
+				r1[k]		  = rng_unit(r.x);
+				d[k]		  = gi_child_dir(r1[k], rng_unit(r.y), n, nt, nb);
+				r1[k + 1]	  = rng_unit(r.z);
+				d[k + 1]	  = gi_child_dir(r1[k + 1], rng_unit(r.w), n, nt, nb);
+				t[k] = t[k + 1] = 0.0f;
+				h[k] = h[k + 1] = -3;
 			}
-			else
+			if(valid)
 			{
-				if(valid)
-				{
-					ha = closest_hit<false, STATS, TRIS>(B, sv, o, da, ta, cnt);
-				}
-				finish(c, da, r1a, ta, ha);
+				closest_hit_xk<SKR_GI_BATCH, STATS, TRIS>(B, sv, o, d, t, h, cnt);
 			}
+#pragma unroll
+			for(int k = 0; k < SKR_GI_BATCH; k++)
+			{
+				finish(c + k, d[k], r1[k], t[k], h[k]);
+			}
+		}
+		uint4 r = make_uint4(0u, 0u, 0u, 0u);
+		for(; c < fp.n_gi; c++) // remainder, one by one
+		{
+			if((c & 1) == 0)
+			{
+				r = rng_block(rng, fp.slot_gi + ((uint32_t) c >> 1));
+			}
+			const float r1 = rng_unit((c & 1) ? r.z : r.x), r2 = rng_unit((c & 1) ? r.w : r.y);
+			const float3 d = gi_child_dir(r1, r2, n, nt, nb);
+			float t		   = 0.0f;
+			int h		   = -3;
+			if(valid)
+			{
+				h = closest_hit<false, STATS, TRIS>(B, sv, o, d, t, cnt);
+			}
+			finish(c, d, r1, t, h);
 		}
 	}
 	if(valid)
