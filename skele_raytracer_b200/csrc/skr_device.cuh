@@ -96,6 +96,25 @@ SKR_DEV uint4 rng_block(const RngCtx &r, uint32_t slot) { return philox4x32_10(m
 // h = d.e (= b/2), cc = e.e - r^2, a = d.d:   disc/4 = h^2 - a*cc,   t2 = (-h - sqrt(h^2 - a*cc)) / a.
 // Same roots, one multiply less per test; the winner's t is then recomputed with the reference's own expression.
 
+#define SKR_TAG_BITS 6
+#define SKR_TAG_MASK ((1u << SKR_TAG_BITS) - 1u)
+// ranking keys of a sphere pair for incoherent rays: v = (-h - a) - sqrt(d4), positive iff 1.0 < t2 (see closest_sphere_table)
+SKR_DEV float2 rank_keys(float2 h, float2 d4, float na)
+{
+	const float2 hm = add2(f2(-h.x, -h.y), splat2(na));
+	return add2(hm, f2(-sqrt_approx(d4.x), -sqrt_approx(d4.y)));
+}
+// winner of the tagged minimum: index from the tag, u = v + a; keys at or above +inf (negative, NaN, no candidate) and
+// v = 0 (t2 = 1.0 exactly) are misses
+SKR_DEV void untag(uint32_t wmin, float a, int &best, float &umin)
+{
+	if(wmin - (SKR_TAG_MASK + 1u) < 0x7f800000u - (SKR_TAG_MASK + 1u))
+	{
+		best = (int) (wmin & SKR_TAG_MASK);
+		umin = __uint_as_float(wmin & ~SKR_TAG_MASK) + a;
+	}
+}
+
 // Closest sphere along (o, d) with 1.0 < t < inf, strict minimum, first wins ties (src/raytrace.h:149-165).
 // PRIMARY: o is the camera position, e and cc come precomputed from the blob.
 // Two spheres per step in packed FP32x2.  Selection on u = a*t2 = -h - sqrt(d4) (a > 0 is common to a ray's spheres):
@@ -114,6 +133,8 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 	const float na = -a;
 	int best	   = -1;
 	float umin	   = CUDART_INF_F;
+	const bool tagged = NP <= (1 << (SKR_TAG_BITS - 1));
+	uint32_t wmin	  = 0xffffffffu;
 	const float2 dx = splat2(d.x), dy = splat2(d.y), dz = splat2(d.z), na2 = splat2(na), two = splat2(2.0f);
 	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
 #pragma unroll 2
@@ -163,22 +184,38 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 		else
 		{
 			// bounce rays are incoherent: in every warp some lane's line hits this sphere, so branches would only add
-			// divergence.  Rank candidates directly on u = -h - sqrt(d4) with an approximate MUFU square root (NaN for
-			// d4 < 0 fails both comparisons): 1.0 < t2 < tmin  <=>  a < u < umin.  No branch, no IEEE sqrt sequence;
-			// the caller recomputes the winner's t exactly (sphere_t_ref).
-			const float ux = -h.x - sqrt_approx(d4.x);
-			const float uy = -h.y - sqrt_approx(d4.y);
-			if((ux > a) & (ux < umin))
+			// divergence.  Rank candidates directly on v = u - a = (-h - a) - sqrt(d4) with an approximate MUFU square
+			// root: 1.0 < t2 <=> v > 0.  The sphere index rides in the low SKR_TAG_BITS mantissa bits of v; as UNSIGNED
+			// integers the positive floats order like floats and sit below every negative float and NaN (d4 < 0), so
+			// one 3-input unsigned minimum per pair keeps the closest valid candidate, lower index on ties.  No branch,
+			// no predicate chain; the caller recomputes the winner's t exactly (sphere_t_ref).
+			if(tagged)
 			{
-				umin = ux;
-				best = 2 * p;
+				const float2 v = rank_keys(h, d4, na);
+				wmin		   = __vimin3_u32(wmin, (__float_as_uint(v.x) & ~SKR_TAG_MASK) | (uint32_t) (2 * p),
+											  (__float_as_uint(v.y) & ~SKR_TAG_MASK) | (uint32_t) (2 * p + 1));
 			}
-			if((uy > a) & (uy < umin))
+			else
 			{
-				umin = uy;
-				best = 2 * p + 1;
+				// more than 2^SKR_TAG_BITS spheres: compare-and-select on u = -h - sqrt(d4), a < u < umin
+				const float ux = -h.x - sqrt_approx(d4.x);
+				const float uy = -h.y - sqrt_approx(d4.y);
+				if((ux > a) & (ux < umin))
+				{
+					umin = ux;
+					best = 2 * p;
+				}
+				if((uy > a) & (uy < umin))
+				{
+					umin = uy;
+					best = 2 * p + 1;
+				}
 			}
 		}
+	}
+	if(!COHERENT && tagged)
+	{
+		untag(wmin, a, best, umin);
 	}
 	tmin = best >= 0 ? __fdiv_rn(umin, a) : CUDART_INF_F;
 	return best;
@@ -186,18 +223,18 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 
 // closest_sphere_table<false, false> for K rays from the same origin (GI children of one hit): e = o - c and
 // cc = e.e - r^2 of a sphere pair are formed once and serve all K rays -- 8 of the 25 instructions per (pair, ray).
-// Per ray the operations and their order are those of the one-ray form: same winner, same t.
+// Per ray the operations and their order are those of the one-ray form (tagged ranking): same winner, same t.
+// Requires NP <= 2^(SKR_TAG_BITS - 1) (closest_hit_xk checks).
 template <int K, bool STATS>
 SKR_DEV void closest_sphere_xk(const float4 *__restrict__ G, int NP, int S, float3 o, const float3 (&d)[K], float (&t)[K], int (&s)[K], Counters &cnt)
 {
-	float a[K], um[K];
-	int b[K];
+	float a[K];
+	uint32_t wm[K];
 #pragma unroll
 	for(int k = 0; k < K; k++)
 	{
 		a[k]  = dot(d[k], d[k]);
-		um[k] = CUDART_INF_F;
-		b[k]  = -1;
+		wm[k] = 0xffffffffu;
 	}
 	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z);
 #pragma unroll 2
@@ -219,24 +256,19 @@ SKR_DEV void closest_sphere_xk(const float4 *__restrict__ G, int NP, int S, floa
 			{
 				cnt.stp += (q.x >= 0.0f) + (q.y >= 0.0f);
 			}
-			const float ux = -h.x - sqrt_approx(q.x), uy = -h.y - sqrt_approx(q.y);
-			if((ux > a[k]) & (ux < um[k]))
-			{
-				um[k] = ux;
-				b[k]  = 2 * p;
-			}
-			if((uy > a[k]) & (uy < um[k]))
-			{
-				um[k] = uy;
-				b[k]  = 2 * p + 1;
-			}
+			const float2 v = rank_keys(h, q, -a[k]);
+			wm[k]		   = __vimin3_u32(wm[k], (__float_as_uint(v.x) & ~SKR_TAG_MASK) | (uint32_t) (2 * p),
+										  (__float_as_uint(v.y) & ~SKR_TAG_MASK) | (uint32_t) (2 * p + 1));
 		}
 	}
 #pragma unroll
 	for(int k = 0; k < K; k++)
 	{
-		t[k] = b[k] >= 0 ? __fdiv_rn(um[k], a[k]) : CUDART_INF_F;
-		s[k] = b[k];
+		int b	 = -1;
+		float um = CUDART_INF_F;
+		untag(wm[k], a[k], b, um);
+		t[k] = b >= 0 ? __fdiv_rn(um, a[k]) : CUDART_INF_F;
+		s[k] = b;
 	}
 }
 
@@ -667,6 +699,15 @@ SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float
 template <int K, bool STATS, bool TRIS>
 SKR_DEV void closest_hit_xk(const float4 *__restrict__ B, const SceneView &sv, float3 o, const float3 (&d)[K], float (&t)[K], int (&h)[K], Counters &cnt)
 {
+	if((sv.S4 >> 1) > (1 << (SKR_TAG_BITS - 1))) // too many spheres for index tags: one by one
+	{
+#pragma unroll
+		for(int k = 0; k < K; k++)
+		{
+			h[k] = closest_hit<false, STATS, TRIS>(B, sv, o, d[k], t[k], cnt);
+		}
+		return;
+	}
 	if(STATS)
 	{
 		cnt.ch += K;
