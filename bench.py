@@ -183,7 +183,7 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
     if world > 1:
         tiles = torch.empty(r.tiles_bytes(base), dtype=torch.uint8, device=dev)
         cst = r.render_tiles_device(dataclasses.replace(base, collect_stats=True), tiles.data_ptr()).as_dict()
-        keys = ["closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "tri_tests", "bvh_node_visits", "sphere_hits", "light_evals"]
+        keys = ["closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "tri_tests", "bvh_node_visits", "sphere_hits", "light_evals", "sphere_tests_executed"]
         cst_local = dict(cst)
         t = torch.tensor([float(cst[k]) for k in keys], dtype=torch.float64, device=dev)
         dist.all_reduce(t)
@@ -359,6 +359,10 @@ def main_gpu(args, rank, world, local_rank):
         dom_ms = m["kernel_ms_per_step"][dom] or m["ms_per_step"]
         dom_launches = 1 if dom == "primary" else max(1, round(m["launches"] / steps))
         achieved = flops / (dom_ms * 1e-3) / 1e12
+        # what the kernels executed: bundle culling proves most sphere tests of a jittered pixel unnecessary
+        st0 = m["stats_rank0"]
+        flops_exec = flops - 25.0 * (st0["sphere_tests"] - st0["sphere_tests_executed"])
+        executed = flops_exec / (dom_ms * 1e-3) / 1e12
         frame_bytes = m["kw"]["width"] * m["kw"]["height"] * 3
         line = {
             "metric": "Mrays/s", "value": m["value"], "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -380,6 +384,10 @@ def main_gpu(args, rank, world, local_rank):
                          "traffic_source": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[1], "kernel": "primary_kernel" if dom == "primary" else "shade_expand_kernel",
                          "kernel_ms_per_frame": dom_ms, "kernel_launches_per_frame": dom_launches,
                          "flops_per_frame_algorithmic_this_rank": flops,
+                         "executed": {"tflops": executed, "frac": executed / fp32_peak, "flops_per_frame_this_rank": flops_exec,
+                                      "sphere_tests_algorithmic": st0["sphere_tests"], "sphere_tests_executed": st0["sphere_tests_executed"],
+                                      "note": "`achieved` counts the reference algorithm's arithmetic (every sphere per query); conservative bundle culling "
+                                              "skips tests that provably fail, so the FP32 pipe executed only this much"},
                          "peak_source": "FFMA microbenchmark measured live in this run (skr_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                          "note": "compute-bound FP32 CUDA-core path (no dense contraction -> tensor cores unused); algorithmic HBM traffic is the RGB8 frame only",
                          "hbm": {"algorithmic_bytes_per_frame": frame_bytes, "achieved_gbs": frame_bytes / (m["ms_per_step"] * 1e-3) / 1e9,

@@ -264,11 +264,11 @@ int main(int argc, char *argv[])
 		const double rays = (double) st.closest_hit_rays + (double) st.shadow_rays;
 		printf("{\"scene\": {\"spheres\": %d, \"triangles\": %d, \"point_lights\": %d, \"fogs\": %d}, \"parse_ms\": %.3f, \"upload_ms\": %.3f, "
 			   "\"render_wall_ms\": %.3f, \"device_ms\": %.3f, \"primary_ms\": %.3f, \"bounce_ms\": %.3f, \"resolve_ms\": %.3f, \"d2h_ms\": %.3f, "
-			   "\"closest_hit_rays\": %llu, \"shadow_rays\": %llu, \"sphere_tests\": %llu, \"tri_tests\": %llu, \"bvh_node_visits\": %llu, "
+			   "\"closest_hit_rays\": %llu, \"shadow_rays\": %llu, \"sphere_tests\": %llu, \"sphere_tests_executed\": %llu, \"tri_tests\": %llu, \"bvh_node_visits\": %llu, "
 			   "\"kernel_launches\": %u, \"mrays_per_s\": %.1f}\n",
 			   scene.nspheres(), scene.ntris(), scene.nplights(), scene.nfogs(), ms(t0, t1), ms(t1, t2), ms(t2, t3), st.ms_total, st.ms_primary, st.ms_bounce,
 			   st.ms_resolve, st.ms_d2h, (unsigned long long) st.closest_hit_rays, (unsigned long long) st.shadow_rays,
-			   (unsigned long long) st.sphere_tests, (unsigned long long) st.tri_tests, (unsigned long long) st.bvh_node_visits, st.kernel_launches,
+			   (unsigned long long) st.sphere_tests, (unsigned long long) st.sphere_tests_executed, (unsigned long long) st.tri_tests, (unsigned long long) st.bvh_node_visits, st.kernel_launches,
 			   st.ms_total > 0 ? rays / (st.ms_total * 1e-3) / 1e6 : 0.0);
 	}
 	skr_destroy(ctx);

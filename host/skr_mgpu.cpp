@@ -293,6 +293,7 @@ int skr_mgpu_render(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stat
 			stats->bvh_node_visits += st[i].bvh_node_visits;
 			stats->sphere_hits += st[i].sphere_hits;
 			stats->light_evals += st[i].light_evals;
+			stats->sphere_tests_executed += st[i].sphere_tests_executed;
 			stats->queue_entries += st[i].queue_entries;
 			stats->kernel_launches += st[i].kernel_launches;
 			stats->queue_chunks += st[i].queue_chunks;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SKR_ABI_VERSION 1
+#define SKR_ABI_VERSION 2
 
 typedef struct skr_ctx skr_ctx;
 
@@ -119,6 +119,10 @@ typedef struct skr_stats
 	float ms_resolve; /* accumulate -> float/RGB8 */
 	float ms_h2d;	  /* 0 for *_device entry points */
 	float ms_d2h;
+	/* counter (valid when collect_stats != 0), ABI 2: sphere tests the kernels actually EXECUTED, bundle-culling tests
+	 * included.  sphere_tests above stays the reference algorithm's count (every sphere per query, shadow loops up to
+	 * their first occluder); the difference is what conservative culling proved unnecessary. */
+	uint64_t sphere_tests_executed;
 } skr_stats;
 
 /* device < 0: use the current CUDA device. */

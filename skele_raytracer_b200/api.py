@@ -58,7 +58,7 @@ class Stats(C.Structure):
                 ("sphere_hits", C.c_uint64), ("light_evals", C.c_uint64), ("queue_entries", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("queue_chunks", C.c_uint32), ("ms_total", C.c_float),
                 ("ms_primary", C.c_float), ("ms_bounce", C.c_float), ("ms_resolve", C.c_float), ("ms_h2d", C.c_float),
-                ("ms_d2h", C.c_float)]
+                ("ms_d2h", C.c_float), ("sphere_tests_executed", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -79,7 +79,7 @@ struct skr_ctx
 	int n_levels_alloc = 0;
 	unsigned *h_count = nullptr; // pinned
 
-	unsigned long long *d_counters = nullptr; // 8
+	unsigned long long *d_counters = nullptr; // 9 (16 allocated)
 	int *d_err = nullptr;
 	int *h_err = nullptr; // pinned
 
@@ -677,7 +677,7 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	pl.fp.err	   = ctx->d_err;
 	if(!async)
 	{
-		CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 8, st));
+		CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 16, st));
 		CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
 		CK(cudaEventRecord(ctx->ev_begin, st));
 	}
@@ -696,7 +696,7 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	}
 	CK(cudaEventRecord(ctx->ev_end, st));
 	CK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-	unsigned long long hc[8] = {0};
+	unsigned long long hc[9] = {0};
 	if(want_stats)
 	{
 		CK(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -717,6 +717,7 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 		stats->bvh_node_visits	= hc[5];
 		stats->sphere_hits		= hc[6];
 		stats->light_evals		= hc[7];
+		stats->sphere_tests_executed = hc[8];
 		stats->queue_entries	= ctx->queue_entries;
 		stats->kernel_launches	= ctx->launches;
 		stats->queue_chunks		= ctx->chunks;
@@ -804,7 +805,7 @@ int skr_init(int device, skr_ctx **out)
 		return bail(e, "cudaStreamCreate");
 	}
 	cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-	if((e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8)) != cudaSuccess)
+	if((e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 16)) != cudaSuccess)
 	{
 		return bail(e, "cudaMalloc");
 	}

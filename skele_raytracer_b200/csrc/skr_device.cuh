@@ -50,9 +50,9 @@ struct SceneView
 
 struct Counters // per-thread, reduced at kernel exit when STATS
 {
-	unsigned ch, sh, st, stp, tt, nv, hits, le;
+	unsigned ch, sh, st, stp, tt, nv, hits, le, se;
 };
-SKR_DEV void zero(Counters &c) { c.ch = c.sh = c.st = c.stp = c.tt = c.nv = c.hits = c.le = 0; }
+SKR_DEV void zero(Counters &c) { c.ch = c.sh = c.st = c.stp = c.tt = c.nv = c.hits = c.le = c.se = 0; }
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011).  Keying, identical to oracle/skr_oracle.c.  One call yields 128 bits, so draws
@@ -157,6 +157,7 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 		if(STATS)
 		{
 			cnt.st += (2 * p < S) + (2 * p + 1 < S);
+			cnt.se += (2 * p < S) + (2 * p + 1 < S);
 			cnt.stp += (d4.x >= 0.0f) + (d4.y >= 0.0f);
 		}
 		if(COHERENT)
@@ -246,6 +247,7 @@ SKR_DEV void closest_sphere_xk(const float4 *__restrict__ G, int NP, int S, floa
 		if(STATS)
 		{
 			cnt.st += K * ((2 * p < S) + (2 * p + 1 < S));
+			cnt.se += K * ((2 * p < S) + (2 * p + 1 < S));
 		}
 #pragma unroll
 		for(int k = 0; k < K; k++)
@@ -328,6 +330,10 @@ SKR_DEV bool occluded(const float4 *__restrict__ B, const SceneView &sv, float3 
 			const float2 w	= fma2(two, h, cc);
 			const bool occ0 = (h.x < na) & (d4.x >= 0.0f) & (w.x > na);
 			const bool occ1 = (h.y < na) & (d4.y >= 0.0f) & (w.y > na);
+			if(STATS)
+			{
+				cnt.se += (2 * pp < sv.S) + (2 * pp + 1 < sv.S);
+			}
 			if(STATS && !any) // count like the reference's loop: up to and including the first occluder
 			{
 				cnt.st += (2 * pp < sv.S) + ((2 * pp + 1 < sv.S) & !occ0);
@@ -359,8 +365,13 @@ SKR_DEV bool occluded(const float4 *__restrict__ B, const SceneView &sv, float3 
 //   m = 0.01 |w| for shadow bundles, whose ray origins lie |w| away from the apex (|o - c| <= |u| + |w|).
 // Comparisons are written so that NaN keeps the sphere.  Returns one bit per sphere PAIR.
 // ------------------------------------------------------------------------------------------------
-SKR_DEV uint32_t cull_pairs(const float4 *__restrict__ C, int NP, float3 w, float beta, float m)
+template <bool STATS>
+SKR_DEV uint32_t cull_pairs(const float4 *__restrict__ C, int NP, int S, float3 w, float beta, float m, Counters &cnt)
 {
+	if(STATS)
+	{
+		cnt.se += S; // one bundle test per sphere
+	}
 	const float2 ninv = splat2(-__fdividef(1.0f, dot(w, w)));
 	const float2 wx = splat2(w.x), wy = splat2(w.y), wz = splat2(w.z), b2 = splat2(beta), m2 = splat2(m);
 	uint32_t mask = 0;
@@ -401,6 +412,7 @@ SKR_DEV int closest_sphere_masked(const float4 *__restrict__ G, uint32_t mask, i
 		if(STATS)
 		{
 			cnt.stp += (d4.x >= 0.0f) + (d4.y >= 0.0f);
+			cnt.se += (2 * p < S) + (2 * p + 1 < S);
 		}
 		if(d4.x >= 0.0f)
 		{
@@ -453,6 +465,7 @@ SKR_DEV bool occluded_masked(const float4 *__restrict__ B, const SceneView &sv, 
 		if(STATS)
 		{
 			cnt.stp += (d4.x >= 0.0f) + ((d4.y >= 0.0f) & !occ0);
+			cnt.se += (2 * pp < sv.S) + (2 * pp + 1 < sv.S);
 		}
 		if(occ0 | occ1)
 		{
@@ -471,7 +484,8 @@ SKR_DEV bool occluded_masked(const float4 *__restrict__ B, const SceneView &sv, 
 }
 
 // Shadow-ray masks of the hit points within `rho` of pc, one NP-bit field per point light (sv.cull_shadow).
-SKR_DEV uint64_t shadow_masks(const float4 *__restrict__ B, const SceneView &sv, float3 pc, float rho)
+template <bool STATS>
+SKR_DEV uint64_t shadow_masks(const float4 *__restrict__ B, const SceneView &sv, float3 pc, float rho, Counters &cnt)
 {
 	const int NP		= sv.S4 >> 1;
 	const uint32_t full = NP >= 32 ? 0xffffffffu : (1u << NP) - 1u;
@@ -483,7 +497,7 @@ SKR_DEV uint64_t shadow_masks(const float4 *__restrict__ B, const SceneView &sv,
 		uint32_t mk		= full;
 		if(rho <= 0.45f * len) // asin(x) <= 1.05 x there
 		{
-			mk = cull_pairs(B + sv.off_cull + 3 * NP * (1 + i), NP, w, __fdividef(1.07f * rho, len), 0.01f * len);
+			mk = cull_pairs<STATS>(B + sv.off_cull + 3 * NP * (1 + i), NP, sv.S, w, __fdividef(1.07f * rho, len), 0.01f * len, cnt);
 		}
 		all |= (uint64_t) mk << (i * NP);
 	}

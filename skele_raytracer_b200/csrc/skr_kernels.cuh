@@ -62,7 +62,7 @@ struct FrameParams
 	unsigned *band_count, *band_flag;
 	unsigned band_ctas, band_seq;
 	long long *accum; // 3 per local pixel (gi only)
-	unsigned long long *counters; // 8 device counters (STATS)
+	unsigned long long *counters; // 9 device counters (STATS)
 	int *err;
 };
 
@@ -185,9 +185,9 @@ SKR_DEV void flush_counters(const FrameParams &fp, Counters &c)
 	{
 		return;
 	}
-	unsigned v[8] = {c.ch, c.sh, c.st, c.stp, c.tt, c.nv, c.hits, c.le};
+	unsigned v[9] = {c.ch, c.sh, c.st, c.stp, c.tt, c.nv, c.hits, c.le, c.se};
 #pragma unroll
-	for(int k = 0; k < 8; k++)
+	for(int k = 0; k < 9; k++)
 	{
 		unsigned s = v[k];
 #pragma unroll
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		uint32_t mk		= NP >= 32 ? 0xffffffffu : (1u << NP) - 1u;
 		if(fp.cull_delta <= 0.45f * len)
 		{
-			mk = cull_pairs(B + sv.off_cull, NP, dc, __fdividef(1.05f * fp.cull_delta, len), 0.0f);
+			mk = cull_pairs<STATS>(B + sv.off_cull, NP, sv.S, dc, __fdividef(1.05f * fp.cull_delta, len), 0.0f, cnt);
 		}
 		pmask = __reduce_or_sync(0xffffffffu, p.valid ? mk : 0u);
 	}
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 						const float rho = __fdividef(2.5f * fp.cull_delta * t, fmaxf(ci, 0.05f));
 						pc				= hp;
 						rho2			= rho * rho;
-						smask			= shadow_masks(B, sv, hp, rho);
+						smask			= shadow_masks<STATS>(B, sv, hp, rho, cnt);
 					}
 				}
 				sum += direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt, true, smcull, smask);
