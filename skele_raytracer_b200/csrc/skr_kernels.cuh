@@ -202,40 +202,47 @@ SKR_DEV void flush_counters(const FrameParams &fp, Counters &c)
 	}
 }
 
-// warp-aggregated push: one atomic per warp per call.  Must be called by all 32 lanes.
+// Warp-aggregated push.  queue_reserve: ONE atomic per warp for `count` entries (all 32 lanes call it, count uniform);
+// queue_store: one entry.
+SKR_DEV unsigned queue_reserve(const Queue &q, unsigned count)
+{
+	unsigned base = 0;
+	if(count == 0)
+	{
+		return 0;
+	}
+	if((threadIdx.x & 31) == 0)
+	{
+		base = atomicAdd(q.count, count);
+	}
+	return __shfl_sync(0xffffffffu, base, 0);
+}
+SKR_DEV void queue_store(const Queue &q, unsigned idx, float3 p, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, float3 dir, int *err)
+{
+	if(idx < q.cap)
+	{
+		q.a[idx] = make_float4(p.x, p.y, p.z, u2f(pixel));
+		q.b[idx] = make_float4(thr.x, thr.y, thr.z, u2f(node));
+		q.c[idx] = (sample & 0xffffu) | ((uint32_t) sphere << 16);
+		if(q.d)
+		{
+			q.d[idx] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+		}
+	}
+	else
+	{
+		atomicOr(err, 1); // cannot happen: the host sizes chunks so that a full fan-out fits
+	}
+}
+// one entry per lane that wants one.  Must be called by all 32 lanes.
 SKR_DEV void queue_push(const Queue &q, bool want, float3 p, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, float3 dir,
 						int *err)
 {
 	const unsigned mask = __ballot_sync(0xffffffffu, want);
-	if(mask == 0)
-	{
-		return;
-	}
-	const int lane	 = threadIdx.x & 31;
-	const int leader = __ffs(mask) - 1;
-	unsigned base	 = 0;
-	if(lane == leader)
-	{
-		base = atomicAdd(q.count, (unsigned) __popc(mask));
-	}
-	base = __shfl_sync(0xffffffffu, base, leader);
+	const unsigned base = queue_reserve(q, (unsigned) __popc(mask));
 	if(want)
 	{
-		const unsigned idx = base + __popc(mask & ((1u << lane) - 1u));
-		if(idx < q.cap)
-		{
-			q.a[idx] = make_float4(p.x, p.y, p.z, u2f(pixel));
-			q.b[idx] = make_float4(thr.x, thr.y, thr.z, u2f(node));
-			q.c[idx] = (sample & 0xffffu) | ((uint32_t) sphere << 16);
-			if(q.d)
-			{
-				q.d[idx] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-			}
-		}
-		else
-		{
-			atomicOr(err, 1); // cannot happen: the host sizes chunks so that a full fan-out fits
-		}
+		queue_store(q, base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u)), p, pixel, thr, node, sample, sphere, dir, err);
 	}
 }
 
@@ -446,9 +453,9 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 		basis_from_normal(n, nt, nb);
 		const float3 tk = thr * kd * (6.28318530717958648f / (float) fp.n_gi);
 		const float3 o	= adds_rn(hp, 0.00001f);
-		// one child: weight, miss -> background, hit -> exact t and a push to the next level
-		const auto finish = [&](int c, float3 d, float r1, float t, int h) {
-			const float3 w = tk * r1;
+		// one child: weight, miss -> background, hit -> exact t and hit point
+		const auto finish = [&](float3 d, float r1, float t, int h, float3 &w, float3 &cp) {
+			w = tk * r1;
 			if(h == -2)
 			{
 				contrib += w * sv.background;
@@ -457,11 +464,10 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			{
 				t = sphere_t_ref(o, d, f3(B[sv.off_geom + h]), B[sv.off_spec + h].w, t);
 			}
-			const float3 cp = add_rn(o, muls_rn(d, t));
-			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, fp.err);
+			cp = add_rn(o, muls_rn(d, t));
 		};
 		// children are traced SKR_GI_BATCH at a time: they share the per-sphere origin terms of their intersection tests
-		// (children 2m and 2m+1 also share a Philox block)
+		// (children 2m and 2m+1 also share a Philox block) and ONE queue reservation
 		int c = 0;
 		for(; c + SKR_GI_BATCH <= fp.n_gi; c += SKR_GI_BATCH)
 		{
@@ -483,10 +489,25 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			{
 				closest_hit_xk<SKR_GI_BATCH, STATS, TRIS>(B, sv, o, d, t, h, cnt);
 			}
+			float3 w[SKR_GI_BATCH], cp[SKR_GI_BATCH];
+			unsigned m[SKR_GI_BATCH], total = 0;
 #pragma unroll
 			for(int k = 0; k < SKR_GI_BATCH; k++)
 			{
-				finish(c + k, d[k], r1[k], t[k], h[k]);
+				finish(d[k], r1[k], t[k], h[k], w[k], cp[k]);
+				m[k] = __ballot_sync(0xffffffffu, h[k] >= 0);
+				total += (unsigned) __popc(m[k]);
+			}
+			unsigned at = queue_reserve(out, total);
+#pragma unroll
+			for(int k = 0; k < SKR_GI_BATCH; k++)
+			{
+				if(h[k] >= 0)
+				{
+					queue_store(out, at + __popc(m[k] & ((1u << (threadIdx.x & 31)) - 1u)), cp[k], rng.pixel, w[k], rng.node * fp.node_base + (uint32_t) (c + k) + 1u,
+								rng.sample, h[k], d[k], fp.err);
+				}
+				at += (unsigned) __popc(m[k]);
 			}
 		}
 		uint4 r = make_uint4(0u, 0u, 0u, 0u);
@@ -504,7 +525,9 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			{
 				h = closest_hit<false, STATS, TRIS>(B, sv, o, d, t, cnt);
 			}
-			finish(c, d, r1, t, h);
+			float3 w, cp;
+			finish(d, r1, t, h, w, cp);
+			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, fp.err);
 		}
 	}
 	if(valid)
