@@ -437,6 +437,63 @@ SKR_DEV int closest_sphere_masked(const float4 *__restrict__ G, uint32_t mask, i
 	return best;
 }
 
+// occluded() for TWO shadow rays from the same point (two lights): e = o - c and cc = e.e - r^2 of a sphere pair are formed
+// once and serve both rays.  Per ray the operations are those of occluded().  Returns bit 0 / bit 1.
+template <bool STATS>
+SKR_DEV unsigned occluded_x2(const float4 *__restrict__ B, const SceneView &sv, float3 p, float3 dir0, float3 dir1, Counters &cnt)
+{
+	const float3 o	= adds_rn(p, 0.000001f);
+	const float na0 = -dot(dir0, dir0), na1 = -dot(dir1, dir1);
+	const int NP	= sv.S4 >> 1;
+	const float4 *__restrict__ G = B + sv.off_pgeom;
+	const float2 ox = splat2(o.x), oy = splat2(o.y), oz = splat2(o.z), two = splat2(2.0f);
+	if(STATS)
+	{
+		cnt.sh += 2;
+	}
+	bool any0 = false, any1 = false;
+	for(int p2 = 0; p2 < NP; p2 += 2) // two pairs = four spheres per iteration, one exit test
+	{
+#pragma unroll
+		for(int k = 0; k < 2; k++)
+		{
+			const int pp	= p2 + k;
+			const float4 g0 = G[2 * pp], g1 = G[2 * pp + 1];
+			const float2 ex = add2(ox, f2(g0.x, g0.y)), ey = add2(oy, f2(g0.z, g0.w)), ez = add2(oz, f2(g1.x, g1.y));
+			const float2 cc = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, f2(g1.z, g1.w))));
+			const float2 h0 = fma2(splat2(dir0.z), ez, fma2(splat2(dir0.y), ey, mul2(splat2(dir0.x), ex)));
+			const float2 h1 = fma2(splat2(dir1.z), ez, fma2(splat2(dir1.y), ey, mul2(splat2(dir1.x), ex)));
+			const float2 q0 = fma2(h0, h0, mul2(splat2(na0), cc));
+			const float2 q1 = fma2(h1, h1, mul2(splat2(na1), cc));
+			const float2 w0 = fma2(two, h0, cc), w1 = fma2(two, h1, cc);
+			const bool a0 = (h0.x < na0) & (q0.x >= 0.0f) & (w0.x > na0), b0 = (h0.y < na0) & (q0.y >= 0.0f) & (w0.y > na0);
+			const bool a1 = (h1.x < na1) & (q1.x >= 0.0f) & (w1.x > na1), b1 = (h1.y < na1) & (q1.y >= 0.0f) & (w1.y > na1);
+			if(STATS)
+			{
+				const int real = (2 * pp < sv.S) + (2 * pp + 1 < sv.S);
+				cnt.se += 2 * real;
+				if(!any0) // count like the reference's loops: each ray up to and including its first occluder
+				{
+					cnt.st += (2 * pp < sv.S) + ((2 * pp + 1 < sv.S) & !a0);
+					cnt.stp += (q0.x >= 0.0f) + ((q0.y >= 0.0f) & !a0);
+				}
+				if(!any1)
+				{
+					cnt.st += (2 * pp < sv.S) + ((2 * pp + 1 < sv.S) & !a1);
+					cnt.stp += (q1.x >= 0.0f) + ((q1.y >= 0.0f) & !a1);
+				}
+			}
+			any0 |= a0 | b0;
+			any1 |= a1 | b1;
+		}
+		if(any0 & any1)
+		{
+			break;
+		}
+	}
+	return (any0 ? 1u : 0u) | (any1 ? 2u : 0u);
+}
+
 // occluded() over the pairs of `mask` only (per-lane mask).
 template <bool STATS>
 SKR_DEV bool occluded_masked(const float4 *__restrict__ B, const SceneView &sv, uint32_t mask, float3 p, float3 dir, Counters &cnt)
@@ -567,16 +624,18 @@ SKR_DEV float3 fog_term(const float4 *__restrict__ B, const SceneView &sv, const
 // direct_illumination as HEAD computes it (src/raytrace.h:36-44): ambient + diffuse + specular.  One shadow ray per
 // light serves both terms (the reference casts the same ray twice).  View direction is towards the CAMERA POSITION
 // even for bounce hits (src/blinn_phong.h:93).
-template <bool STATS, bool FOG>
+// COHERENT: primary hits (image-coherent warps): per-pixel bundle masks / static per-receiver masks.  Otherwise (bounce
+// hits, every lane another receiver): no masks, shadow rays of two lights tested together.
+template <bool STATS, bool FOG, bool COHERENT>
 SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, bool use_shadows, const RngCtx &rng, int sidx, float3 p, float3 n,
-							Counters &cnt, bool coherent = false, bool masked = false, uint64_t smask = 0)
+							Counters &cnt, bool masked = false, uint64_t smask = 0)
 {
 	const int NP = sv.S4 >> 1;
 	// Primary hits without a pixel bundle (single-sample pixels): the static per-receiver masks, if p really lies on
 	// sphere sidx.  Not for bounce hits: every lane holds another receiver there, and 32 different per-lane pair loops
 	// cost more than the uniform loop over all pairs (config 5: 216 ms against 208 ms).
 	const uint32_t *rmask = nullptr;
-	if(coherent && !masked && use_shadows && sv.off_rmask >= 0)
+	if(COHERENT && !masked && use_shadows && sv.off_rmask >= 0)
 	{
 		const uint32_t *tab = reinterpret_cast<const uint32_t *>(B + sv.off_rmask);
 		const float3 q		= p - f3(B[sv.off_geom + sidx]);
@@ -592,16 +651,39 @@ SKR_DEV float3 direct_light(const float4 *__restrict__ B, const SceneView &sv, b
 	float3 col		= f3(am);
 	const bool fog	= FOG && sv.F > 0;
 	const float3 view = (has_spec && (!fog || sv.D > 0)) ? normalize_fast(sv.cam_pos - p) : f3(0.0f, 0.0f, 0.0f); // specular terms only
+	// no masks (bounce hits): the shadow rays of two lights are tested together, sharing the per-sphere origin terms
+	const bool paired = !COHERENT && use_shadows && sv.L >= 2 && sv.L <= 32;
+	unsigned occ	  = 0;
+	if(paired)
+	{
+		for(int i = 0; i + 1 < sv.L; i += 2)
+		{
+			const float3 lv0 = f3(B[sv.off_plpos + i]) - p, lv1 = f3(B[sv.off_plpos + i + 1]) - p;
+			occ |= occluded_x2<STATS>(B, sv, p, lv0 * rsqrtf(dot(lv0, lv0)), lv1 * rsqrtf(dot(lv1, lv1)), cnt) << i;
+		}
+		if(sv.L & 1)
+		{
+			const float3 lv = f3(B[sv.off_plpos + sv.L - 1]) - p;
+			occ |= (occluded<STATS>(B, sv, p, lv * rsqrtf(dot(lv, lv)), cnt) ? 1u : 0u) << (sv.L - 1);
+		}
+	}
 	for(int i = 0; i < sv.L; i++)
 	{
 		const float3 lv	  = f3(B[sv.off_plpos + i]) - p;
 		const float d2	  = dot(lv, lv);
 		const float3 lhat = lv * rsqrtf(d2); // also the shadow-ray direction
-		if(use_shadows)
+		if(paired)
 		{
-			if(masked ? occluded_masked<STATS>(B, sv, (uint32_t) (smask >> (i * NP)) & (uint32_t) ((1ull << NP) - 1ull), p, lhat, cnt)
-			   : rmask ? occluded_masked<STATS>(B, sv, rmask[i], p, lhat, cnt)
-					   : occluded<STATS>(B, sv, p, lhat, cnt))
+			if((occ >> i) & 1u)
+			{
+				continue;
+			}
+		}
+		else if(use_shadows)
+		{
+			if((COHERENT && masked) ? occluded_masked<STATS>(B, sv, (uint32_t) (smask >> (i * NP)) & (uint32_t) ((1ull << NP) - 1ull), p, lhat, cnt)
+			   : (COHERENT && rmask) ? occluded_masked<STATS>(B, sv, rmask[i], p, lhat, cnt)
+									 : occluded<STATS>(B, sv, p, lhat, cnt))
 			{
 				continue;
 			}

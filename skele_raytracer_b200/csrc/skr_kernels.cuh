@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 						smask			= shadow_masks<STATS>(B, sv, hp, rho, cnt);
 					}
 				}
-				sum += direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt, true, smcull, smask);
+				sum += direct_light<STATS, FOG, true>(B, sv, fp.shadows != 0, rng, h, hp, n, cnt, smcull, smask);
 			}
 		}
 		if(GI)
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 	const float3 kd = f3(B[sv.off_diff + sidx]);
 	if(valid)
 	{
-		const float3 direct = direct_light<STATS, FOG>(B, sv, fp.shadows != 0, rng, sidx, hp, n, cnt);
+		const float3 direct = direct_light<STATS, FOG, false>(B, sv, fp.shadows != 0, rng, sidx, hp, n, cnt);
 		// with --gillum: (direct / pi) * kd (src/raytrace.h:213); fresnel-only trees return direct as is (:103, :218)
 		contrib = fp.gi ? thr * kd * (direct * 0.318309886183790672f) : thr * direct;
 		if(fp.gi && fp.n_gi == 0)
