@@ -45,7 +45,7 @@ WORKLOADS = {
 SEED = 1
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu capture
 # (bench.py cannot run ncu on itself): profiles/r01_c2_primary_ncu_raw.txt
-NCU_TRAFFIC_BYTES = {"c2": (583424 + 87552, "profiles/r01_c2_primary_ncu_raw.txt"), "c4": (613376 + 1024, "profiles/r01_c4_primary_ncu_raw.txt")}
+NCU_TRAFFIC_BYTES = {"c2": (583680 + 129536, "profiles/r01_c2_primary_ncu_raw.txt"), "c4": (613376 + 1024, "profiles/r01_c4_primary_ncu_raw.txt")}
 
 
 def algorithmic_flops(st, primary_samples):
