@@ -43,7 +43,14 @@ constexpr unsigned MAX_QUEUE_CAP = 128u << 20; // entries per level (36 B each, 
 constexpr unsigned MIN_QUEUE_CAP = 1u << 20;
 constexpr int DEFAULT_TILE = 32;
 constexpr int MAX_BANDS = 8;
+constexpr int BRUTE_FORCE_TRIS = 4;
 } // namespace
+
+struct BvhGraphKey
+{
+	int T;
+	const void *tris_raw, *tri_v, *bvh, *scratch;
+};
 
 struct skr_ctx
 {
@@ -92,8 +99,13 @@ struct skr_ctx
 	cudaStream_t copy_stream = nullptr;
 	unsigned *d_band = nullptr; // [0, MAX_BANDS): counts, [MAX_BANDS, 2 MAX_BANDS): flags
 	unsigned band_seq = 0;
+	unsigned long long band_geom = 0; // geometry the band counters were last reset for
 	CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned) = nullptr;
 	CUresult (*write_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned) = nullptr;
+
+	// LBVH build replayed as a CUDA graph (build_bvh)
+	BvhGraphKey bvh_graph_key{};
+	cudaGraphExec_t bvh_graph = nullptr;
 
 	unsigned launches = 0, chunks = 0;
 	bool timing = true; // false: fire-and-forget frame, no per-kernel events
@@ -294,7 +306,9 @@ int build_bvh(skr_ctx *ctx, int T)
 	// persistent buffers grow on demand and are reused by later uploads (an e2e loop re-uploads the same scene)
 	CK(ensure(ctx->d_tri_v, ctx->tri_v_bytes, sizeof(float4) * 3 * (size_t) T));
 	const char *nobvh = getenv("SKR_NO_BVH");
-	if((nobvh && nobvh[0] == '1') || T == 1)
+	// a handful of triangles (spheres1.scn has two): testing them all costs less per ray than a node visit, and the
+	// ~27 dependent launches of the build would dominate the upload (0.21 ms against 0.03 ms)
+	if((nobvh && nobvh[0] == '1') || T <= BRUTE_FORCE_TRIS)
 	{
 		iota_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, ctx->d_tri_v);
 		CK(cudaGetLastError());
@@ -331,8 +345,25 @@ int build_bvh(skr_ctx *ctx, int T)
 	int2 *children = (int2 *) (base + o_children);
 	int *parent = (int *) (base + o_parent), *flags = (int *) (base + o_flags);
 
-	const float init_box[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
-	CK(cudaMemcpyAsync(scene_box, init_box, sizeof init_box, cudaMemcpyHostToDevice, st));
+	// The build is ~30 small dependent launches: launch-bound.  It is captured once into a CUDA graph and replayed while
+	// the triangle count and the buffers stay the same (an e2e loop re-uploads the same scene every frame).
+	const BvhGraphKey key{T, ctx->d_tris_raw, ctx->d_tri_v, ctx->d_bvh, ctx->d_scratch};
+	const char *nograph = getenv("SKR_NO_GRAPH");
+	const bool use_graph = !(nograph && nograph[0] == '1');
+	if(use_graph && ctx->bvh_graph && memcmp(&key, &ctx->bvh_graph_key, sizeof key) == 0)
+	{
+		CK(cudaGraphLaunch(ctx->bvh_graph, st));
+		ctx->sv.bvh				 = ctx->d_bvh;
+		ctx->sv.bvh_root_is_leaf = 0;
+		return SKR_OK;
+	}
+	if(ctx->bvh_graph)
+	{
+		cudaGraphExecDestroy(ctx->bvh_graph);
+		ctx->bvh_graph = nullptr;
+	}
+	bool capturing = use_graph && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+	init_scene_box_kernel<<<1, 32, 0, st>>>(scene_box);
 	tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box);
 	morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0]);
 	int cur = 0;
@@ -344,10 +375,30 @@ int build_bvh(skr_ctx *ctx, int T)
 		sort_scatter_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], T, shift, hist, nwarps, keys[cur ^ 1], vals[cur ^ 1]);
 		cur ^= 1;
 	}
-	CK(cudaMemsetAsync(flags, 0, sizeof(int) * T, st));
+	cudaMemsetAsync(flags, 0, sizeof(int) * T, st);
 	karras_kernel<<<gridT, B, 0, st>>>(keys[cur], T, children, parent);
 	refit_kernel<<<gridT, B, 0, st>>>(T, vals[cur], box_lo, box_hi, children, parent, node_lo, node_hi, flags, ctx->d_bvh);
 	gather_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, vals[cur], T, ctx->d_tri_v);
+	if(capturing)
+	{
+		cudaGraph_t g = nullptr;
+		if(cudaStreamEndCapture(st, &g) == cudaSuccess && g && cudaGraphInstantiate(&ctx->bvh_graph, g, 0) == cudaSuccess)
+		{
+			ctx->bvh_graph_key = key;
+			cudaGraphDestroy(g);
+			CK(cudaGraphLaunch(ctx->bvh_graph, st));
+		}
+		else
+		{
+			if(g)
+			{
+				cudaGraphDestroy(g);
+			}
+			ctx->bvh_graph = nullptr;
+			cudaGetLastError();
+			return fail(ctx, SKR_ERR_CUDA, "LBVH build: graph capture failed (set SKR_NO_GRAPH=1 to launch the kernels directly)");
+		}
+	}
 	CK(cudaGetLastError());
 	ctx->sv.bvh				 = ctx->d_bvh;
 	ctx->sv.bvh_root_is_leaf = 0;
@@ -675,10 +726,15 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	ctx->timing		 = !async;
 	pl.fp.counters = ctx->d_counters;
 	pl.fp.err	   = ctx->d_err;
+	// a single-kernel frame needs no per-kernel events (its span is the frame), no counter reset unless counters were
+	// asked for, and no reset of the error word (zero unless a frame failed; cleared again below when read non-zero)
+	ctx->timing = !async && tree;
 	if(!async)
 	{
-		CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 16, st));
-		CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st));
+		if(want_stats)
+		{
+			CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * 16, st));
+		}
 		CK(cudaEventRecord(ctx->ev_begin, st));
 	}
 	int rc = want_stats ? render_frame<true>(ctx, o, pl) : render_frame<false>(ctx, o, pl);
@@ -704,6 +760,7 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	CK(cudaStreamSynchronize(st));
 	if(*ctx->h_err)
 	{
+		cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st);
 		return fail(ctx, SKR_ERR_CUDA, "internal: %s (flag %d)", (*ctx->h_err & 2) ? "BVH traversal stack overflow" : "wavefront queue overflow", *ctx->h_err);
 	}
 	if(stats)
@@ -729,7 +786,7 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 			CK(cudaEventElapsedTime(&ms, ctx->spans[i].a, ctx->spans[i].b));
 			cat[ctx->spans[i].cat] += ms;
 		}
-		stats->ms_primary = cat[CAT_PRIMARY];
+		stats->ms_primary = tree ? cat[CAT_PRIMARY] : stats->ms_total;
 		stats->ms_bounce  = cat[CAT_BOUNCE];
 		stats->ms_resolve = cat[CAT_RESOLVE];
 	}
@@ -864,6 +921,10 @@ void skr_destroy(skr_ctx *ctx)
 	if(ctx->copy_stream)
 	{
 		cudaStreamDestroy(ctx->copy_stream);
+	}
+	if(ctx->bvh_graph)
+	{
+		cudaGraphExecDestroy(ctx->bvh_graph);
 	}
 	if(ctx->h_count)
 	{
@@ -1220,7 +1281,14 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 	const size_t row8 = (size_t) opt->width * 3, row32 = row8 * sizeof(float);
 	if(nb > 0)
 	{
-		CK(cudaMemsetAsync(ctx->d_band, 0, sizeof(unsigned) * MAX_BANDS, ctx->stream));
+		// the per-band CTA counters run on from frame to frame; reset when the band geometry changes (and now and then,
+		// far from 32-bit wrap-around) or after a frame that did not complete
+		const unsigned long long geom = ((unsigned long long) pl.fp.band_ctas << 32) | (unsigned) (pl.npix_local / SKR_BLOCK);
+		if(geom != ctx->band_geom || (pl.fp.band_seq & 0xffffu) == 0u)
+		{
+			CK(cudaMemsetAsync(ctx->d_band, 0, sizeof(unsigned) * MAX_BANDS, ctx->stream));
+			ctx->band_geom = geom;
+		}
 		// The waits are enqueued AFTER the kernel they wait for: should the two streams share a hardware queue, the copies
 		// then merely line up behind the kernel; a wait enqueued first could block the kernel behind it for ever.
 		bool enqueued		   = false;
@@ -1253,12 +1321,15 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 		rc = render_common(ctx, opt, pl, &local, copy_bands);
 		if(enqueued)
 		{
-			// whatever happened above, nothing stays parked on the copy stream: publish every flag behind the frame
-			for(int b = 0; b < nb; b++)
+			if(rc)
 			{
-				ctx->write_value32((CUstream) ctx->stream, (CUdeviceptr) (pl.fp.band_flag + b), pl.fp.band_seq, 0);
+				// the frame failed somewhere: nothing may stay parked on the copy stream -- publish every flag
+				for(int b = 0; b < nb; b++)
+				{
+					ctx->write_value32((CUstream) ctx->stream, (CUdeviceptr) (pl.fp.band_flag + b), pl.fp.band_seq, 0);
+				}
+				cudaStreamSynchronize(ctx->stream);
 			}
-			cudaStreamSynchronize(ctx->stream);
 			const cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
 			if(!rc)
 			{
@@ -1267,6 +1338,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 		}
 		if(rc)
 		{
+			ctx->band_geom = 0;
 			return rc;
 		}
 		CK(cudaEventElapsedTime(&local.ms_d2h, ctx->ev_x0, ctx->ev_x1));

@@ -50,6 +50,14 @@ __device__ __forceinline__ void atomic_max_f(float *addr, float v)
 	}
 }
 
+__global__ void init_scene_box_kernel(float *scene_box) // (min.xyz, max.xyz) = (+3e38, -3e38)
+{
+	if(threadIdx.x < 6)
+	{
+		scene_box[threadIdx.x] = threadIdx.x < 3 ? 3.0e38f : -3.0e38f;
+	}
+}
+
 // tris: [T][9] floats as uploaded.  box_lo/box_hi: float4 per triangle.  scene_box: 6 floats (lo, hi), pre-set to +-FLT_MAX.
 __global__ void tri_bounds_kernel(const float *__restrict__ tris, int T, float4 *__restrict__ box_lo, float4 *__restrict__ box_hi, float *scene_box)
 {

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			const unsigned b	= blockIdx.x / fp.band_ctas;
 			const unsigned left = gridDim.x - b * fp.band_ctas;
 			const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
-			if(atomicAdd(fp.band_count + b, 1u) + 1u == want)
+			if((atomicAdd(fp.band_count + b, 1u) + 1u) % want == 0u) // counters run on from frame to frame (same geometry)
 			{
 				__threadfence_system();
 				atomicExch(fp.band_flag + b, fp.band_seq);
