@@ -1,5 +1,6 @@
 // host/skr_mgpu.cpp -- implementation of include/skr_mgpu.h (libskr_mgpu.so): one process, one host thread and one
-// skr_ctx per GPU, NCCL all-gather of the finished RGB8 tiles.  See the header for the design.
+// skr_ctx per GPU.  Frame assembly: peer stores over NVLink straight into GPU 0's frame when every GPU can map it
+// (no collective, no de-interleave pass), else one NCCL all-gather of the finished RGB8 tiles.  See the header.
 #include "../include/skr_mgpu.h"
 
 #include <cuda_runtime.h>
@@ -7,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -27,6 +29,7 @@ struct skr_mgpu
 	std::vector<size_t> cap_tiles;
 	uint8_t *d_frame = nullptr; // GPU 0
 	size_t cap_frame = 0;
+	bool p2p = false; // every GPU has GPU 0's memory mapped (cudaDeviceEnablePeerAccess)
 	std::string err;
 };
 
@@ -41,6 +44,114 @@ int fail(skr_mgpu *m, int code, const char *fmt, ...)
 	va_end(ap);
 	(m ? m->err : g_err) = buf;
 	return code;
+}
+void sum_stats(skr_stats *stats, const std::vector<skr_stats> &st)
+{
+	memset(stats, 0, sizeof *stats);
+	for(const skr_stats &s : st)
+	{
+		stats->closest_hit_rays += s.closest_hit_rays;
+		stats->shadow_rays += s.shadow_rays;
+		stats->sphere_tests += s.sphere_tests;
+		stats->sphere_tests_pos += s.sphere_tests_pos;
+		stats->tri_tests += s.tri_tests;
+		stats->bvh_node_visits += s.bvh_node_visits;
+		stats->sphere_hits += s.sphere_hits;
+		stats->light_evals += s.light_evals;
+		stats->sphere_tests_executed += s.sphere_tests_executed;
+		stats->queue_entries += s.queue_entries;
+		stats->kernel_launches += s.kernel_launches;
+		stats->queue_chunks += s.queue_chunks;
+		if(s.ms_total > stats->ms_total)
+		{
+			stats->ms_total	  = s.ms_total;
+			stats->ms_primary = s.ms_primary;
+			stats->ms_bounce  = s.ms_bounce;
+			stats->ms_resolve = s.ms_resolve;
+		}
+	}
+}
+
+// Collective-free frame: every GPU renders its interleaved tiles with skr_render_peers_device and stores each finished
+// pixel into GPU 0's row-major frame (peer-mapped; the stores cross NVLink while the kernel is still tracing).  When all
+// host threads have seen their kernels complete the frame is whole: one D2H copy from GPU 0.
+int render_p2p(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stats *stats, size_t frame_bytes)
+{
+	const int W = m->world;
+	cudaSetDevice(0);
+	if(m->cap_frame < frame_bytes)
+	{
+		cudaFree(m->d_frame);
+		m->d_frame = nullptr;
+		if(cudaMalloc(&m->d_frame, frame_bytes) != cudaSuccess)
+		{
+			m->cap_frame = 0;
+			return fail(m, SKR_ERR_CUDA, "skr_mgpu_render: cudaMalloc(frame) failed");
+		}
+		m->cap_frame = frame_bytes;
+	}
+	std::vector<int> rc(W, 0);
+	std::vector<std::string> msg(W);
+	std::vector<skr_stats> st(W);
+	std::vector<std::thread> th;
+	for(int i = 0; i < W; i++)
+	{
+		th.emplace_back([&, i]() {
+			cudaSetDevice(i);
+			skr_options oi = *opt;
+			oi.world	   = W;
+			oi.rank		   = i;
+			memset(&st[i], 0, sizeof st[i]);
+			void *frames[1] = {m->d_frame};
+			rc[i]			= skr_render_peers_device(m->ctx[i], &oi, frames, 1, &st[i]);
+			if(rc[i])
+			{
+				msg[i] = skr_last_error(m->ctx[i]);
+			}
+			else if(skr_sync(m->ctx[i]) != SKR_OK)
+			{
+				rc[i]  = SKR_ERR_CUDA;
+				msg[i] = skr_last_error(m->ctx[i]);
+			}
+		});
+	}
+	for(std::thread &t : th)
+	{
+		t.join();
+	}
+	for(int i = 0; i < W; i++)
+	{
+		if(rc[i])
+		{
+			return fail(m, rc[i], "GPU %d: %s", i, msg[i].c_str());
+		}
+	}
+	cudaSetDevice(0);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	cudaStream_t s = (cudaStream_t) skr_stream(m->ctx[0]);
+	cudaEventRecord(e0, s);
+	cudaError_t ce = cudaMemcpyAsync(rgb8, m->d_frame, frame_bytes, cudaMemcpyDeviceToHost, s);
+	cudaEventRecord(e1, s);
+	if(ce == cudaSuccess)
+	{
+		ce = cudaStreamSynchronize(s);
+	}
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if(ce != cudaSuccess)
+	{
+		return fail(m, SKR_ERR_CUDA, "skr_mgpu_render: copying the frame out failed: %s", cudaGetErrorString(ce));
+	}
+	if(stats)
+	{
+		sum_stats(stats, st);
+		stats->ms_d2h = ms;
+	}
+	return SKR_OK;
 }
 } // namespace
 
@@ -120,7 +231,29 @@ int skr_mgpu_init(int n_gpus, skr_mgpu **out)
 	m->d_gathered.assign(n_gpus, nullptr);
 	m->cap_tiles.assign(n_gpus, 0);
 	m->comm.assign(n_gpus, nullptr);
-	if(n_gpus > 1)
+	// peer path: every other GPU maps GPU 0's memory; its kernels then store finished pixels into GPU 0's frame
+	{
+		const char *no = getenv("SKR_MGPU_NO_P2P");
+		m->p2p		   = n_gpus > 1 && !(no && no[0] == '1');
+		for(int i = 1; i < n_gpus && m->p2p; i++)
+		{
+			int can = 0;
+			cudaSetDevice(i);
+			if(cudaDeviceCanAccessPeer(&can, i, 0) != cudaSuccess || !can)
+			{
+				m->p2p = false;
+				break;
+			}
+			const cudaError_t e = cudaDeviceEnablePeerAccess(0, 0);
+			if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+			{
+				m->p2p = false;
+			}
+			cudaGetLastError();
+		}
+		cudaSetDevice(0);
+	}
+	if(n_gpus > 1 && !m->p2p)
 	{
 		std::vector<int> devs(n_gpus);
 		for(int i = 0; i < n_gpus; i++)
@@ -181,6 +314,10 @@ int skr_mgpu_render(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stat
 		return fail(m, SKR_ERR_ARG, "skr_mgpu_render: bad options");
 	}
 	const size_t frame_bytes = (size_t) opt->width * opt->height * 3;
+	if(m->p2p)
+	{
+		return render_p2p(m, opt, rgb8, stats, frame_bytes);
+	}
 	for(int i = 0; i < W; i++)
 	{
 		cudaSetDevice(i);
@@ -282,29 +419,7 @@ int skr_mgpu_render(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stat
 	}
 	if(stats)
 	{
-		memset(stats, 0, sizeof *stats);
-		for(int i = 0; i < W; i++)
-		{
-			stats->closest_hit_rays += st[i].closest_hit_rays;
-			stats->shadow_rays += st[i].shadow_rays;
-			stats->sphere_tests += st[i].sphere_tests;
-			stats->sphere_tests_pos += st[i].sphere_tests_pos;
-			stats->tri_tests += st[i].tri_tests;
-			stats->bvh_node_visits += st[i].bvh_node_visits;
-			stats->sphere_hits += st[i].sphere_hits;
-			stats->light_evals += st[i].light_evals;
-			stats->sphere_tests_executed += st[i].sphere_tests_executed;
-			stats->queue_entries += st[i].queue_entries;
-			stats->kernel_launches += st[i].kernel_launches;
-			stats->queue_chunks += st[i].queue_chunks;
-			if(st[i].ms_total > stats->ms_total)
-			{
-				stats->ms_total	  = st[i].ms_total;
-				stats->ms_primary = st[i].ms_primary;
-				stats->ms_bounce  = st[i].ms_bounce;
-				stats->ms_resolve = st[i].ms_resolve;
-			}
-		}
+		sum_stats(stats, st);
 		stats->ms_d2h = ms_tail[0];
 	}
 	return SKR_OK;
