@@ -44,11 +44,13 @@ constexpr unsigned MIN_QUEUE_CAP = 1u << 20;
 constexpr int DEFAULT_TILE = 32;
 constexpr int MAX_BANDS = 8;
 constexpr int BRUTE_FORCE_TRIS = 4;
+constexpr int BIG_TRI_CAP = 16;	 // outsized triangles kept out of the hierarchy (morton_kernel)
+constexpr int BIG_TRI_MIN_T = 64; // scenes smaller than this keep everything in the tree
 } // namespace
 
-struct BvhGraphKey
+struct BvhGraphKey // compared with memcmp: no padding
 {
-	int T;
+	long long T;
 	const void *tris_raw, *tri_v, *bvh, *scratch;
 };
 
@@ -67,6 +69,7 @@ struct skr_ctx
 	float *d_tris_raw = nullptr;
 	float4 *d_tri_v = nullptr;
 	float4 *d_bvh = nullptr;
+	float4 *d_big = nullptr; // BIG_TRI_CAP x 3 float4 + the int counter behind them
 	size_t blob_bytes = 0, tris_raw_bytes = 0, tri_v_bytes = 0, bvh_bytes = 0, scratch_bytes = 0;
 	char *d_scratch = nullptr; // LBVH build scratch, kept between uploads
 	size_t smem_bytes = 0;
@@ -314,8 +317,17 @@ int build_bvh(skr_ctx *ctx, int T)
 		CK(cudaGetLastError());
 		ctx->sv.bvh				 = nullptr;
 		ctx->sv.bvh_root_is_leaf = 0;
+		ctx->sv.nbig			 = 0;
+		*ctx->h_count			 = 0;
 		return SKR_OK;
 	}
+	if(!ctx->d_big)
+	{
+		CK(cudaMalloc(&ctx->d_big, sizeof(float4) * 3 * BIG_TRI_CAP + 256));
+	}
+	int *big_count	  = reinterpret_cast<int *>(ctx->d_big + 3 * BIG_TRI_CAP);
+	const int big_cap = T >= BIG_TRI_MIN_T ? BIG_TRI_CAP : 0;
+	ctx->sv.big_v	  = ctx->d_big;
 	CK(ensure(ctx->d_bvh, ctx->bvh_bytes, sizeof(float4) * 4 * (size_t) (T - 1)));
 	const int nwarps  = (T + SORT_ITEMS_PER_WARP - 1) / SORT_ITEMS_PER_WARP;
 	const int sblocks = (nwarps + SORT_WARPS - 1) / SORT_WARPS;
@@ -353,6 +365,7 @@ int build_bvh(skr_ctx *ctx, int T)
 	if(use_graph && ctx->bvh_graph && memcmp(&key, &ctx->bvh_graph_key, sizeof key) == 0)
 	{
 		CK(cudaGraphLaunch(ctx->bvh_graph, st));
+		CK(cudaMemcpyAsync(ctx->h_count, big_count, sizeof(int), cudaMemcpyDeviceToHost, st)); // read after the upload's sync
 		ctx->sv.bvh				 = ctx->d_bvh;
 		ctx->sv.bvh_root_is_leaf = 0;
 		return SKR_OK;
@@ -364,8 +377,9 @@ int build_bvh(skr_ctx *ctx, int T)
 	}
 	bool capturing = use_graph && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
 	init_scene_box_kernel<<<1, 32, 0, st>>>(scene_box);
+	cudaMemsetAsync(big_count, 0, sizeof(int), st);
 	tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box);
-	morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0]);
+	morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0], ctx->d_tris_raw, big_count, ctx->d_big, big_cap);
 	int cur = 0;
 	for(int pass = 0; pass < 8; pass++)
 	{
@@ -400,6 +414,7 @@ int build_bvh(skr_ctx *ctx, int T)
 		}
 	}
 	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(ctx->h_count, big_count, sizeof(int), cudaMemcpyDeviceToHost, st)); // read after the upload's sync
 	ctx->sv.bvh				 = ctx->d_bvh;
 	ctx->sv.bvh_root_is_leaf = 0;
 	return SKR_OK;
@@ -917,7 +932,7 @@ void skr_destroy(skr_ctx *ctx)
 	{
 		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c), cudaFree(q.d);
 	}
-	cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band);
+	cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band), cudaFree(ctx->d_big);
 	if(ctx->copy_stream)
 	{
 		cudaStreamDestroy(ctx->copy_stream);
@@ -1189,6 +1204,7 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		sv.tri_v = ctx->d_tri_v;
 	}
 	CK(cudaStreamSynchronize(ctx->stream));
+	sv.nbig			= T > 0 ? std::min((int) *ctx->h_count, BIG_TRI_CAP) : 0;
 	ctx->have_scene = true;
 	return SKR_OK;
 }

@@ -72,6 +72,19 @@ SKR_DEV bool tri_any_hit_line(const SceneView &sv, float3 o, float3 d, float tma
 	{
 		return tri_leaf_hit<STATS>(sv, 0, o, d, tmax, cnt);
 	}
+	for(int k = 0; k < sv.nbig; k++) // outsized triangles first: any hit ends the query
+	{
+		const float4 a = __ldg(sv.big_v + 3 * k + 0), b = __ldg(sv.big_v + 3 * k + 1), c = __ldg(sv.big_v + 3 * k + 2);
+		if(STATS)
+		{
+			cnt.tt++;
+		}
+		float t;
+		if(tri_test_ref(o, d, f3(a), f3(b), f3(c), t) && t < tmax)
+		{
+			return true;
+		}
+	}
 	const float3 inv = f3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
 	int stack[SKR_BVH_STACK];
 	int sp	 = 0;

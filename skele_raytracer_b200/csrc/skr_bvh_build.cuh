@@ -127,8 +127,14 @@ __device__ __forceinline__ unsigned long long expand21(unsigned v) // spread 21 
 	return x;
 }
 
-__global__ void morton_kernel(const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, const float *__restrict__ scene_box, int T,
-							  unsigned long long *__restrict__ keys, unsigned *__restrict__ vals)
+// Also pulls OUTSIZED triangles out of the hierarchy (dragon.scn: two ground triangles spanning the whole scene around a
+// model 1/200 of its size; inside an LBVH they inflate every ancestor box, so that every ray walks ~10 nodes): a
+// triangle whose box surface exceeds SKR_BIG_TRI_FRACTION of the scene box's goes to a short list (big_v, at most
+// big_cap entries) that traversal tests first -- any hit ends the query -- and its leaf box collapses to its centre, so
+// it no longer widens its ancestors.  (The leaf stays in the tree: harmless, its test is exact whatever the box.)
+#define SKR_BIG_TRI_FRACTION 0.1f
+__global__ void morton_kernel(float4 *box_lo, float4 *box_hi, const float *__restrict__ scene_box, int T, unsigned long long *__restrict__ keys,
+							  unsigned *__restrict__ vals, const float *__restrict__ tris, int *big_count, float4 *__restrict__ big_v, int big_cap)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= T)
@@ -140,6 +146,22 @@ __global__ void morton_kernel(const float4 *__restrict__ box_lo, const float4 *_
 	const float4 lo = box_lo[i], hi = box_hi[i];
 	const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
 	const float ex = fmaxf(shi.x - slo.x, 1e-30f), ey = fmaxf(shi.y - slo.y, 1e-30f), ez = fmaxf(shi.z - slo.z, 1e-30f);
+	if(big_cap > 0)
+	{
+		const float bx = hi.x - lo.x, by = hi.y - lo.y, bz = hi.z - lo.z;
+		if(bx * by + by * bz + bz * bx > SKR_BIG_TRI_FRACTION * (ex * ey + ey * ez + ez * ex))
+		{
+			const int slot = atomicAdd(big_count, 1);
+			if(slot < big_cap)
+			{
+				const float *t		= tris + 9 * (size_t) i;
+				big_v[3 * slot + 0] = make_float4(t[0], t[1], t[2], 0.0f);
+				big_v[3 * slot + 1] = make_float4(t[3], t[4], t[5], 0.0f);
+				big_v[3 * slot + 2] = make_float4(t[6], t[7], t[8], 0.0f);
+				box_lo[i] = box_hi[i] = make_float4(cx, cy, cz, 0.0f);
+			}
+		}
+	}
 	// quantise in double: 21 bits exceed the float mantissa's headroom near the top of the range
 	const unsigned qx = (unsigned) fmin(fmax((double) (cx - slo.x) / (double) ex * 2097152.0, 0.0), 2097151.0);
 	const unsigned qy = (unsigned) fmin(fmax((double) (cy - slo.y) / (double) ey * 2097152.0, 0.0), 2097151.0);

@@ -43,6 +43,8 @@ struct SceneView
 	const float4 *blob;	 // device
 	const float4 *tri_v; // 3 float4 per triangle (v0, v1, v2), LBVH leaf order
 	const float4 *bvh;	 // 4 float4 per internal node (see skr_bvh.cuh)
+	const float4 *big_v; // 3 float4 per outsized triangle, tested before the hierarchy (skr_bvh_build.cuh: morton_kernel)
+	int nbig;
 	int bvh_root_is_leaf; // T == 1
 	int *err;			  // device error word (bit 1: BVH traversal stack overflow)
 	float3 cam_pos, cam_dir, cam_up, cam_right, background;
