@@ -170,7 +170,7 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 				const float w = fmaf(2.0f, h.x, cc.x), m = -h.x - umin;
 				if((h.x < na) & (w > na) & ((m < 0.0f) | (d4.x > m * m)))
 				{
-					umin = -h.x - __fsqrt_rn(d4.x);
+					umin = -h.x - sqrt_approx(d4.x); // ranking only: the winner's t is recomputed exactly
 					best = 2 * p;
 				}
 			}
@@ -179,7 +179,7 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 				const float w = fmaf(2.0f, h.y, cc.y), m = -h.y - umin;
 				if((h.y < na) & (w > na) & ((m < 0.0f) | (d4.y > m * m)))
 				{
-					umin = -h.y - __fsqrt_rn(d4.y);
+					umin = -h.y - sqrt_approx(d4.y);
 					best = 2 * p + 1;
 				}
 			}
@@ -392,7 +392,8 @@ SKR_DEV uint32_t cull_pairs(const float4 *__restrict__ C, int NP, int S, float3 
 
 // closest_sphere_table<ORIGIN_TABLE = true, COHERENT = true> over the pairs of `mask` only (ascending, so the first
 // sphere still wins ties).  `mask` is uniform across the warp: no divergence, broadcast shared-memory reads.
-template <bool STATS>
+// EXACT_T: tmin by IEEE division (it bounds the triangle query); otherwise tmin is only sphere_t_ref's fallback.
+template <bool STATS, bool EXACT_T>
 SKR_DEV int closest_sphere_masked(const float4 *__restrict__ G, uint32_t mask, int S, float3 d, float &tmin, Counters &cnt)
 {
 	const float a  = dot(d, d);
@@ -421,7 +422,7 @@ SKR_DEV int closest_sphere_masked(const float4 *__restrict__ G, uint32_t mask, i
 			const float w = fmaf(2.0f, h.x, cc.x), mm = -h.x - umin;
 			if((h.x < na) & (w > na) & ((mm < 0.0f) | (d4.x > mm * mm)))
 			{
-				umin = -h.x - __fsqrt_rn(d4.x);
+				umin = -h.x - sqrt_approx(d4.x); // ranking only: the winner's t is recomputed exactly
 				best = 2 * p;
 			}
 		}
@@ -430,12 +431,12 @@ SKR_DEV int closest_sphere_masked(const float4 *__restrict__ G, uint32_t mask, i
 			const float w = fmaf(2.0f, h.y, cc.y), mm = -h.y - umin;
 			if((h.y < na) & (w > na) & ((mm < 0.0f) | (d4.y > mm * mm)))
 			{
-				umin = -h.y - __fsqrt_rn(d4.y);
+				umin = -h.y - sqrt_approx(d4.y);
 				best = 2 * p + 1;
 			}
 		}
 	}
-	tmin = best >= 0 ? __fdiv_rn(umin, a) : CUDART_INF_F;
+	tmin = best >= 0 ? (EXACT_T ? __fdiv_rn(umin, a) : __fdividef(umin, a)) : CUDART_INF_F;
 	return best;
 }
 
@@ -776,7 +777,7 @@ SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float
 	{
 		cnt.ch++;
 	}
-	const int s = (PRIMARY && masked) ? closest_sphere_masked<STATS>(B + sv.off_pprim, pmask, sv.S, d, tmin, cnt)
+	const int s = (PRIMARY && masked) ? closest_sphere_masked<STATS, TRIS>(B + sv.off_pprim, pmask, sv.S, d, tmin, cnt)
 									  : closest_sphere<PRIMARY, STATS>(B, sv, o, d, tmin, cnt);
 	if(TRIS && sv.T > 0 && tri_any_hit_line<STATS>(sv, o, d, tmin, cnt))
 	{

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			hp			   = add_rn(o, muls_rn(d, t)); // src/raytrace.h:204
 			if(!GI)
 			{
-				const float3 n	  = normalize_rn(sub_rn(hp, c));
+				const float3 n	  = normalize_fast(sub_rn(hp, c)); // feeds shading terms only (no --gillum here)
 				const bool smcull = cull && fp.shadows != 0 && sv.cull_shadow != 0;
 				if(smcull)
 				{
