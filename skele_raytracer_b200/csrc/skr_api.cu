@@ -503,12 +503,9 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 
 int ensure_queues(skr_ctx *ctx, int levels, unsigned cap, bool want_dir)
 {
-	if(levels <= ctx->n_levels_alloc && cap == ctx->queue_cap && (!want_dir || ctx->queues_have_dir))
+	(void) want_dir; // every entry carries its ray now (Queue::d)
+	if(levels <= ctx->n_levels_alloc && cap == ctx->queue_cap)
 	{
-		if(!want_dir && ctx->queues_have_dir)
-		{
-			// keep the arrays but hide them from the kernels of a non-fresnel frame
-		}
 		return SKR_OK;
 	}
 	for(Queue &q : ctx->queues)
@@ -529,10 +526,7 @@ int ensure_queues(skr_ctx *ctx, int levels, unsigned cap, bool want_dir)
 		CK(cudaMalloc(&q.a, sizeof(float4) * (size_t) cap));
 		CK(cudaMalloc(&q.b, sizeof(float4) * (size_t) cap));
 		CK(cudaMalloc(&q.c, sizeof(uint32_t) * (size_t) cap));
-		if(want_dir)
-		{
-			CK(cudaMalloc(&q.d, sizeof(float4) * (size_t) cap));
-		}
+		CK(cudaMalloc(&q.d, sizeof(float4) * (size_t) cap));
 		q.count = ctx->d_counts + l;
 		q.cap	= cap;
 		ctx->queues.push_back(q);
@@ -553,12 +547,8 @@ int read_count(skr_ctx *ctx, int level, unsigned &out)
 
 Queue queue_view(const skr_ctx *ctx, int level, const FrameParams &fp)
 {
-	Queue q = ctx->queues[level];
-	if(!fp.fresnel)
-	{
-		q.d = nullptr; // direction array (if allocated by an earlier fresnel frame) stays untouched
-	}
-	return q;
+	(void) fp;
+	return ctx->queues[level];
 }
 
 template <bool STATS>

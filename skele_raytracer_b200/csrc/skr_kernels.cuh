@@ -34,10 +34,13 @@
 
 struct Queue
 {
-	float4 *a;		 // (P.xyz, bits(global pixel id))
+	// An entry is a HIT AWAITING SHADING, stored as the ray that found it: the consumer recomputes the hit point
+	// P = o + d * t with the reference's expression (sphere_t_ref) -- every lane of a consumer warp holds an entry, while
+	// in the producer only the 15-30 % of lanes that hit something would run that code.
+	float4 *a;		 // (ray origin.xyz, bits(global pixel id))
 	float4 *b;		 // (throughput.xyz, bits(node id))
 	uint32_t *c;	 // sample | sphere << 16
-	float4 *d;		 // (incoming ray direction.xyz, -) -- only allocated in fresnel mode, else null
+	float4 *d;		 // (ray direction.xyz, t of the intersection loop = sphere_t_ref's fallback)
 	unsigned *count; // device counter
 	unsigned cap;
 };
@@ -219,17 +222,15 @@ SKR_DEV unsigned queue_reserve(const Queue &q, unsigned count)
 	}
 	return __shfl_sync(0xffffffffu, base, 0);
 }
-SKR_DEV void queue_store(const Queue &q, unsigned idx, float3 p, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, float3 dir, int *err)
+SKR_DEV void queue_store(const Queue &q, unsigned idx, float3 o, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, float3 dir, float t,
+						 int *err)
 {
 	if(idx < q.cap)
 	{
-		q.a[idx] = make_float4(p.x, p.y, p.z, u2f(pixel));
+		q.a[idx] = make_float4(o.x, o.y, o.z, u2f(pixel));
 		q.b[idx] = make_float4(thr.x, thr.y, thr.z, u2f(node));
 		q.c[idx] = (sample & 0xffffu) | ((uint32_t) sphere << 16);
-		if(q.d)
-		{
-			q.d[idx] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-		}
+		q.d[idx] = make_float4(dir.x, dir.y, dir.z, t);
 	}
 	else
 	{
@@ -237,15 +238,22 @@ SKR_DEV void queue_store(const Queue &q, unsigned idx, float3 p, uint32_t pixel,
 	}
 }
 // one entry per lane that wants one.  Must be called by all 32 lanes.
-SKR_DEV void queue_push(const Queue &q, bool want, float3 p, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, float3 dir,
+SKR_DEV void queue_push(const Queue &q, bool want, float3 o, uint32_t pixel, float3 thr, uint32_t node, uint32_t sample, int sphere, float3 dir, float t,
 						int *err)
 {
 	const unsigned mask = __ballot_sync(0xffffffffu, want);
 	const unsigned base = queue_reserve(q, (unsigned) __popc(mask));
 	if(want)
 	{
-		queue_store(q, base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u)), p, pixel, thr, node, sample, sphere, dir, err);
+		queue_store(q, base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u)), o, pixel, thr, node, sample, sphere, dir, t, err);
 	}
+}
+// consumer side: the hit point of an entry, src/raytrace.h:197-204 (exact t, then P = o + d * t)
+SKR_DEV float3 queue_hit_point(const float4 *__restrict__ B, const SceneView &sv, const float4 &qa, const float4 &qd, int sidx)
+{
+	const float3 o = f3(qa), d = f3(qd);
+	const float t  = sphere_t_ref(o, d, f3(B[sv.off_geom + sidx]), B[sv.off_spec + sidx].w, qd.w);
+	return add_rn(o, muls_rn(d, t));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -331,17 +339,15 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		{
 			h = closest_hit<true, STATS, TRIS>(B, sv, o, d, t, cnt, cull, pmask);
 		}
-		float3 hp = f3(0.0f, 0.0f, 0.0f);
 		if(h == -2)
 		{
 			sum += sv.background;
 		}
-		else if(h >= 0)
+		else if(!GI && h >= 0)
 		{
-			const float3 c = f3(B[sv.off_geom + h]);
-			t			   = sphere_t_ref(o, d, c, B[sv.off_spec + h].w, t);
-			hp			   = add_rn(o, muls_rn(d, t)); // src/raytrace.h:204
-			if(!GI)
+			const float3 c	= f3(B[sv.off_geom + h]);
+			t				= sphere_t_ref(o, d, c, B[sv.off_spec + h].w, t);
+			const float3 hp = add_rn(o, muls_rn(d, t)); // src/raytrace.h:204
 			{
 				const float3 n	  = normalize_fast(sub_rn(hp, c)); // feeds shading terms only (no --gillum here)
 				const bool smcull = cull && fp.shadows != 0 && sv.cull_shadow != 0;
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		}
 		if(GI)
 		{
-			queue_push(q0, h >= 0, hp, rng.pixel, f3(1.0f, 1.0f, 1.0f), 0u, (uint32_t) s, h, d, fp.err);
+			queue_push(q0, h >= 0, o, rng.pixel, f3(1.0f, 1.0f, 1.0f), 0u, (uint32_t) s, h, d, t, fp.err);
 		}
 	}
 
@@ -424,9 +430,10 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 	const float4 qa	  = in.a[i];
 	const float4 qb	  = in.b[i];
 	const uint32_t qc = in.c[i];
-	const float3 hp	  = f3(qa);
+	const float4 qd	  = in.d[i];
 	const float3 thr  = f3(qb);
 	const int sidx	  = (int) (qc >> 16);
+	const float3 hp	  = queue_hit_point(B, sv, qa, qd, sidx);
 	RngCtx rng;
 	rng.pixel  = f2u(qa.w);
 	rng.sample = qc & 0xffffu;
@@ -455,18 +462,13 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 		basis_from_normal(n, nt, nb);
 		const float3 tk = thr * kd * (6.28318530717958648f / (float) fp.n_gi);
 		const float3 o	= adds_rn(hp, 0.00001f);
-		// one child: weight, miss -> background, hit -> exact t and hit point
-		const auto finish = [&](float3 d, float r1, float t, int h, float3 &w, float3 &cp) {
+		// one child: weight; a miss adds the background, a hit is pushed as (o, d, t) for the next level to finish
+		const auto finish = [&](float r1, int h, float3 &w) {
 			w = tk * r1;
 			if(h == -2)
 			{
 				contrib += w * sv.background;
 			}
-			if(h >= 0)
-			{
-				t = sphere_t_ref(o, d, f3(B[sv.off_geom + h]), B[sv.off_spec + h].w, t);
-			}
-			cp = add_rn(o, muls_rn(d, t));
 		};
 		// children are traced SKR_GI_BATCH at a time: they share the per-sphere origin terms of their intersection tests
 		// (children 2m and 2m+1 also share a Philox block) and ONE queue reservation
@@ -491,12 +493,12 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			{
 				closest_hit_xk<SKR_GI_BATCH, STATS, TRIS>(B, sv, o, d, t, h, cnt);
 			}
-			float3 w[SKR_GI_BATCH], cp[SKR_GI_BATCH];
+			float3 w[SKR_GI_BATCH];
 			unsigned m[SKR_GI_BATCH], total = 0;
 #pragma unroll
 			for(int k = 0; k < SKR_GI_BATCH; k++)
 			{
-				finish(d[k], r1[k], t[k], h[k], w[k], cp[k]);
+				finish(r1[k], h[k], w[k]);
 				m[k] = __ballot_sync(0xffffffffu, h[k] >= 0);
 				total += (unsigned) __popc(m[k]);
 			}
@@ -506,8 +508,8 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			{
 				if(h[k] >= 0)
 				{
-					queue_store(out, at + __popc(m[k] & ((1u << (threadIdx.x & 31)) - 1u)), cp[k], rng.pixel, w[k], rng.node * fp.node_base + (uint32_t) (c + k) + 1u,
-								rng.sample, h[k], d[k], fp.err);
+					queue_store(out, at + __popc(m[k] & ((1u << (threadIdx.x & 31)) - 1u)), o, rng.pixel, w[k], rng.node * fp.node_base + (uint32_t) (c + k) + 1u,
+								rng.sample, h[k], d[k], t[k], fp.err);
 				}
 				at += (unsigned) __popc(m[k]);
 			}
@@ -527,9 +529,9 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			{
 				h = closest_hit<false, STATS, TRIS>(B, sv, o, d, t, cnt);
 			}
-			float3 w, cp;
-			finish(d, r1, t, h, w, cp);
-			queue_push(out, h >= 0, cp, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, fp.err);
+			float3 w;
+			finish(r1, h, w);
+			queue_push(out, h >= 0, o, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, t, fp.err);
 		}
 	}
 	if(valid)
@@ -602,8 +604,9 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 	const unsigned i = start + (valid ? g : 0u);
 	const float4 qa = in.a[i], qb = in.b[i], qd = in.d[i];
 	const uint32_t qc = in.c[i];
-	const float3 hp = f3(qa), thr = f3(qb), dir = f3(qd);
-	const int sidx = (int) (qc >> 16);
+	const float3 thr = f3(qb), dir = f3(qd);
+	const int sidx	 = (int) (qc >> 16);
+	const float3 hp	 = queue_hit_point(B, sv, qa, qd, sidx);
 	const uint32_t pixel = f2u(qa.w), node = f2u(qb.w), sample = qc & 0xffffu;
 	const float3 n	= normalize_rn(sub_rn(hp, f3(B[sv.off_geom + sidx])));
 	const float3 kd = f3(B[sv.off_diff + sidx]);
@@ -634,12 +637,7 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 			{
 				contrib += w * sv.background;
 			}
-			if(h >= 0)
-			{
-				t = sphere_t_ref(hp, d, f3(B[sv.off_geom + h]), B[sv.off_spec + h].w, t);
-			}
-			const float3 cp = add_rn(hp, muls_rn(d, t));
-			queue_push(out, h >= 0, cp, pixel, w, node * fp.node_base + (uint32_t) (fp.n_gi + 2 * li + kind) + 1u, sample, h, d, fp.err);
+			queue_push(out, h >= 0, hp, pixel, w, node * fp.node_base + (uint32_t) (fp.n_gi + 2 * li + kind) + 1u, sample, h, d, t, fp.err);
 		}
 	}
 	if(valid && (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f))
