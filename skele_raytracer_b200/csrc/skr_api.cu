@@ -39,7 +39,7 @@ struct Span
 };
 
 constexpr size_t SMEM_BLOB_LIMIT = 64 * 1024;
-constexpr unsigned MAX_QUEUE_CAP = 128u << 20; // entries per level (36 B each, 4.6 GB): fewer, fuller chunks -- config 5: 228 ms at 32 M, 213 ms at 128 M
+constexpr unsigned MAX_QUEUE_CAP = 128u << 20; // entries per level (52 B each, 6.7 GB): fewer, fuller chunks -- config 5: 228 ms at 32 M, 213 ms at 128 M
 constexpr unsigned MIN_QUEUE_CAP = 1u << 20;
 constexpr int DEFAULT_TILE = 32;
 constexpr int MAX_BANDS = 8;
