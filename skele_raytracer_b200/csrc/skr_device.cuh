@@ -228,7 +228,7 @@ SKR_DEV int closest_sphere_table(const float4 *__restrict__ G, int NP, int S, fl
 // cc = e.e - r^2 of a sphere pair are formed once and serve all K rays -- 8 of the 25 instructions per (pair, ray).
 // Per ray the operations and their order are those of the one-ray form (tagged ranking): same winner, same t.
 // Requires NP <= 2^(SKR_TAG_BITS - 1) (closest_hit_xk checks).
-template <int K, bool STATS>
+template <int K, bool STATS, bool EXACT_T>
 SKR_DEV void closest_sphere_xk(const float4 *__restrict__ G, int NP, int S, float3 o, const float3 (&d)[K], float (&t)[K], int (&s)[K], Counters &cnt)
 {
 	float a[K];
@@ -271,7 +271,7 @@ SKR_DEV void closest_sphere_xk(const float4 *__restrict__ G, int NP, int S, floa
 		int b	 = -1;
 		float um = CUDART_INF_F;
 		untag(wm[k], a[k], b, um);
-		t[k] = b >= 0 ? __fdiv_rn(um, a[k]) : CUDART_INF_F;
+		t[k] = b >= 0 ? (EXACT_T ? __fdiv_rn(um, a[k]) : __fdividef(um, a[k])) : CUDART_INF_F; // exact only where it bounds a triangle query
 		s[k] = b;
 	}
 }
@@ -811,7 +811,7 @@ SKR_DEV void closest_hit_xk(const float4 *__restrict__ B, const SceneView &sv, f
 	{
 		cnt.ch += K;
 	}
-	closest_sphere_xk<K, STATS>(B + sv.off_pgeom, sv.S4 >> 1, sv.S, o, d, t, h, cnt);
+	closest_sphere_xk<K, STATS, TRIS>(B + sv.off_pgeom, sv.S4 >> 1, sv.S, o, d, t, h, cnt);
 #pragma unroll
 	for(int k = 0; k < K; k++)
 	{
