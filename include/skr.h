@@ -95,7 +95,7 @@ typedef struct skr_options
 	int32_t world;
 	int32_t tile;			/* tile edge in pixels; 0 = default (32) */
 	int32_t collect_stats;	/* nonzero: count rays/tests on the device (slower; not for timed runs) */
-	int32_t queue_capacity; /* entries per wavefront queue level; 0 = default */
+	int32_t queue_capacity; /* entries (52 B each) per wavefront queue level; 0 = default: sized to the frame, 1 M .. 128 M */
 } skr_options;
 
 typedef struct skr_stats

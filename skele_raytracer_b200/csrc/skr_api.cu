@@ -63,7 +63,6 @@ struct skr_ctx
 
 	// scene
 	bool have_scene = false;
-	bool queues_have_dir = false;
 	SceneView sv{};
 	float4 *d_blob = nullptr;
 	float *d_tris_raw = nullptr;
@@ -501,9 +500,8 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	return SKR_OK;
 }
 
-int ensure_queues(skr_ctx *ctx, int levels, unsigned cap, bool want_dir)
+int ensure_queues(skr_ctx *ctx, int levels, unsigned cap)
 {
-	(void) want_dir; // every entry carries its ray now (Queue::d)
 	if(levels <= ctx->n_levels_alloc && cap == ctx->queue_cap)
 	{
 		return SKR_OK;
@@ -533,7 +531,6 @@ int ensure_queues(skr_ctx *ctx, int levels, unsigned cap, bool want_dir)
 	}
 	ctx->n_levels_alloc	 = levels;
 	ctx->queue_cap		 = cap;
-	ctx->queues_have_dir = want_dir;
 	return SKR_OK;
 }
 
@@ -545,9 +542,8 @@ int read_count(skr_ctx *ctx, int level, unsigned &out)
 	return SKR_OK;
 }
 
-Queue queue_view(const skr_ctx *ctx, int level, const FrameParams &fp)
+Queue queue_view(const skr_ctx *ctx, int level)
 {
-	(void) fp;
 	return ctx->queues[level];
 }
 
@@ -580,7 +576,7 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 	const bool expand_gi  = deeper && fp.gi && fp.n_gi > 0;
 	const bool expand_fr  = deeper && fp.fresnel && (ctx->sv.L + ctx->sv.D) > 0;
 	const unsigned fan	  = (expand_gi ? (unsigned) fp.n_gi : 0u) + (expand_fr ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
-	const Queue in		  = queue_view(ctx, level, fp);
+	const Queue in		  = queue_view(ctx, level);
 	ctx->queue_entries += count;
 	if(fan == 0)
 	{
@@ -591,7 +587,7 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 		CK(cudaGetLastError());
 		return SKR_OK;
 	}
-	const Queue out		 = queue_view(ctx, level + 1, fp);
+	const Queue out		 = queue_view(ctx, level + 1);
 	const unsigned chunk = out.cap / fan;
 	for(unsigned s = 0; s < count; s += chunk)
 	{
@@ -662,7 +658,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		{
 			cap = need * SKR_BLOCK;
 		}
-		int rc = ensure_queues(ctx, pl.levels, cap, fp.fresnel != 0);
+		int rc = ensure_queues(ctx, pl.levels, cap);
 		if(rc)
 		{
 			return rc;
@@ -681,7 +677,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		CK(cudaGetLastError());
 		return SKR_OK;
 	}
-	const Queue q0	  = queue_view(ctx, 0, fp);
+	const Queue q0	  = queue_view(ctx, 0);
 	long long batch	  = (long long) (q0.cap / (unsigned) fp.spp) / SKR_BLOCK * SKR_BLOCK;
 	for(long long lp0 = 0; lp0 < pl.npix_local; lp0 += batch)
 	{
