@@ -108,6 +108,7 @@ struct skr_ctx
 	// LBVH build replayed as a CUDA graph (build_bvh)
 	BvhGraphKey bvh_graph_key{};
 	cudaGraphExec_t bvh_graph = nullptr;
+	bool bvh_graph_broken = false; // capture failed once: direct launches from then on
 
 	unsigned launches = 0, chunks = 0;
 	bool timing = true; // false: fire-and-forget frame, no per-kernel events
@@ -374,43 +375,55 @@ int build_bvh(skr_ctx *ctx, int T)
 		cudaGraphExecDestroy(ctx->bvh_graph);
 		ctx->bvh_graph = nullptr;
 	}
-	bool capturing = use_graph && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-	init_scene_box_kernel<<<1, 32, 0, st>>>(scene_box);
-	cudaMemsetAsync(big_count, 0, sizeof(int), st);
-	tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box);
-	morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0], ctx->d_tris_raw, big_count, ctx->d_big, big_cap);
-	int cur = 0;
-	for(int pass = 0; pass < 8; pass++)
+	const auto enqueue_build = [&]() {
+		init_scene_box_kernel<<<1, 32, 0, st>>>(scene_box);
+		cudaMemsetAsync(big_count, 0, sizeof(int), st);
+		tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box);
+		morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0], ctx->d_tris_raw, big_count, ctx->d_big, big_cap);
+		int cur = 0;
+		for(int pass = 0; pass < 8; pass++)
+		{
+			const int shift = 8 * pass;
+			sort_hist_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], T, shift, hist, nwarps);
+			sort_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * nwarps);
+			sort_scatter_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], T, shift, hist, nwarps, keys[cur ^ 1], vals[cur ^ 1]);
+			cur ^= 1;
+		}
+		cudaMemsetAsync(flags, 0, sizeof(int) * T, st);
+		karras_kernel<<<gridT, B, 0, st>>>(keys[cur], T, children, parent);
+		refit_kernel<<<gridT, B, 0, st>>>(T, vals[cur], box_lo, box_hi, children, parent, node_lo, node_hi, flags, ctx->d_bvh);
+		gather_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, vals[cur], T, ctx->d_tri_v);
+	};
+	bool launched = false;
+	if(use_graph && !ctx->bvh_graph_broken && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
 	{
-		const int shift = 8 * pass;
-		sort_hist_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], T, shift, hist, nwarps);
-		sort_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * nwarps);
-		sort_scatter_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], T, shift, hist, nwarps, keys[cur ^ 1], vals[cur ^ 1]);
-		cur ^= 1;
-	}
-	cudaMemsetAsync(flags, 0, sizeof(int) * T, st);
-	karras_kernel<<<gridT, B, 0, st>>>(keys[cur], T, children, parent);
-	refit_kernel<<<gridT, B, 0, st>>>(T, vals[cur], box_lo, box_hi, children, parent, node_lo, node_hi, flags, ctx->d_bvh);
-	gather_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, vals[cur], T, ctx->d_tri_v);
-	if(capturing)
-	{
+		enqueue_build();
 		cudaGraph_t g = nullptr;
-		if(cudaStreamEndCapture(st, &g) == cudaSuccess && g && cudaGraphInstantiate(&ctx->bvh_graph, g, 0) == cudaSuccess)
+		if(cudaStreamEndCapture(st, &g) == cudaSuccess && g && cudaGraphInstantiate(&ctx->bvh_graph, g, 0) == cudaSuccess &&
+		   cudaGraphLaunch(ctx->bvh_graph, st) == cudaSuccess)
 		{
 			ctx->bvh_graph_key = key;
-			cudaGraphDestroy(g);
-			CK(cudaGraphLaunch(ctx->bvh_graph, st));
+			launched		   = true;
 		}
 		else
 		{
-			if(g)
+			// capture / instantiation not possible here: launch the kernels one by one, now and from now on
+			if(ctx->bvh_graph)
 			{
-				cudaGraphDestroy(g);
+				cudaGraphExecDestroy(ctx->bvh_graph);
+				ctx->bvh_graph = nullptr;
 			}
-			ctx->bvh_graph = nullptr;
+			ctx->bvh_graph_broken = true;
 			cudaGetLastError();
-			return fail(ctx, SKR_ERR_CUDA, "LBVH build: graph capture failed (set SKR_NO_GRAPH=1 to launch the kernels directly)");
 		}
+		if(g)
+		{
+			cudaGraphDestroy(g);
+		}
+	}
+	if(!launched)
+	{
+		enqueue_build();
 	}
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(ctx->h_count, big_count, sizeof(int), cudaMemcpyDeviceToHost, st)); // read after the upload's sync
