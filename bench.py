@@ -12,10 +12,15 @@ shadow rays, counted on the device in an untimed pass with the same 
             stream, per step, L2 flushed between steps outside the events; max over ranks).
   e2e     : the same metric through the reference-facing call with HOST buffers: skr_scene_upload (H2D) + skr_render
             into pinned host memory (D2H) every step, wall clock around the calls.
-  N > 1   : the frame is split into interleaved 32x32 tiles over the ranks (one process per GPU, torchrun), each
-            rank renders its tiles, ONE all-gather (NCCL) of the RGB8 tiles, de-interleave kernel -> "strong".
+  N > 1   : the frame is split into interleaved 32x32 tiles over the ranks (one process per GPU, torchrun); each rank's
+            render kernel stores its finished pixels straight into every rank's frame over NVLink (torch symmetric
+            memory, skr_render_peers_device) and one symmetric-memory barrier ends the frame; where peer mapping is
+            unavailable (or SKR_BENCH_NO_P2P=1): ONE all-gather (NCCL) of the RGB8 tiles + de-interleave kernel.
+            Total work is fixed -> "strong".
   roofline: FP32 CUDA-core pipe (this path has no dense contraction; tensor cores unused; HBM traffic is the
             framebuffer only).  peak = FMA microbenchmark measured live in this run (MEASURED_PEAKS.json has no FP32).
+            `achieved` = the reference algorithm's arithmetic / kernel time; `executed` = what the kernels really ran
+            (bundle culling proves most sphere tests of a jittered pixel unnecessary and skips them).
   --impl reference : the reference's own CPU code (oracle/_ref/libskr_ref.so, compiled from the reference's sources;
             else the C port) with all host threads on a bounded row window of the same frame.
 """

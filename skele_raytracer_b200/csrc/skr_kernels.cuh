@@ -7,9 +7,11 @@
 //                        to wavefront queue level 0.
 //   shade_expand_kernel  one thread per queued hit: direct illumination (+ shadow rays) of that hit, then -- if the
 //                        reference would recurse (depth - 1 >= 1) -- the fan-out of montecarlo_global_illumination
-//                        (src/raytrace.h:107-136): n child rays generated from Philox draws, intersected, misses
-//                        folded into the local sum, sphere hits pushed (warp-aggregated) to the next queue level.
-//                        Every lane of a warp holds a hit, so shading never idles lanes on misses.
+//                        (src/raytrace.h:107-136): n child rays generated from Philox draws, intersected four at a
+//                        time, misses folded into the local sum, sphere hits pushed (warp-aggregated, one reservation
+//                        per batch) to the next queue level as the ray that found them; the exact hit point is
+//                        computed by the consumer.  Every lane of a warp holds a hit, so shading never idles lanes on
+//                        misses.
 //   resolve_kernel       accumulators -> float image and RGB8 ((unsigned char)(min(1,c)*255), src/main.cpp:96).
 //
 // Accumulation across kernels is in signed 64-bit fixed point (2^-32): integer atomics commute, so the image is
