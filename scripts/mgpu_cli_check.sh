@@ -5,10 +5,6 @@ set -e
 N=${1:-2}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out/mg
-python - <<'PY'
-import numpy as np, os
-# .scn files for the CLI from the golden scene snapshots are not needed: tests/golden/tiny.scn is a real scene file
-PY
 ok=1
 for mode in "--width 1920 --height 1080 --jsample 3 --shadow --seed 5" "--width 640 --height 360 --gillum 8 --jsample 2 --shadow --seed 6" "--width 641 --height 357"; do
   host/raytracer --path tests/golden/tiny.scn --output gpurun_out/mg/a.ppm $mode > /dev/null

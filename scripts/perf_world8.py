@@ -1,3 +1,5 @@
+"""scripts/perf_world8.py -- kernel time of ONE rank's share of the config-2 frame at world = 8 (interleaved tiles), emulated on a
+single GPU: what bounds the 8-GPU step besides the exchange."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

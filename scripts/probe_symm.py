@@ -1,3 +1,5 @@
+"""scripts/probe_symm.py -- run under torchrun: does torch symmetric memory (peer-mapped buffers + barrier) work on this box, and
+what does its barrier cost?  (The answer decided bench.py's frame assembly at N > 1: PeerFrames in distributed.py.)"""
 import os, sys, time
 import torch, torch.distributed as dist
 import torch.distributed._symmetric_memory as symm_mem
