@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SKR_ABI_VERSION 2
+#define SKR_ABI_VERSION 3
 
 typedef struct skr_ctx skr_ctx;
 
@@ -134,6 +134,12 @@ int skr_abi_version(void);
 /* Scene upload: AoS -> SoA device buffers (spheres/materials/lights), triangles flattened to
  * float4 vertex triples and a device-built LBVH (Morton codes, radix sort, Karras hierarchy, refit). */
 int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *scene);
+
+/* Optional (ABI 3): allocates, ahead of time, everything frames with these options need -- the wavefront queue arena and
+ * the accumulators of a --gillum / fresnel tree, the device frame of skr_render -- and loads the kernels they launch,
+ * so that the first frame costs what every later frame costs.  Without it the first frame does this itself (outside
+ * its device-timed span).  Allocations are kept and reused by later frames and uploads. */
+int skr_reserve(skr_ctx *ctx, const skr_options *opt);
 
 /* Renders one frame (or this rank's tiles of it) and copies the result to HOST buffers.
  *   rgb8  : H*W*3 bytes, row-major top-down RGB, (unsigned char)(min(1,c)*255) as src/main.cpp:96; may be NULL

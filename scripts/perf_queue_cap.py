@@ -13,10 +13,10 @@ r = S.Renderer()
 for w in ["c3", "c5"]:
     scene, kw, desc = WORKLOADS[w]
     r.upload(S.Scene.load(os.path.join(G, scene + ".npz")))
-    for cap in [32 << 20, 64 << 20, 128 << 20, 256 << 20, 512 << 20]:
+    for cap in [4 << 20, 8 << 20, 16 << 20, 32 << 20, 64 << 20, 128 << 20]:
         o = S.Options(seed=1, queue_capacity=cap, **kw)
         ts = []
-        for _ in range(5):
+        for _ in range(4):
             st = r.render_device(o, 0, 0)
             ts.append(st.ms_total)
         print(f"{w} cap={cap >> 20}M min={min(ts):.2f} median={sorted(ts)[2]:.2f} max={max(ts):.2f} bounce={st.ms_bounce:.2f} launches={st.kernel_launches} "

@@ -200,6 +200,7 @@ class Renderer:
         L.skr_last_error.argtypes = [C.c_void_p]
         L.skr_scene_upload.argtypes = [C.c_void_p, C.POINTER(_SceneDesc)]
         L.skr_render.argtypes = [C.c_void_p, C.POINTER(_Options), C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        L.skr_reserve.argtypes = [C.c_void_p, C.POINTER(_Options)]
         L.skr_render_device.argtypes = [C.c_void_p, C.POINTER(_Options), C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         L.skr_tiles_bytes.restype = C.c_int64
         L.skr_tiles_bytes.argtypes = [C.POINTER(_Options)]
@@ -238,6 +239,11 @@ class Renderer:
     def upload(self, scene: Scene) -> None:
         d, keep = scene._desc()
         self._check(self.lib.skr_scene_upload(self.ctx, C.byref(d)), "skr_scene_upload")
+
+    def reserve(self, option: Options) -> None:
+        """skr_reserve: allocate queues / accumulators / frame and load the kernels ahead of the first frame."""
+        o = option._c()
+        self._check(self.lib.skr_reserve(self.ctx, C.byref(o)), "skr_reserve")
 
     def render(self, option: Options, rgb8: np.ndarray | None = None, rgb32: np.ndarray | None = None,
                want_rgb8: bool = True, want_rgb32: bool = True):

@@ -81,11 +81,13 @@ struct skr_ctx
 	long long *d_accum = nullptr;
 	size_t accum_bytes = 0;
 
-	// wavefront queues
+	// wavefront queues: ONE arena (counters first, then a / b / c / d of every level), carved by ensure_queues
 	std::vector<Queue> queues;
 	unsigned queue_cap = 0;
-	unsigned *d_counts = nullptr; // one per level
+	unsigned *d_counts = nullptr; // one per level (inside the arena)
 	int n_levels_alloc = 0;
+	char *d_arena = nullptr;
+	size_t arena_bytes = 0;
 	unsigned *h_count = nullptr; // pinned
 
 	unsigned long long *d_counters = nullptr; // 9 (16 allocated)
@@ -111,6 +113,7 @@ struct skr_ctx
 	bool bvh_graph_broken = false; // capture failed once: direct launches from then on
 
 	unsigned launches = 0, chunks = 0;
+	bool async_pending = false; // a fire-and-forget frame was enqueued since the error word was last read
 	bool timing = true; // false: fire-and-forget frame, no per-kernel events
 	unsigned long long queue_entries = 0;
 };
@@ -233,34 +236,49 @@ void launch_primary(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, const 
 	}
 }
 
-template <bool STATS>
-void launch_shade_expand(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, const Queue &in, unsigned start, unsigned count, const Queue &out,
-						 int expand)
+template <bool STATS, bool LEAF>
+void launch_shade_expand_v(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, const Queue &in, unsigned start, unsigned count, const Queue &out,
+						   int expand)
 {
 	const SceneView &sv = ctx->sv;
 	cudaStream_t st		= ctx->stream;
-	const size_t sm		= ctx->smem_bytes;
+	const size_t stage	= LEAF ? (size_t) SKR_LEAF_CTA_BYTES : 0;
+	const size_t sm		= ctx->smem_bytes + stage;
 	if(!sv.blob_in_smem)
 	{
-		shade_expand_kernel<STATS, false, true, true><<<blocks, SKR_BLOCK, 0, st>>>(sv, fp, in, start, count, out, expand);
+		shade_expand_kernel<STATS, false, true, true, LEAF><<<blocks, SKR_BLOCK, stage, st>>>(sv, fp, in, start, count, out, expand);
 		return;
 	}
 	const bool tris = sv.T > 0, fog = sv.F > 0;
 	if(tris && fog)
 	{
-		shade_expand_kernel<STATS, true, true, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+		shade_expand_kernel<STATS, true, true, true, LEAF><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
 	}
 	else if(tris)
 	{
-		shade_expand_kernel<STATS, true, true, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+		shade_expand_kernel<STATS, true, true, false, LEAF><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
 	}
 	else if(fog)
 	{
-		shade_expand_kernel<STATS, true, false, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+		shade_expand_kernel<STATS, true, false, true, LEAF><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
 	}
 	else
 	{
-		shade_expand_kernel<STATS, true, false, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+		shade_expand_kernel<STATS, true, false, false, LEAF><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, in, start, count, out, expand);
+	}
+}
+// expand: 0 = shade only, 1 = shade + push the children to `out`, 2 = shade + shade the (leaf) children in place
+template <bool STATS>
+void launch_shade_expand(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, const Queue &in, unsigned start, unsigned count, const Queue &out,
+						 int expand)
+{
+	if(expand == 2)
+	{
+		launch_shade_expand_v<STATS, true>(ctx, blocks, fp, in, start, count, out, 1);
+	}
+	else
+	{
+		launch_shade_expand_v<STATS, false>(ctx, blocks, fp, in, start, count, out, expand);
 	}
 }
 
@@ -270,7 +288,15 @@ cudaError_t smem_attr_one(int bytes)
 	cudaError_t e = cudaFuncSetAttribute(primary_kernel<GI, STATS, true, TRIS, FOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 	if(e == cudaSuccess && GI)
 	{
-		e = cudaFuncSetAttribute(shade_expand_kernel<STATS, true, TRIS, FOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+		e = cudaFuncSetAttribute(shade_expand_kernel<STATS, true, TRIS, FOG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	}
+	if(e == cudaSuccess && GI)
+	{
+		e = cudaFuncSetAttribute(shade_expand_kernel<STATS, true, TRIS, FOG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + SKR_LEAF_CTA_BYTES);
+	}
+	if(e == cudaSuccess && GI && TRIS && FOG) // once per STATS: the fresnel pass has no (TRIS, FOG) variants
+	{
+		e = cudaFuncSetAttribute(fresnel_expand_kernel<STATS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 	}
 	return e;
 }
@@ -278,7 +304,7 @@ cudaError_t smem_attr_one(int bytes)
 int set_smem_attr(skr_ctx *ctx)
 {
 	const int bytes = (int) ctx->smem_bytes;
-	if(bytes > 48 * 1024)
+	if(bytes + SKR_LEAF_CTA_BYTES > 48 * 1024)
 	{
 		CK((smem_attr_one<false, false, false, false>(bytes)));
 		CK((smem_attr_one<false, false, false, true>(bytes)));
@@ -432,12 +458,50 @@ int build_bvh(skr_ctx *ctx, int T)
 	return SKR_OK;
 }
 
+// Kernel functions of the variants a scene's frames launch (skr_reserve loads them ahead of the first frame: CUDA loads a
+// kernel's code lazily at its first launch, a few ms each).
+template <bool STATS>
+void frame_kernels(const skr_ctx *ctx, bool tree, bool leaf, bool fresnel, std::vector<const void *> &out)
+{
+	const SceneView &sv = ctx->sv;
+	const bool tris = sv.T > 0, fog = sv.F > 0;
+#define SKR_PICK(K, ...)                                                                                                      \
+	(!sv.blob_in_smem ? (const void *) K<__VA_ARGS__, false, true, true SKR_TAIL> :                                           \
+	 tris && fog	   ? (const void *) K<__VA_ARGS__, true, true, true SKR_TAIL> :                                            \
+	 tris			   ? (const void *) K<__VA_ARGS__, true, true, false SKR_TAIL> :                                           \
+	 fog			   ? (const void *) K<__VA_ARGS__, true, false, true SKR_TAIL> :                                           \
+						 (const void *) K<__VA_ARGS__, true, false, false SKR_TAIL>)
+#define SKR_TAIL
+	out.push_back(tree ? SKR_PICK(primary_kernel, true, STATS) : SKR_PICK(primary_kernel, false, STATS));
+#undef SKR_TAIL
+	if(tree)
+	{
+#define SKR_TAIL , false
+		out.push_back(SKR_PICK(shade_expand_kernel, STATS));
+#undef SKR_TAIL
+		if(leaf)
+		{
+#define SKR_TAIL , true
+			out.push_back(SKR_PICK(shade_expand_kernel, STATS));
+#undef SKR_TAIL
+		}
+		if(fresnel)
+		{
+			out.push_back(sv.blob_in_smem ? (const void *) fresnel_expand_kernel<STATS, true> : (const void *) fresnel_expand_kernel<STATS, false>);
+		}
+		out.push_back((const void *) resolve_kernel);
+	}
+#undef SKR_PICK
+}
+
 struct Plan
 {
 	FrameParams fp;
 	long long npix_local; // local pixels incl. padding (tiles_local * tile^2)
 	long long tiles_local;
-	int levels;
+	int levels;		  // depth levels of the --gillum / fresnel tree (0: none)
+	int qlevels;	  // queue levels needed: `levels`, or one less when the leaves are shaded in place
+	bool leaf_inline; // depth-1 hits are shaded by the warp that found them (shade_expand_kernel<..., LEAF>)
 };
 
 int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
@@ -510,6 +574,27 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	pl.tiles_local = (fp.tiles_total + world - 1) / world;
 	pl.npix_local  = pl.tiles_local * tile * tile;
 	pl.levels	   = ((fp.gi || fp.fresnel) && fp.max_depth > 0) ? fp.max_depth : 0;
+	{
+		// leaves in place: plain --gillum trees (the fresnel pass pushes its own leaf children through the queue)
+		const char *no = getenv("SKR_NO_LEAF_INLINE");
+		pl.leaf_inline = pl.levels >= 2 && fp.gi && fp.n_gi > 0 && fp.n_gi <= SKR_LEAF_MAX_CHILDREN && !fp.fresnel && !(no && no[0] == '1');
+		pl.qlevels	   = pl.leaf_inline ? pl.levels - 1 : pl.levels;
+	}
+	{
+		// Philox counters number the nodes of a sample's tree as child = parent * node_base + c + 1 in 32 bits: the ids of
+		// level k stay below node_base^k, so the deepest level (max_depth - 1) must fit.  (The reference would trace
+		// node_base^(depth-1) rays per sample there: hours per pixel long before this limit.)
+		double top = 1.0;
+		for(int k = 1; k < pl.levels; k++)
+		{
+			top *= (double) fp.node_base;
+		}
+		if(top > 4294967295.0)
+		{
+			return fail(ctx, SKR_ERR_ARG, "skr_options: a tree of %u children per hit and depth %d needs more than 32 bits of node ids (%.3g nodes per sample)",
+						fp.node_base - 1u, fp.max_depth, top);
+		}
+	}
 	return SKR_OK;
 }
 
@@ -519,31 +604,40 @@ int ensure_queues(skr_ctx *ctx, int levels, unsigned cap)
 	{
 		return SKR_OK;
 	}
-	for(Queue &q : ctx->queues)
-	{
-		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c), cudaFree(q.d);
-	}
+	// one allocation for all levels; an arena that is already big enough is re-carved, not re-allocated
+	const auto up = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+	const size_t per_level = up(sizeof(float4) * (size_t) cap) * 3 + up(sizeof(uint32_t) * (size_t) cap);
+	const size_t head	   = up(sizeof(unsigned) * (size_t) (levels + 1));
+	const size_t want	   = head + per_level * (size_t) levels;
 	ctx->queues.clear();
-	if(ctx->d_counts)
-	{
-		cudaFree(ctx->d_counts);
-		ctx->d_counts = nullptr;
-	}
 	ctx->n_levels_alloc = 0;
-	CK(cudaMalloc(&ctx->d_counts, sizeof(unsigned) * (size_t) (levels + 1)));
+	ctx->queue_cap		= 0;
+	if(want > ctx->arena_bytes)
+	{
+		if(ctx->d_arena)
+		{
+			cudaFree(ctx->d_arena);
+			ctx->d_arena	 = nullptr;
+			ctx->arena_bytes = 0;
+		}
+		CK(cudaMalloc(&ctx->d_arena, want));
+		ctx->arena_bytes = want;
+	}
+	ctx->d_counts = reinterpret_cast<unsigned *>(ctx->d_arena);
+	char *at	  = ctx->d_arena + head;
 	for(int l = 0; l < levels; l++)
 	{
 		Queue q{};
-		CK(cudaMalloc(&q.a, sizeof(float4) * (size_t) cap));
-		CK(cudaMalloc(&q.b, sizeof(float4) * (size_t) cap));
-		CK(cudaMalloc(&q.c, sizeof(uint32_t) * (size_t) cap));
-		CK(cudaMalloc(&q.d, sizeof(float4) * (size_t) cap));
+		q.a = reinterpret_cast<float4 *>(at), at += up(sizeof(float4) * (size_t) cap);
+		q.b = reinterpret_cast<float4 *>(at), at += up(sizeof(float4) * (size_t) cap);
+		q.d = reinterpret_cast<float4 *>(at), at += up(sizeof(float4) * (size_t) cap);
+		q.c = reinterpret_cast<uint32_t *>(at), at += up(sizeof(uint32_t) * (size_t) cap);
 		q.count = ctx->d_counts + l;
 		q.cap	= cap;
 		ctx->queues.push_back(q);
 	}
-	ctx->n_levels_alloc	 = levels;
-	ctx->queue_cap		 = cap;
+	ctx->n_levels_alloc = levels;
+	ctx->queue_cap		= cap;
 	return SKR_OK;
 }
 
@@ -591,10 +685,11 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 	const unsigned fan	  = (expand_gi ? (unsigned) fp.n_gi : 0u) + (expand_fr ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
 	const Queue in		  = queue_view(ctx, level);
 	ctx->queue_entries += count;
-	if(fan == 0)
+	const bool leaves_here = pl.leaf_inline && depth == 2; // the children of these hits are leaves: shaded in place
+	if(fan == 0 || leaves_here)
 	{
 		span_begin(ctx, CAT_BOUNCE);
-		launch_shade_expand<STATS>(ctx, (count + SKR_BLOCK - 1) / SKR_BLOCK, fp, in, 0u, count, in, 0);
+		launch_shade_expand<STATS>(ctx, (count + SKR_BLOCK - 1) / SKR_BLOCK, fp, in, 0u, count, in, leaves_here ? 2 : 0);
 		span_end(ctx);
 		ctx->launches++;
 		CK(cudaGetLastError());
@@ -632,53 +727,61 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 	return SKR_OK;
 }
 
+// Everything a frame allocates, sized and allocated BEFORE its timed span (and by skr_reserve ahead of the first frame):
+// the queue arena and the accumulators of a --gillum / fresnel tree.  An allocation that is already big enough is kept.
+int prepare_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
+{
+	FrameParams &fp = pl.fp;
+	if(!((fp.gi || fp.fresnel) && pl.levels > 0))
+	{
+		return SKR_OK;
+	}
+	const unsigned fan = (unsigned) fp.n_gi + (fp.fresnel ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
+	unsigned cap	   = (unsigned) o->queue_capacity;
+	if(o->queue_capacity <= 0)
+	{
+		// default: what one fan-out of all primary samples could need, between 1 M and 128 M entries, and never more
+		// than a quarter of the free memory over all levels; an allocation that is already big enough is kept
+		const unsigned long long want = (unsigned long long) pl.npix_local * (unsigned) fp.spp * (fan ? fan : 1u);
+		cap = want > MAX_QUEUE_CAP ? MAX_QUEUE_CAP : (want < MIN_QUEUE_CAP ? MIN_QUEUE_CAP : (unsigned) want);
+		if(ctx->queue_cap >= cap && ctx->n_levels_alloc >= pl.qlevels)
+		{
+			cap = ctx->queue_cap;
+		}
+		else
+		{
+			size_t free_b = 0, total_b = 0;
+			if(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+			{
+				const size_t budget = (free_b + ctx->arena_bytes) / 4 / (size_t) pl.qlevels / 52;
+				if(budget < cap)
+				{
+					cap = (unsigned) budget;
+				}
+			}
+		}
+	}
+	const unsigned need = fan > (unsigned) fp.spp ? fan : (unsigned) fp.spp;
+	if(cap < need * SKR_BLOCK)
+	{
+		cap = need * SKR_BLOCK;
+	}
+	int rc = ensure_queues(ctx, pl.qlevels, cap);
+	if(rc)
+	{
+		return rc;
+	}
+	CK(ensure(ctx->d_accum, ctx->accum_bytes, sizeof(long long) * SKR_ACC_STRIDE * (size_t) pl.npix_local));
+	fp.accum = ctx->d_accum;
+	return SKR_OK;
+}
+
 template <bool STATS>
 int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 {
 	FrameParams &fp = pl.fp;
 	cudaStream_t st = ctx->stream;
 	const bool tree = fp.gi || fp.fresnel;
-	if(tree)
-	{
-		const unsigned fan0 = (unsigned) fp.n_gi + (fp.fresnel ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
-		unsigned cap		= (unsigned) o->queue_capacity;
-		if(o->queue_capacity <= 0)
-		{
-			// default: what one fan-out of all primary samples could need, between 1 M and 128 M entries, and never more
-			// than a quarter of the free memory over all levels; an allocation that is already big enough is kept
-			const unsigned long long want = (unsigned long long) pl.npix_local * (unsigned) fp.spp * (fan0 ? fan0 : 1u);
-			cap = want > MAX_QUEUE_CAP ? MAX_QUEUE_CAP : (want < MIN_QUEUE_CAP ? MIN_QUEUE_CAP : (unsigned) want);
-			if(ctx->queue_cap >= cap && ctx->n_levels_alloc >= pl.levels)
-			{
-				cap = ctx->queue_cap;
-			}
-			else
-			{
-				size_t free_b = 0, total_b = 0;
-				if(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-				{
-					const size_t budget = free_b / 4 / (size_t) (pl.levels > 0 ? pl.levels : 1) / 52;
-					if(budget < cap)
-					{
-						cap = (unsigned) budget;
-					}
-				}
-			}
-		}
-		const unsigned fan	= (unsigned) fp.n_gi + (fp.fresnel ? 1u + (unsigned) (ctx->sv.L + ctx->sv.D) : 0u);
-		const unsigned need = fan > (unsigned) fp.spp ? fan : (unsigned) fp.spp;
-		if(cap < need * SKR_BLOCK)
-		{
-			cap = need * SKR_BLOCK;
-		}
-		int rc = ensure_queues(ctx, pl.levels, cap);
-		if(rc)
-		{
-			return rc;
-		}
-		CK(ensure(ctx->d_accum, ctx->accum_bytes, sizeof(long long) * 3 * (size_t) pl.npix_local));
-		fp.accum = ctx->d_accum;
-	}
 	if(!tree || pl.levels == 0)
 	{
 		span_begin(ctx, CAT_PRIMARY);
@@ -722,6 +825,22 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	return SKR_OK;
 }
 
+// the device error word after the stream has drained (h_err holds a fresh copy): reported once, then cleared
+int check_error_word(skr_ctx *ctx, const char *what)
+{
+	const int flag		= *ctx->h_err;
+	const bool pending	= ctx->async_pending;
+	ctx->async_pending	= false;
+	if(!flag)
+	{
+		return SKR_OK;
+	}
+	*ctx->h_err = 0;
+	cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream);
+	return fail(ctx, SKR_ERR_CUDA, "internal: %s (flag %d) in %s%s", (flag & 2) ? "BVH traversal stack overflow" : "wavefront queue overflow", flag, what,
+				pending ? " or in an asynchronous frame enqueued before it" : "");
+}
+
 // common driver: outputs already set in pl.fp
 // `after_launch` (optional) runs once the frame's kernels are enqueued, before anything waits for them.
 int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats, const std::function<int()> &after_launch = nullptr)
@@ -743,6 +862,13 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	// a single-kernel frame needs no per-kernel events (its span is the frame), no counter reset unless counters were
 	// asked for, and no reset of the error word (zero unless a frame failed; cleared again below when read non-zero)
 	ctx->timing = !async && tree;
+	{
+		const int rc_prep = prepare_frame(ctx, o, pl);
+		if(rc_prep)
+		{
+			return rc_prep;
+		}
+	}
 	if(!async)
 	{
 		if(want_stats)
@@ -762,6 +888,7 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	}
 	if(async)
 	{
+		ctx->async_pending = true; // its error word is read by skr_sync() or by the next synchronous frame
 		return SKR_OK;
 	}
 	CK(cudaEventRecord(ctx->ev_end, st));
@@ -772,10 +899,12 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 		CK(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, st));
 	}
 	CK(cudaStreamSynchronize(st));
-	if(*ctx->h_err)
 	{
-		cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st);
-		return fail(ctx, SKR_ERR_CUDA, "internal: %s (flag %d)", (*ctx->h_err & 2) ? "BVH traversal stack overflow" : "wavefront queue overflow", *ctx->h_err);
+		const int rc_err = check_error_word(ctx, "this frame");
+		if(rc_err)
+		{
+			return rc_err;
+		}
 	}
 	if(stats)
 	{
@@ -880,7 +1009,7 @@ int skr_init(int device, skr_ctx **out)
 	{
 		return bail(e, "cudaMalloc");
 	}
-	if((e = cudaMalloc(&c->d_err, sizeof(int))) != cudaSuccess)
+	if((e = cudaMalloc(&c->d_err, sizeof(int))) != cudaSuccess || (e = cudaMemset(c->d_err, 0, sizeof(int))) != cudaSuccess)
 	{
 		return bail(e, "cudaMalloc");
 	}
@@ -892,6 +1021,7 @@ int skr_init(int device, skr_ctx **out)
 	{
 		return bail(e, "cudaHostAlloc");
 	}
+	*c->h_err = 0;
 	cudaEventCreate(&c->ev_begin);
 	cudaEventCreate(&c->ev_end);
 	cudaEventCreate(&c->ev_x0);
@@ -927,11 +1057,8 @@ void skr_destroy(skr_ctx *ctx)
 	}
 	cudaFree(ctx->d_blob), cudaFree(ctx->d_tris_raw), cudaFree(ctx->d_tri_v), cudaFree(ctx->d_bvh), cudaFree(ctx->d_scratch);
 	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
-	for(Queue &q : ctx->queues)
-	{
-		cudaFree(q.a), cudaFree(q.b), cudaFree(q.c), cudaFree(q.d);
-	}
-	cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band), cudaFree(ctx->d_big);
+	cudaFree(ctx->d_arena);
+	cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band), cudaFree(ctx->d_big);
 	if(ctx->copy_stream)
 	{
 		cudaStreamDestroy(ctx->copy_stream);
@@ -971,8 +1098,15 @@ void *skr_stream(skr_ctx *ctx)
 int skr_sync(skr_ctx *ctx)
 {
 	REQUIRE_CTX();
+	if(!ctx->async_pending)
+	{
+		CK(cudaStreamSynchronize(ctx->stream));
+		return SKR_OK;
+	}
+	// asynchronous frames report through the device error word (queue / traversal-stack overflow): read it here
+	CK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-	return SKR_OK;
+	return check_error_word(ctx, "an asynchronous frame");
 }
 
 int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
@@ -1205,6 +1339,40 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	CK(cudaStreamSynchronize(ctx->stream));
 	sv.nbig			= T > 0 ? std::min((int) *ctx->h_count, BIG_TRI_CAP) : 0;
 	ctx->have_scene = true;
+	return SKR_OK;
+}
+
+int skr_reserve(skr_ctx *ctx, const skr_options *opt)
+{
+	REQUIRE_CTX();
+	REQUIRE_SCENE();
+	Plan pl;
+	int rc = make_plan(ctx, opt, pl);
+	if(rc)
+	{
+		return rc;
+	}
+	if((rc = prepare_frame(ctx, opt, pl)) != 0)
+	{
+		return rc;
+	}
+	const size_t npx = (size_t) opt->width * opt->height;
+	CK(ensure(ctx->d_rgb8, ctx->rgb8_bytes, npx * 3));
+	std::vector<const void *> fns;
+	const bool tree = (pl.fp.gi || pl.fp.fresnel) && pl.levels > 0;
+	if(opt->collect_stats)
+	{
+		frame_kernels<true>(ctx, tree, pl.leaf_inline, pl.fp.fresnel != 0, fns);
+	}
+	else
+	{
+		frame_kernels<false>(ctx, tree, pl.leaf_inline, pl.fp.fresnel != 0, fns);
+	}
+	for(const void *f : fns)
+	{
+		cudaFuncAttributes a;
+		CK(cudaFuncGetAttributes(&a, f));
+	}
 	return SKR_OK;
 }
 

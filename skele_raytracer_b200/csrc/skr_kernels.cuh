@@ -68,7 +68,7 @@ struct FrameParams
 	// stream-ordered wait on the copy stream is parked on.  Null when unused.
 	unsigned *band_count, *band_flag;
 	unsigned band_ctas, band_seq;
-	long long *accum; // 3 per local pixel (gi only)
+	long long *accum; // SKR_ACC_STRIDE per local pixel (gi / fresnel frames only)
 	unsigned long long *counters; // 9 device counters (STATS)
 	int *err;
 };
@@ -110,12 +110,68 @@ SKR_DEV long long encode_pixel(const FrameParams &fp, int x, int y)
 	return lt * (long long) (fp.tile * fp.tile) + (w << 5) + lane;
 }
 
-SKR_DEV long long to_fixed(float v)
+// Accumulators (--gillum / fresnel frames): per local pixel 3 x int64 fixed point (2^-32) + one flags word.  Integer
+// atomics commute, so the frame is bit-identical whatever order the queues were filled in.  Contributions that fixed
+// point cannot hold -- NaN (`--gillum 0` divides by zero paths, src/raytrace.h:133), +-inf, |v| >= 2^16 -- are recorded
+// OUT OF BAND in the flags word (bit ch: NaN, bit 3 + ch: +huge, bit 6 + ch: -huge) and add nothing to the sum, so any
+// number of them per pixel resolves like the reference's float sum would: NaN stays NaN (-> byte 255, std::min(1, NaN)
+// = 1), +inf stays +inf, +inf - inf = NaN.
+#define SKR_ACC_STRIDE 4
+SKR_DEV long long to_fixed(float v, unsigned &flags, int ch)
 {
-	v = (v != v) ? 1.0e9f : fminf(fmaxf(v, -1.0e9f), 1.0e9f); // NaN -> white, like std::min(float(1), NaN) = 1
+	if(!(fabsf(v) < 65536.0f))
+	{
+		flags |= (v != v ? 1u : (v > 0.0f ? 8u : 64u)) << ch;
+		return 0;
+	}
 	return __float2ll_rn(v * SKR_FIX_SCALE);
 }
-SKR_DEV float from_fixed(long long a) { return (float) ((double) a * (1.0 / 4294967296.0)); }
+SKR_DEV float from_fixed(long long a, unsigned flags, int ch)
+{
+	const unsigned f = flags >> ch;
+	if((f & 1u) || ((f & 8u) && (f & 64u)))
+	{
+		return CUDART_NAN_F;
+	}
+	if(f & 8u)
+	{
+		return CUDART_INF_F;
+	}
+	if(f & 64u)
+	{
+		return -CUDART_INF_F;
+	}
+	return (float) ((double) a * (1.0 / 4294967296.0));
+}
+SKR_DEV void accum_store(long long *accum, long long lp, float3 c) // first writer of the pixel (primary_kernel)
+{
+	unsigned fl		= 0;
+	long long *a	= accum + SKR_ACC_STRIDE * lp;
+	const long long x = to_fixed(c.x, fl, 0), y = to_fixed(c.y, fl, 1), z = to_fixed(c.z, fl, 2);
+	reinterpret_cast<longlong2 *>(a)[0] = make_longlong2(x, y);
+	reinterpret_cast<longlong2 *>(a)[1] = make_longlong2(z, (long long) fl);
+}
+// (ex, ey, ez, efl): fixed-point terms already summed elsewhere (leaf hits shaded in place), folded into the same atomics
+SKR_DEV void accum_add(long long *accum, long long lp, float3 c, long long ex = 0, long long ey = 0, long long ez = 0, unsigned efl = 0)
+{
+	unsigned fl				= efl;
+	unsigned long long *a	= reinterpret_cast<unsigned long long *>(accum + SKR_ACC_STRIDE * lp);
+	const long long x = to_fixed(c.x, fl, 0) + ex, y = to_fixed(c.y, fl, 1) + ey, z = to_fixed(c.z, fl, 2) + ez;
+	atomicAdd(a + 0, (unsigned long long) x);
+	atomicAdd(a + 1, (unsigned long long) y);
+	atomicAdd(a + 2, (unsigned long long) z);
+	if(fl)
+	{
+		atomicOr(a + 3, (unsigned long long) fl);
+	}
+}
+SKR_DEV float3 accum_load(const long long *accum, long long lp)
+{
+	const longlong2 p = reinterpret_cast<const longlong2 *>(accum + SKR_ACC_STRIDE * lp)[0];
+	const longlong2 q = reinterpret_cast<const longlong2 *>(accum + SKR_ACC_STRIDE * lp)[1];
+	const unsigned fl = (unsigned) q.y;
+	return f3(from_fixed(p.x, fl, 0), from_fixed(p.y, fl, 1), from_fixed(q.x, fl, 2));
+}
 
 SKR_DEV uint8_t quantise(float c) // (unsigned char)(std::min(float(1), c) * 255), src/main.cpp:96
 {
@@ -380,9 +436,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 	{
 		if(GI)
 		{
-			fp.accum[3 * lp + 0] = to_fixed(sum.x);
-			fp.accum[3 * lp + 1] = to_fixed(sum.y);
-			fp.accum[3 * lp + 2] = to_fixed(sum.z);
+			accum_store(fp.accum, lp, sum);
 		}
 		else
 		{
@@ -414,9 +468,122 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Leaf hits shaded in place (shade_expand_kernel<..., LEAF = true>).
+//
+// The children of a depth-2 hit have depth 1: the reference shades them and recurses no further (src/raytrace.h:142-145
+// under :212).  They are the bulk of a --gillum tree (config 5: 90 % of all sphere hits).  Instead of a round trip
+// through a global-memory queue (52 B written + read per hit, three 64-bit global atomics per hit) the warp that found
+// them shades them itself -- but never with the 15-30 % of lanes that happen to hold a hit: the hits of the warp's 32
+// parents are compacted into a per-warp staging ring in shared memory (ballot + popc), and as soon as 32 are pending
+// ALL lanes shade one each.  A leaf's contribution is added, in fixed point, to its parent's accumulator in shared
+// memory (integer adds commute -> the frame stays bit-identical to the queued path, run to run and for any chunking);
+// the parent's lane folds that into its ONE global atomic triple.
+//
+// Per-warp staging: SKR_LEAF_SLOTS x 2 float4   slot = (child direction, loop t), (weight w = T kd 2pi r1 / n, meta)
+//                                               meta = sphere | parent lane << 16 | child index << 21
+//                   32 x 4 x u64                per parent lane: fixed-point sum r, g, b + flags
+#define SKR_LEAF_SLOTS (32 + 32 * SKR_GI_BATCH)
+#define SKR_LEAF_WARP_BYTES (SKR_LEAF_SLOTS * 32 + 32 * 4 * 8)
+#define SKR_LEAF_CTA_BYTES ((SKR_BLOCK / 32) * SKR_LEAF_WARP_BYTES)
+#define SKR_LEAF_MAX_CHILDREN 2047
+
+struct LeafStage
+{
+	float4 *slot;			 // this warp's ring
+	unsigned long long *acc; // this warp's 32 x 4 parent accumulators
+	unsigned pending;		 // warp-uniform
+};
+
+// shade `count` (<= 32) staged leaf hits starting at slot `first`; every lane of the warp calls this
+template <bool STATS, bool FOG>
+SKR_DEV void leaf_shade_round(const float4 *__restrict__ B, const SceneView &sv, const FrameParams &fp, const LeafStage &ls, unsigned first, unsigned count,
+							  float3 o, const RngCtx &rng, Counters &cnt)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const bool act		= lane < count;
+	const unsigned at	= first + (act ? lane : 0u);
+	const float4 s0 = ls.slot[2 * at], s1 = ls.slot[2 * at + 1];
+	const uint32_t meta = f2u(s1.w);
+	const int sidx		= (int) (meta & 0xffffu);
+	const int src		= (int) ((meta >> 16) & 31u);
+	// the parent's ray origin and RNG coordinates live in the parent lane's registers
+	const float3 po = f3(__shfl_sync(0xffffffffu, o.x, src), __shfl_sync(0xffffffffu, o.y, src), __shfl_sync(0xffffffffu, o.z, src));
+	RngCtx r2;
+	r2.pixel  = __shfl_sync(0xffffffffu, rng.pixel, src);
+	r2.sample = __shfl_sync(0xffffffffu, rng.sample, src);
+	r2.node	  = __shfl_sync(0xffffffffu, rng.node, src) * fp.node_base + (meta >> 21) + 1u;
+	r2.key	  = fp.key;
+	if(act)
+	{
+		// exactly the arithmetic of a queued leaf entry (queue_hit_point + the shade-only branch of shade_expand_kernel)
+		const float4 g	= B[sv.off_geom + sidx];
+		const float3 d	= f3(s0);
+		const float t	= sphere_t_ref(po, d, f3(g), B[sv.off_spec + sidx].w, s0.w);
+		const float3 hp = add_rn(po, muls_rn(d, t));
+		const float3 n	= normalize_rn(sub_rn(hp, f3(g)));
+		const float3 kd = f3(B[sv.off_diff + sidx]);
+		const float3 direct	 = direct_light<STATS, FOG, false>(B, sv, fp.shadows != 0, r2, sidx, hp, n, cnt);
+		const float3 contrib = f3(s1) * kd * (direct * 0.318309886183790672f);
+		unsigned fl			 = 0;
+		const long long x = to_fixed(contrib.x, fl, 0), y = to_fixed(contrib.y, fl, 1), z = to_fixed(contrib.z, fl, 2);
+		unsigned long long *a = ls.acc + 4 * src;
+		atomicAdd(a + 0, (unsigned long long) x);
+		atomicAdd(a + 1, (unsigned long long) y);
+		atomicAdd(a + 2, (unsigned long long) z);
+		if(fl)
+		{
+			atomicOr(a + 3, (unsigned long long) fl);
+		}
+	}
+}
+
+// shade whole rounds of 32 while that many are pending; keep the rest at the front of the ring
+template <bool STATS, bool FOG>
+SKR_DEV void leaf_drain(const float4 *__restrict__ B, const SceneView &sv, const FrameParams &fp, LeafStage &ls, float3 o, const RngCtx &rng, Counters &cnt,
+						bool flush)
+{
+	__syncwarp();
+	const unsigned whole = ls.pending & ~31u;
+	for(unsigned first = 0; first < whole; first += 32)
+	{
+		leaf_shade_round<STATS, FOG>(B, sv, fp, ls, first, 32u, o, rng, cnt);
+	}
+	const unsigned left = ls.pending - whole;
+	if(flush)
+	{
+		if(left)
+		{
+			leaf_shade_round<STATS, FOG>(B, sv, fp, ls, whole, left, o, rng, cnt);
+		}
+		ls.pending = 0;
+		__syncwarp();
+		return;
+	}
+	if(whole && left)
+	{
+		const unsigned lane = threadIdx.x & 31u;
+		float4 a = make_float4(0, 0, 0, 0), b = a;
+		if(lane < left)
+		{
+			a = ls.slot[2 * (whole + lane)];
+			b = ls.slot[2 * (whole + lane) + 1];
+		}
+		__syncwarp();
+		if(lane < left)
+		{
+			ls.slot[2 * lane]	  = a;
+			ls.slot[2 * lane + 1] = b;
+		}
+	}
+	ls.pending = left;
+	__syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
 // shade_expand_kernel: queue entries [start, start + count) of `in`
 // ------------------------------------------------------------------------------------------------
-template <bool STATS, bool SMEM, bool TRIS, bool FOG>
+// LEAF: the children are leaves of the tree (depth 1) and are shaded in place, see above; `out` is unused.
+template <bool STATS, bool SMEM, bool TRIS, bool FOG, bool LEAF>
 __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
 																  const Queue out, int expand)
 {
@@ -424,6 +591,18 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 	const float4 *B = stage_scene<SMEM>(sv, smem);
 	Counters cnt;
 	zero(cnt);
+	LeafStage ls;
+	if constexpr(LEAF)
+	{
+		char *base = reinterpret_cast<char *>(smem) + (SMEM ? (size_t) sv.blob_f4 * sizeof(float4) : 0) + (threadIdx.x >> 5) * SKR_LEAF_WARP_BYTES;
+		ls.slot	   = reinterpret_cast<float4 *>(base);
+		ls.acc	   = reinterpret_cast<unsigned long long *>(base + SKR_LEAF_SLOTS * 32);
+		ls.pending = 0;
+		const unsigned lane = threadIdx.x & 31u;
+		reinterpret_cast<ulonglong2 *>(ls.acc + 4 * lane)[0] = make_ulonglong2(0ull, 0ull);
+		reinterpret_cast<ulonglong2 *>(ls.acc + 4 * lane)[1] = make_ulonglong2(0ull, 0ull);
+		__syncwarp();
+	}
 
 	const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool valid = g < count;
@@ -504,16 +683,39 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 				m[k] = __ballot_sync(0xffffffffu, h[k] >= 0);
 				total += (unsigned) __popc(m[k]);
 			}
-			unsigned at = queue_reserve(out, total);
-#pragma unroll
-			for(int k = 0; k < SKR_GI_BATCH; k++)
+			if constexpr(LEAF)
 			{
-				if(h[k] >= 0)
+				unsigned at = ls.pending;
+#pragma unroll
+				for(int k = 0; k < SKR_GI_BATCH; k++)
 				{
-					queue_store(out, at + __popc(m[k] & ((1u << (threadIdx.x & 31)) - 1u)), o, rng.pixel, w[k], rng.node * fp.node_base + (uint32_t) (c + k) + 1u,
-								rng.sample, h[k], d[k], t[k], fp.err);
+					if(h[k] >= 0)
+					{
+						const unsigned idx	 = at + __popc(m[k] & ((1u << (threadIdx.x & 31)) - 1u));
+						ls.slot[2 * idx]	 = make_float4(d[k].x, d[k].y, d[k].z, t[k]);
+						ls.slot[2 * idx + 1] = make_float4(w[k].x, w[k].y, w[k].z, u2f((uint32_t) h[k] | ((threadIdx.x & 31u) << 16) | ((uint32_t) (c + k) << 21)));
+					}
+					at += (unsigned) __popc(m[k]);
 				}
-				at += (unsigned) __popc(m[k]);
+				ls.pending = at;
+				if(at >= 32u)
+				{
+					leaf_drain<STATS, FOG>(B, sv, fp, ls, o, rng, cnt, false);
+				}
+			}
+			else
+			{
+				unsigned at = queue_reserve(out, total);
+#pragma unroll
+				for(int k = 0; k < SKR_GI_BATCH; k++)
+				{
+					if(h[k] >= 0)
+					{
+						queue_store(out, at + __popc(m[k] & ((1u << (threadIdx.x & 31)) - 1u)), o, rng.pixel, w[k], rng.node * fp.node_base + (uint32_t) (c + k) + 1u,
+									rng.sample, h[k], d[k], t[k], fp.err);
+					}
+					at += (unsigned) __popc(m[k]);
+				}
 			}
 		}
 		uint4 r = make_uint4(0u, 0u, 0u, 0u);
@@ -533,16 +735,44 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 			}
 			float3 w;
 			finish(r1, h, w);
-			queue_push(out, h >= 0, o, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, t, fp.err);
+			if constexpr(LEAF)
+			{
+				const unsigned m = __ballot_sync(0xffffffffu, h >= 0);
+				if(h >= 0)
+				{
+					const unsigned idx	 = ls.pending + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+					ls.slot[2 * idx]	 = make_float4(d.x, d.y, d.z, t);
+					ls.slot[2 * idx + 1] = make_float4(w.x, w.y, w.z, u2f((uint32_t) h | ((threadIdx.x & 31u) << 16) | ((uint32_t) c << 21)));
+				}
+				ls.pending += (unsigned) __popc(m);
+				if(ls.pending >= 32u)
+				{
+					leaf_drain<STATS, FOG>(B, sv, fp, ls, o, rng, cnt, false);
+				}
+			}
+			else
+			{
+				queue_push(out, h >= 0, o, rng.pixel, w, rng.node * fp.node_base + (uint32_t) c + 1u, rng.sample, h, d, t, fp.err);
+			}
+		}
+		if constexpr(LEAF)
+		{
+			leaf_drain<STATS, FOG>(B, sv, fp, ls, o, rng, cnt, true);
 		}
 	}
 	if(valid)
 	{
 		const int x = (int) (rng.pixel % (uint32_t) fp.width), y = (int) (rng.pixel / (uint32_t) fp.width);
 		const long long lp = encode_pixel(fp, x, y);
-		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 0), (unsigned long long) to_fixed(contrib.x));
-		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 1), (unsigned long long) to_fixed(contrib.y));
-		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 2), (unsigned long long) to_fixed(contrib.z));
+		if constexpr(LEAF)
+		{
+			const unsigned long long *a = ls.acc + 4 * (threadIdx.x & 31u);
+			accum_add(fp.accum, lp, contrib, (long long) a[0], (long long) a[1], (long long) a[2], (unsigned) a[3]);
+		}
+		else
+		{
+			accum_add(fp.accum, lp, contrib);
+		}
 	}
 	flush_counters<STATS>(fp, cnt);
 }
@@ -646,9 +876,7 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 	{
 		const int x = (int) (pixel % (uint32_t) fp.width), y = (int) (pixel / (uint32_t) fp.width);
 		const long long lp = encode_pixel(fp, x, y);
-		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 0), (unsigned long long) to_fixed(contrib.x));
-		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 1), (unsigned long long) to_fixed(contrib.y));
-		atomicAdd(reinterpret_cast<unsigned long long *>(fp.accum + 3 * lp + 2), (unsigned long long) to_fixed(contrib.z));
+		accum_add(fp.accum, lp, contrib);
 	}
 	flush_counters<STATS>(fp, cnt);
 }
@@ -666,11 +894,7 @@ __global__ void __launch_bounds__(SKR_BLOCK) resolve_kernel(const FrameParams fp
 	{
 		return;
 	}
-	float3 c = f3(from_fixed(fp.accum[3 * lp + 0]), from_fixed(fp.accum[3 * lp + 1]), from_fixed(fp.accum[3 * lp + 2]));
-	// to_fixed() parks NaN contributions at +1e9 (far above any radiance sum); hand them back as NaN
-	c.x = c.x > 4.0e8f ? CUDART_NAN_F : c.x;
-	c.y = c.y > 4.0e8f ? CUDART_NAN_F : c.y;
-	c.z = c.z > 4.0e8f ? CUDART_NAN_F : c.z;
+	float3 c = accum_load(fp.accum, lp);
 	if(fp.grid > 0)
 	{
 		const float n2 = (float) fp.spp;

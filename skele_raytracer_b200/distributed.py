@@ -22,17 +22,23 @@ def render_frame_distributed(renderer, option, rank: int, world: int, device=Non
     opt = dataclasses.replace(option, rank=rank, world=world)
     nbytes = renderer.tiles_bytes(opt)
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    local = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(nbytes * world, dtype=torch.uint8, device=dev)
-    frame = torch.empty((opt.height, opt.width, 3), dtype=torch.uint8, device=dev)
-    st = renderer.render_tiles_device(opt, local.data_ptr())  # returns after the library's stream has drained
-    if world > 1:
-        dist.all_gather_into_tensor(gathered, local)
-        torch.cuda.current_stream().synchronize()
-    else:
-        gathered = local
-    renderer.deinterleave_device(opt, gathered.data_ptr(), frame.data_ptr())
-    renderer.sync()
+    # everything -- allocations included -- happens on the LIBRARY's stream, so that torch's caching allocator and NCCL
+    # order the buffers against the kernels that use them; the caller's stream then waits for the finished frame
+    caller = torch.cuda.current_stream(dev)
+    lib = torch.cuda.ExternalStream(renderer.stream(), device=dev)
+    lib.wait_stream(caller)
+    with torch.cuda.stream(lib):
+        local = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        gathered = torch.empty(nbytes * world, dtype=torch.uint8, device=dev)
+        frame = torch.empty((opt.height, opt.width, 3), dtype=torch.uint8, device=dev)
+        st = renderer.render_tiles_device(opt, local.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local)
+        else:
+            gathered = local
+        renderer.deinterleave_device(opt, gathered.data_ptr(), frame.data_ptr())
+    caller.wait_stream(lib)
+    frame.record_stream(caller)
     return frame, st
 
 
@@ -73,14 +79,28 @@ class PeerFrames:
         except Exception:  # no P2P / symmetric memory in this environment
             return None
 
-    def render(self, renderer, option, rank: int, world: int, want_stats: bool = False):
-        """Enqueue one frame; returns (frame tensor view HxWx3 that is whole once the current stream reaches this point,
-        Stats or None)."""
+    def render(self, renderer, option, rank: int, world: int, want_stats: bool = False, targets=None):
+        """Enqueue one frame; returns (frame tensor view HxWx3, Stats or None).
+
+        Stream contract: the render kernel runs on the LIBRARY's stream (renderer.stream()), and so does the
+        symmetric-memory barrier that ends the frame -- this method enters that stream itself.  The caller's current
+        stream is made to wait for the barrier, so work the caller enqueues next sees a whole frame; nothing here blocks
+        the host.  `targets`: ranks whose frames are filled (default: all; e.g. [0] when only rank 0 reads the frame)."""
         import dataclasses
+
+        import torch
 
         k = self.i & 1
         self.i += 1
         opt = dataclasses.replace(option, rank=rank, world=world)
-        st = renderer.render_peers_device(opt, self.hdls[k].buffer_ptrs, want_stats=want_stats)
-        self.hdls[k].barrier()
+        ptrs = list(self.hdls[k].buffer_ptrs)
+        if targets is not None:
+            ptrs = [ptrs[t] for t in targets]
+        caller = torch.cuda.current_stream()
+        lib = torch.cuda.ExternalStream(renderer.stream(), device=self.bufs[k].device)
+        lib.wait_stream(caller)  # the previous reader of this buffer (on the caller's stream) is done before it is overwritten
+        with torch.cuda.stream(lib):
+            st = renderer.render_peers_device(opt, ptrs, want_stats=want_stats)
+            self.hdls[k].barrier()
+        caller.wait_stream(lib)
         return self.bufs[k].view(option.height, option.width, 3), st

@@ -348,7 +348,15 @@ def test_gi_energy_bookkeeping_matches_ray_counts(gpu, gscenes):
     w, h, n, depth = 320, 180, 8, 3
     st = gpu.render(S.Options(width=w, height=h, max_depth=depth, monte_carlo=True, num_path_traces=n, collect_stats=True, seed=4),
                     want_rgb8=False, want_rgb32=False)[2]
-    assert st.queue_entries == st.sphere_hits
+    # depth-1 hits (the leaves) are shaded in place by the warp that found them, never queued
+    assert 0 < st.queue_entries < st.sphere_hits
+    os.environ["SKR_NO_LEAF_INLINE"] = "1"
+    try:
+        st2 = gpu.render(S.Options(width=w, height=h, max_depth=depth, monte_carlo=True, num_path_traces=n, collect_stats=True, seed=4),
+                         want_rgb8=False, want_rgb32=False)[2]
+    finally:
+        del os.environ["SKR_NO_LEAF_INLINE"]
+    assert st2.queue_entries == st2.sphere_hits == st.sphere_hits
     # hits at depth >= 2 expand into n children each; depth-1 hits do not.  With depth 3: levels 0 and 1 expand.
     assert (st.closest_hit_rays - w * h) % n == 0
 
@@ -524,6 +532,117 @@ def test_render_device_matches_host_render(gpu, gscenes):
     d32 = torch.zeros((180, 320, 3), dtype=torch.float32, device="cuda")
     gpu.render_device(o, d8.data_ptr(), d32.data_ptr())
     assert np.array_equal(d8.cpu().numpy(), h8) and np.array_equal(d32.cpu().numpy(), h32)
+
+
+
+# ---- leaves shaded in place == leaves through the queue, bit for bit -------------------------------
+
+LEAF_CASES = [("spheres2", dict(width=160, height=90, max_depth=4, monte_carlo=True, num_path_traces=16, seed=41)),             # config 3 shape (fog)
+              ("bear", dict(width=96, height=54, monte_carlo=True, num_path_traces=64, grid_size=2, use_shadows=True, seed=42)),  # config 5 shape
+              ("spheres1", dict(width=128, height=72, max_depth=2, monte_carlo=True, num_path_traces=7, use_shadows=True, seed=43)),   # odd n: remainder loop
+              ("test", dict(width=96, height=54, max_depth=3, monte_carlo=True, num_path_traces=5, grid_size=2, seed=44)),        # triangles
+              ("spheres2_nofog", dict(width=64, height=36, max_depth=5, monte_carlo=True, num_path_traces=3, use_shadows=True, seed=45)),
+              ("bear", dict(width=33, height=17, max_depth=2, monte_carlo=True, num_path_traces=1, seed=46))]
+
+
+@pytest.mark.parametrize("scene,kw", LEAF_CASES)
+def test_leaves_in_place_equal_leaves_through_the_queue(gpu, gscenes, scene, kw):
+    """shade_expand_kernel<LEAF>: the depth-1 hits are compacted in shared memory and shaded by the warp that found them;
+    frame (float bit patterns) and every device counter must equal the all-queued wavefront (SKR_NO_LEAF_INLINE=1)."""
+    gpu.upload(gscenes[scene])
+    o = S.Options(collect_stats=True, **kw)
+    a32, a8, sa = gpu.render(o)
+    os.environ["SKR_NO_LEAF_INLINE"] = "1"
+    try:
+        b32, b8, sb = gpu.render(o)
+    finally:
+        del os.environ["SKR_NO_LEAF_INLINE"]
+    assert np.array_equal(a32.view(np.uint32), b32.view(np.uint32)) and np.array_equal(a8, b8)
+    for f in ("closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "sphere_hits", "light_evals", "tri_tests"):
+        assert getattr(sa, f) == getattr(sb, f), f
+    assert sa.queue_entries < sb.queue_entries and sa.kernel_launches <= sb.kernel_launches
+
+
+def test_many_spheres_leaves_in_place_on_the_global_memory_path(gpu, port):
+    rng = np.random.default_rng(6)
+    sc = random_scene(rng, nspheres=1200, nplights=2)
+    sc.spheres[:, 3] *= 0.2
+    oo, go = opts(width=48, height=27, max_depth=2, monte_carlo=True, num_path_traces=4, use_shadows=True, seed=3)
+    p32, p8, _, _ = port.render(sc, oo, rng_mode=O.RNG_PHILOX, seed=3)
+    gpu.upload(to_gpu_scene(sc))
+    g32, g8, _ = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, min_ok=0.995, what="1200 spheres, gillum, leaves in place")
+
+
+# ---- hardening ------------------------------------------------------------------------------------
+
+def test_gillum_zero_with_jsample_is_nan_on_every_hit_pixel(gpu, port, scenes, gscenes):
+    """`--gillum 0 --jsample 3`: nine NaN contributions per hit pixel.  Non-finite contributions are kept out of band
+    (a flags word beside the fixed-point sums), so any number of them resolves like the reference's float sum."""
+    oo, go = opts(width=64, height=36, max_depth=2, monte_carlo=True, num_path_traces=0, grid_size=3, seed=7)
+    p32, p8, _, _ = port.render(scenes["spheres1"], oo, rng_mode=O.RNG_PHILOX, seed=7)
+    gpu.upload(gscenes["spheres1"])
+    g32, g8, _ = gpu.render(go)
+    assert np.isnan(p32).any() and np.array_equal(np.isnan(g32), np.isnan(p32))
+    assert np.array_equal(g8, p8) and (g8[np.isnan(g32)] == 255).all()
+
+
+def test_infinite_radiance_saturates_instead_of_wrapping(gpu, gscenes):
+    """Light colours of 1e30: every lit contribution overflows fixed point many times over; the pixel must come out
+    +inf / 255, never a wrapped value."""
+    sc = dataclasses.replace(gscenes["spheres1"])
+    sc.plights = sc.plights.copy()
+    sc.plights[:, 3:6] = 1.0e30
+    gpu.upload(sc)
+    g32, g8, _ = gpu.render(S.Options(width=64, height=36, max_depth=3, monte_carlo=True, num_path_traces=4, grid_size=2, seed=1))
+    d32, d8, _ = gpu.render(S.Options(width=64, height=36, max_depth=1))
+    lit = d32.max(axis=2) > 1.0e20
+    assert lit.mean() > 0.05 and np.isposinf(g32[lit]).any(axis=1).mean() > 0.98 and (g8[lit].max(axis=1) == 255).mean() > 0.98
+    assert not (g32 < 0).any()
+
+
+def test_node_ids_beyond_32_bits_are_rejected(gpu, gscenes):
+    gpu.upload(gscenes["spheres1"])
+    with pytest.raises(S.SkrError, match="node ids"):
+        gpu.render(S.Options(width=8, height=8, max_depth=8, monte_carlo=True, num_path_traces=64))
+    gpu.render(S.Options(width=8, height=8, max_depth=6, monte_carlo=True, num_path_traces=2))  # 3^5 nodes: fine
+
+
+@pytest.mark.parametrize("kw", [dict(fresnel=True, max_depth=3), dict(monte_carlo=True, num_path_traces=3, max_depth=2, seed=2)])
+def test_blob_between_48_and_64_kb(gpu, port, kw):
+    """About 600 spheres: the scene blob is staged in shared memory but needs the opt-in size attribute on EVERY kernel that
+    stages it (fresnel_expand_kernel included)."""
+    rng = np.random.default_rng(11)
+    sc = random_scene(rng, nspheres=600, nplights=2)
+    sc.spheres[:, 3] *= 0.25
+    oo, go = opts(width=64, height=36, use_shadows=True, **dict(kw))
+    p32, p8, _, _ = port.render(sc, oo, rng_mode=O.RNG_PHILOX, seed=go.seed)
+    gpu.upload(to_gpu_scene(sc))
+    g32, g8, _ = gpu.render(go)
+    assert_image_parity(g32, p32, g8, p8, min_ok=0.995, what=f"600 spheres {kw}")
+
+
+def test_reserve_makes_the_first_frame_cost_what_every_frame_costs():
+    r = S.Renderer()
+    try:
+        r.upload(S.Scene.load(os.path.join(GOLDEN, "scenes", "bear.npz")))
+        o = S.Options(width=64, height=36, max_depth=3, monte_carlo=True, num_path_traces=8, use_shadows=True, seed=5)
+        r.reserve(o)
+        first = r.render(o)[2].ms_total
+        later = min(r.render(o)[2].ms_total for _ in range(3))
+        assert first < 5.0 and first < 20 * later + 1.0, (first, later)
+    finally:
+        r.close()
+
+
+def test_async_frame_errors_surface_at_sync(gpu, gscenes):
+    """Fire-and-forget frames report through the device error word; skr_sync reads it (nothing to report here)."""
+    import torch
+    gpu.upload(gscenes["dragon"])
+    d8 = torch.zeros((90, 160, 3), dtype=torch.uint8, device="cuda")
+    gpu.render_device(S.Options(width=160, height=90), d8.data_ptr(), 0, want_stats=False)
+    gpu.sync()
+    assert d8.any()
 
 
 # ---- error behaviour ------------------------------------------------------------------------------
