@@ -1,30 +1,38 @@
 #!/usr/bin/env python
-"""bench.py -- headline measurement of the per-pixel tracing loop on B200.
+"""bench.py -- measurement of the per-pixel tracing loop on B200: headline line + every BASELINE config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1..c5] [--all-configs]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1..c5] [--only-headline]
 
-A "step" is one frame of the workload.  Default workload = BASELINE.json configs[1]:
-scenes/spheres2.scn 1920x1080 --jsample 5 --shadow (the scene snapshot in tests/golden/scenes, produced by the
-reference's own parser).  Metric: Mrays/s, rays = closest-hit rays (shade() invocations with depth > 0) + distinct
-shadow rays, counted on the device in an untimed pass with the same seed.
+A "step" is one frame of a workload.  Headline workload = BASELINE.json configs[1]: scenes/spheres2.scn 1920x1080
+--jsample 5 --shadow (the scene snapshot in tests/golden/scenes, produced by the reference's own parser).  Metric:
+Mrays/s, rays = closest-hit rays (shade() invocations with depth > 0) + distinct shadow rays, counted on
+the device in an untimed pass with the same seed.
 
   value   : whole-job Mrays/s, scene resident in HBM, frame left in HBM (device time, CUDA events on the library's
             stream, per step, L2 flushed between steps outside the events; max over ranks).
-  e2e     : the same metric through the reference-facing call with HOST buffers: skr_scene_upload (H2D) + skr_render
-            into pinned host memory (D2H) every step, wall clock around the calls.
+  e2e     : the same metric through the reference-facing call with HOST buffers, wall clock: N = 1: skr_scene_upload
+            (H2D) + skr_render into pinned host memory, every step.  N > 1: every rank uploads the scene and renders its
+            tiles with the kernel storing each finished pixel straight into ONE page-locked host frame shared by the
+            ranks (a /dev/shm segment, skr_pin_host), each GPU over its own PCIe link; a barrier ends the step.
   N > 1   : the frame is split into interleaved 32x32 tiles over the ranks (one process per GPU, torchrun); each rank's
-            render kernel stores its finished pixels straight into every rank's frame over NVLink (torch symmetric
-            memory, skr_render_peers_device) and one symmetric-memory barrier ends the frame; where peer mapping is
-            unavailable (or SKR_BENCH_NO_P2P=1): ONE all-gather (NCCL) of the RGB8 tiles + de-interleave kernel.
+            render kernel stores its finished pixels straight into rank 0's frame over NVLink (torch symmetric memory,
+            skr_render_peers_device) and one symmetric-memory barrier ends the frame; where peer mapping is unavailable
+            (or SKR_BENCH_NO_P2P=1): ONE all-gather (NCCL) of the RGB8 tiles + de-interleave kernel.
             Total work is fixed -> "strong".
-  roofline: FP32 CUDA-core pipe (this path has no dense contraction; tensor cores unused; HBM traffic is the
-            framebuffer only).  peak = FMA microbenchmark measured live in this run (MEASURED_PEAKS.json has no FP32).
-            `achieved` = the reference algorithm's arithmetic / kernel time; `executed` = what the kernels really ran
-            (bundle culling proves most sphere tests of a jittered pixel unnecessary and skips them).
-  --impl reference : the reference's own CPU code (oracle/_ref/libskr_ref.so, compiled from the reference's sources;
-            else the C port) with all host threads on a bounded row window of the same frame.
+  configs : the same measurement (device time, e2e, roofline, CPU baseline) for EVERY BASELINE.json config c1..c5, at
+            every N; the headline workload's entry repeats the top-level figures.
+  roofline: sphere scenes: FP32 CUDA-core pipe (no dense contraction on this path; tensor cores unused; HBM traffic is
+            the framebuffer only), peak = FMA microbenchmark measured live in this run.  `achieved` / `frac` = the
+            arithmetic the kernels EXECUTED; `algorithmic` = the reference algorithm's count (every sphere per query),
+            which conservative bundle culling proves partly unnecessary.  Triangle scene (c4): the BVH / primitive
+            fetch goes through L1 -> bound "l1", bytes = 64 B per node visit + 48 B per leaf test, against L1 / L2 /
+            shared-memory read bandwidths measured live (skr_measure_bandwidth) and the HBM figure of MEASURED_PEAKS.json.
+  cpu_baseline: the reference's own code (oracle/_ref, compiled from /root/reference/src) on the host cores, on a bounded
+            row window of the same frame: the -O2 build and the reference's own flags (-g, no -O: src/Makefile:2).
+  --impl reference : that CPU code as the timed arm (all host threads), same config / metric / unit.
 """
 import argparse
+import dataclasses
 import json
 import os
 import statistics
@@ -47,19 +55,31 @@ WORKLOADS = {
     "c5": ("bear", dict(width=3840, height=2160, monte_carlo=True, num_path_traces=64, grid_size=4, use_shadows=True),
            "scenes/bear.scn 3840x2160 --gillum 64 --jsample 4 --shadow"),
 }
+MAX_STEPS = {"c1": 20, "c2": 1000, "c3": 10, "c4": 20, "c5": 3}   # timed steps per config in the `configs` block
+CPU_BUDGET_S = {"c1": 1.0, "c2": 2.0, "c3": 2.0, "c4": 2.0, "c5": 2.0}  # seconds per sample and build; the headline gets 8 s
 SEED = 1
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu capture
-# (bench.py cannot run ncu on itself): profiles/r01_c2_primary_ncu_raw.txt
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu captures
+# (bench.py cannot run ncu on itself)
 NCU_TRAFFIC_BYTES = {"c2": (583680 + 129536, "profiles/r01_c2_primary_ncu_raw.txt"), "c4": (613376 + 1024, "profiles/r01_c4_primary_ncu_raw.txt")}
+STAT_KEYS = ["closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "tri_tests", "bvh_node_visits", "sphere_hits", "light_evals",
+             "sphere_tests_executed"]
 
 
-def algorithmic_flops(st, primary_samples):
-    """SURVEY 8(d) per-unit figures x the device counters of one frame (FMA = 2, everything else = 1)."""
-    return (25.0 * st["sphere_tests"] + 8.0 * st["sphere_tests_pos"] + 18.0 * st["sphere_hits"]  # F_ch(S) = 25 S + 8 h + 18 [hit]
-            + 15.0 * st["shadow_rays"]                                                           # shadow ray set-up (tests counted above at 25/33)
-            + 33.0 * st["sphere_hits"] + 89.0 * st["light_evals"]                                # direct shading 33 + 89 L
-            + 24.0 * st["bvh_node_visits"] + 35.0 * st["tri_tests"]                              # line-slab test / triangle test
-            + 20.0 * primary_samples)                                                            # ray generation
+def algorithmic_flops(st, primary_samples, executed=False):
+    """SURVEY 8(d) per-unit figures x the device counters of one frame (FMA = 2, everything else = 1).
+    executed=True: sphere tests the kernels really ran (bundle culling) instead of the reference algorithm's count."""
+    tests = st["sphere_tests_executed"] if executed else st["sphere_tests"]
+    return (25.0 * tests + 8.0 * st["sphere_tests_pos"] + 18.0 * st["sphere_hits"]   # F_ch(S) = 25 S + 8 h + 18 [hit]
+            + 15.0 * st["shadow_rays"]                                               # shadow ray set-up (tests counted above at 25/33)
+            + 33.0 * st["sphere_hits"] + 89.0 * st["light_evals"]                    # direct shading 33 + 89 L
+            + 24.0 * st["bvh_node_visits"] + 35.0 * st["tri_tests"]                  # line-slab test / triangle test
+            + 20.0 * primary_samples)                                                # ray generation
+
+
+def fetch_bytes(st):
+    """Bytes the triangle path pulls through L1 per frame: one 64 B node (both child boxes) per node visit, 48 B of
+    vertices per leaf test (SURVEY 8d states 32 B per child box)."""
+    return 64.0 * st["bvh_node_visits"] + 48.0 * st["tri_tests"]
 
 
 class ClockSampler:
@@ -105,52 +125,74 @@ class ClockSampler:
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p)), "measured"
-    return {"hbm_gbs": 6650.0}, "fallback"
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------
 
-def cpu_reference_run(workload, budget_s, steps, warmup, force_port=False):
-    """Times `steps` (+ `warmup`) bounded samples of the workload on the host cores.  Each sample is a window of rows
-    of the same frame, sized so that one sample takes about budget_s.  -> dict(value Mrays/s, kind, cores, sample,
-    ms_per_step)."""
+def cpu_reference_run(workload, budget_s, steps, warmup, force_port=False, unoptimised=False):
+    """Times `steps` (+ `warmup`) bounded samples of the workload on the host cores.  A sample is the SAME frame -- same
+    scene, camera, aspect and flags -- at 1/k^2 of the pixels (k = 1: the full frame), k chosen from a probe so that one
+    sample takes about budget_s; rays per pixel do not depend on the resolution, so the rate (Mrays/s) is the full
+    frame's.  -> dict(value Mrays/s, kind, cores, sample, ms_per_step, frame_s_extrapolated)."""
     from oracle import oracle_lib as O
 
     scene_name, kw, desc = WORKLOADS[workload]
     sc = O.Scene.load(os.path.join(GOLD, scene_name + ".npz"))
-    opt = O.Options(**kw)
+    full = O.Options(**kw)
     port = O.Port()
     use_ref = O.ref_available() and not force_port
-    ref = O.Ref() if use_ref else None
+    if unoptimised and not (use_ref and os.path.exists(O.REF_O0_SO)):
+        return None
+    ref = O.Ref(unoptimised=unoptimised) if use_ref else None
     cores = ref.max_threads() if use_ref else port.max_threads()
-    h = opt.height
 
-    def run(y0, y1):
+    def at_scale(k):
+        return dataclasses.replace(full, width=max(1, full.width // k), height=max(1, full.height // k))
+
+    def run(opt):
         if use_ref:
-            return ref.render(sc, opt, seed=SEED, threads=cores, y0=y0, y1=y1)[2]
-        return port.render(sc, opt, rng_mode=O.RNG_PHILOX, seed=SEED, threads=cores, y0=y0, y1=y1, want_rgb8=False)[3]
+            return ref.render(sc, opt, seed=SEED, threads=cores)[2]
+        return port.render(sc, opt, rng_mode=O.RNG_PHILOX, seed=SEED, threads=cores, want_rgb8=False)[3]
 
-    mid = h // 2
-    probe_rows = max(1, min(4, h))
-    t = run(mid, mid + probe_rows)
-    rows = int(max(1, min(h, probe_rows * budget_s / max(t, 1e-4))))
-    y0 = max(0, mid - rows // 2)
-    y1 = min(h, y0 + rows)
-    # rays in the window: counted by the port on the same window (same algorithm; keyed RNG)
-    st = port.render(sc, opt, rng_mode=O.RNG_PHILOX, seed=SEED, y0=y0, y1=y1, want_rgb8=False)[2]
+    # two probes: a tiny frame (config 5 costs ~10 ms of CPU per PIXEL), then one sized for ~1/8 of the budget
+    probe = at_scale(160)                                    # 12x6 for 1080p, 24x13 for 4K
+    t_px = max(run(probe), 1e-5) / (probe.width * probe.height)
+    k = 1
+    while k < 160 and (full.width // k) * (full.height // k) * t_px > budget_s / 8:
+        k += 1
+    if k < 160:
+        probe = at_scale(k)
+        t_px = max(run(probe), 1e-5) / (probe.width * probe.height)
+    k = 1
+    while k < 160 and (full.width // k) * (full.height // k) * t_px > budget_s:
+        k += 1
+    opt = at_scale(k)
+    for _ in range(3):                                       # a sample far below the budget (probe noise): grow it
+        t = run(opt)
+        if k == 1 or t > budget_s / 3:
+            break
+        k = max(1, min(k - 1, int(k * (max(t, 1e-4) / budget_s) ** 0.5)))
+        opt = at_scale(k)
+    # rays of the sample: counted by the port on the same frame (same algorithm; keyed RNG)
+    st = port.render(sc, opt, rng_mode=O.RNG_PHILOX, seed=SEED, want_rgb8=False)[2]
     rays = st["closest_hit_rays"] + st["shadow_rays"]
     for _ in range(warmup):
-        run(y0, y1)
-    times = [run(y0, y1) for _ in range(steps)]
+        run(opt)
+    times = [run(opt) for _ in range(steps)]
     tot = sum(times)
+    build = ("reference's own src/ compiled -O2 -fopenmp (oracle/_ref), OMP threads share rand()" if use_ref and not unoptimised else
+             "reference's own src/ compiled with ITS flags (-g, no -O, src/Makefile:2) -fopenmp (oracle/_ref)" if use_ref else
+             "C port oracle/skr_oracle.c -O2 -fopenmp")
+    frac = (opt.width * opt.height) / float(full.width * full.height)
     return {"value": rays * steps / tot / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference" if use_ref else "port",
-            "sample": f"rows [{y0},{y1}) of the {opt.width}x{opt.height} frame of {desc}: {rays} rays per sample, {steps} timed samples, "
-                      f"render loop only (no parse, no PPM write); " + ("reference's own src/ compiled -O2 -fopenmp (oracle/_ref), OMP threads share rand()"
-                                                                       if use_ref else "C port oracle/skr_oracle.c -O2 -fopenmp"),
-            "ms_per_step": tot / steps * 1e3, "rays_per_sample": rays}
+            "sample": f"the frame of {desc} at {opt.width}x{opt.height} ({frac:.4f} of the {full.width}x{full.height} pixels; same scene, camera, aspect and "
+                      f"flags): {rays} rays per sample, {steps} timed samples, render loop only (no parse, no PPM write); " + build,
+            "ms_per_step": tot / steps * 1e3, "rays_per_sample": rays, "sample_size": [opt.width, opt.height],
+            "frame_s_extrapolated": tot / steps / frac}
 
 
 def main_reference(args, rank):
@@ -162,7 +204,8 @@ def main_reference(args, rank):
     scene_name, kw, desc = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": "Mrays/s", "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "scene": scene_name, **kw, "seed": SEED, "note": "each step is a bounded row window of the frame"},
+            "config": {"workload": desc, "scene": scene_name, **kw, "seed": SEED,
+                       "note": f"each step is the same frame at {r['sample_size'][0]}x{r['sample_size'][1]} (bounded sample, see cpu_baseline.sample)"},
             "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
@@ -172,27 +215,78 @@ def main_reference(args, rank):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 
-def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_buf, want_e2e=True):
-    import numpy as np
+class SharedHostFrame:
+    """ONE host frame for all ranks of the box: a /dev/shm segment every rank maps and page-locks (skr_pin_host), so that
+    each rank's render kernel stores its own tiles into it over its own PCIe link."""
 
+    def __init__(self, torch, dist, r, nbytes, rank, world):
+        import mmap
+
+        self.r, self.rank = r, rank
+        name = [f"/dev/shm/skr_bench_{os.getpid()}_{nbytes}" if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        self.path = name[0]
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        if world > 1:
+            dist.barrier()
+        self.f = open(self.path, "r+b")
+        self.mm = mmap.mmap(self.f.fileno(), nbytes)
+        import ctypes
+        import numpy as np
+        self.np = np.frombuffer(self.mm, dtype=np.uint8)
+        self.host_ptr = ctypes.addressof(ctypes.c_char.from_buffer(self.mm))
+        self.dev_ptr, self.registered = r.pin_host(self.host_ptr, nbytes)
+
+    def close(self, dist, world):
+        try:
+            if self.registered:
+                self.r.unpin_host(self.host_ptr)
+        except Exception:
+            pass
+        if world > 1:
+            dist.barrier()
+        self.np = None
+        try:
+            self.mm.close()
+        except BufferError:
+            pass
+        self.f.close()
+        if self.rank == 0:
+            try:
+                os.remove(self.path)
+            except OSError:
+                pass
+
+
+def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_buf, want_e2e=True):
     scene_name, kw, desc = WORKLOADS[workload]
     scene = S.Scene.load(os.path.join(GOLD, scene_name + ".npz"))
     r.upload(scene)
     base = S.Options(seed=SEED, rank=rank, world=world, **kw)
     dev = torch.device("cuda", torch.cuda.current_device())
     ext = torch.cuda.ExternalStream(r.stream(), device=dev)
+    t_first0 = time.time()
+    r.reserve(base)   # queue arena / accumulators / kernels loaded ahead of the first frame
+    reserve_ms = (time.time() - t_first0) * 1e3
 
     # untimed counting pass (same seed -> same rays)
-    import dataclasses
-    cst = r.render_device(dataclasses.replace(base, collect_stats=True), 0, 0).as_dict() if world == 1 else None
-    if world > 1:
-        tiles = torch.empty(r.tiles_bytes(base), dtype=torch.uint8, device=dev)
-        cst = r.render_tiles_device(dataclasses.replace(base, collect_stats=True), tiles.data_ptr()).as_dict()
-        keys = ["closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "tri_tests", "bvh_node_visits", "sphere_hits", "light_evals", "sphere_tests_executed"]
+    if world == 1:
+        first = r.render_device(dataclasses.replace(base, collect_stats=True), 0, 0)
+        cst = first.as_dict()
         cst_local = dict(cst)
-        t = torch.tensor([float(cst[k]) for k in keys], dtype=torch.float64, device=dev)
+        peer_frames = None
+        tiles = gathered = None
+    else:
+        tiles = torch.empty(r.tiles_bytes(base), dtype=torch.uint8, device=dev)
+        first = r.render_tiles_device(dataclasses.replace(base, collect_stats=True), tiles.data_ptr())
+        cst = first.as_dict()
+        cst_local = dict(cst)
+        t = torch.tensor([float(cst[k]) for k in STAT_KEYS], dtype=torch.float64, device=dev)
         dist.all_reduce(t)
-        for k, v in zip(keys, t.tolist()):
+        for k, v in zip(STAT_KEYS, t.tolist()):
             cst[k] = int(v)
         gathered = torch.empty(tiles.numel() * world, dtype=torch.uint8, device=dev)
         from skele_raytracer_b200.distributed import PeerFrames
@@ -201,9 +295,6 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank takes the same path
         if int(ok.item()) == 0:
             peer_frames = None
-    else:
-        cst_local = dict(cst)
-        peer_frames = None
     frame = torch.empty((base.height, base.width, 3), dtype=torch.uint8, device=dev)
     rays = cst["closest_hit_rays"] + cst["shadow_rays"]
 
@@ -216,8 +307,8 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         if world == 1:
             return r.render_device(base, frame.data_ptr(), 0, want_stats=ws)
         if peer_frames is not None:
-            # collective-free: P2P stores of the finished pixels into every rank's frame + symmetric-memory barrier
-            step.frame, st = peer_frames.render(r, base, rank, world, want_stats=ws)
+            # collective-free: P2P stores of the finished pixels into rank 0's frame + symmetric-memory barrier
+            step.frame, st = peer_frames.render(r, base, rank, world, want_stats=ws, targets=[0])
             return st
         st = r.render_tiles_device(base, tiles.data_ptr(), want_stats=ws)
         dist.all_gather_into_tensor(gathered, tiles)
@@ -263,53 +354,110 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
-    out = {"desc": desc, "scene": scene_name, "kw": kw, "rays": rays, "p2p": world > 1 and peer_frames is not None, "ms_per_step": dev_ms / steps, "value": rays / (dev_ms / steps) / 1e3,
+    out = {"workload": workload, "desc": desc, "scene": scene_name, "kw": kw, "rays": rays, "p2p": world > 1 and peer_frames is not None,
+           "ms_per_step": dev_ms / steps, "value": rays / (dev_ms / steps) / 1e3, "steps": steps, "warmup": warmup,
            "ms_per_step_min": min(per_step), "ms_per_step_median": sorted(per_step)[len(per_step) // 2],
            "wall_ms_per_step": (t_end - t_begin) * 1e3 / steps, "launches": launches, "stats": cst, "stats_rank0": cst_local, "t_begin": t_begin, "t_end": t_end,
            "kernel_ms_per_step": {k: v / steps for k, v in kernel_ms.items()},
+           "first_frame_ms": first.ms_total, "reserve_ms": reserve_ms,
            "primary_samples": base.width * base.height * (base.grid_size ** 2 if base.grid_size else 1)}
 
     if want_e2e:
-        # end to end through the reference-facing call: host scene arrays -> skr_scene_upload, skr_render -> pinned host RGB8
-        host = torch.empty((base.height, base.width, 3), dtype=torch.uint8).pin_memory().numpy()
         sc_bytes = sum(getattr(scene, f).nbytes for f in ("spheres", "tris", "plights", "dlights", "fogs", "camera", "ambient", "background"))
-        opt1 = dataclasses.replace(base, rank=0, world=1)
         n_e2e = max(3, min(steps, 20))
-        for _ in range(2):
-            r.upload(scene)
-            r.render(opt1, rgb8=host, want_rgb32=False)
-        t0 = time.time()
-        for _ in range(n_e2e):
-            r.upload(scene)
-            r.render(opt1, rgb8=host, want_rgb32=False)
-        t1 = time.time()
-        full_rays = rays if world == 1 else None
-        if world > 1:
-            # e2e at N > 1: every rank uploads, renders its tiles, gathers; rank 0 copies the frame to pinned host memory
+        nbytes = base.height * base.width * 3
+        if world == 1:
+            # end to end through the reference-facing call: host scene arrays -> skr_scene_upload, skr_render -> pinned host RGB8
+            host = torch.empty((base.height, base.width, 3), dtype=torch.uint8).pin_memory().numpy()
+            opt1 = dataclasses.replace(base, rank=0, world=1)
+            for _ in range(2):
+                r.upload(scene)
+                r.render(opt1, rgb8=host, want_rgb32=False)
+            t0 = time.time()
+            for _ in range(n_e2e):
+                r.upload(scene)
+                r.render(opt1, rgb8=host, want_rgb32=False)
+            t1 = time.time()
+            path = "skr_scene_upload + skr_render (host arrays in, pinned host RGB8 out), wall clock"
+        else:
+            # every rank: upload + render its tiles with the kernel storing straight into the shared page-locked host frame
+            # (its own PCIe link) + stream sync; a barrier over the ranks ends the step
+            shf = SharedHostFrame(torch, dist, r, nbytes, rank, world)
+
             def e2e_step():
                 r.upload(scene)
-                step()
-                if rank == 0:
-                    torch.from_numpy(host).copy_(getattr(step, "frame", frame), non_blocking=False)
-            with torch.cuda.stream(ext):
+                st = r.render_peers_device(base, [shf.dev_ptr], want_stats=tree)
+                r.sync()
+                dist.barrier()
+                return st
+
+            e2e_step()
+            e2e_step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.time()
+            for _ in range(n_e2e):
                 e2e_step()
-                torch.cuda.synchronize()
-                dist.barrier()
-                t0 = time.time()
-                for _ in range(n_e2e):
-                    e2e_step()
-                torch.cuda.synchronize()
-                dist.barrier()
-                t1 = time.time()
+            t1 = time.time()
             t = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t1 = t0 + float(t.item())
-            full_rays = rays
-        out["e2e"] = {"value": full_rays * n_e2e / (t1 - t0) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(sc_bytes) * (world if world > 1 else 1),
-                      "d2h_bytes_per_step": int(host.nbytes), "ms_per_step": (t1 - t0) * 1e3 / n_e2e, "steps": n_e2e,
-                      "path": "skr_scene_upload + skr_render (host arrays in, pinned host RGB8 out), wall clock"
-                      if world == 1 else "per rank skr_scene_upload + frame split (same exchange as `value`), D2H of the frame on rank 0; wall clock, max over ranks"}
+            out["e2e_frame_nonzero"] = bool(shf.np.any()) if rank == 0 else None
+            shf.close(dist, world)
+            path = ("per rank skr_scene_upload + skr_render_peers_device into ONE page-locked host frame shared by the ranks (each GPU stores its "
+                    "tiles over its own PCIe link), stream sync + barrier per step; wall clock, max over ranks")
+        out["e2e"] = {"value": rays * n_e2e / (t1 - t0) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(sc_bytes) * world,
+                      "d2h_bytes_per_step": int(nbytes), "ms_per_step": (t1 - t0) * 1e3 / n_e2e, "steps": n_e2e, "path": path}
     return out
+
+
+def roofline_of(m, world, peaks, peaks_src, fp32_peak, bw):
+    """Roofline of the dominant kernel AS LAUNCHED ON RANK 0: its own share of the frame's work / its own duration."""
+    st0 = m["stats_rank0"]
+    kw = m["kw"]
+    dom = "bounce" if kw.get("monte_carlo") else "primary"
+    dom_ms = m["kernel_ms_per_step"][dom] or m["ms_per_step"]
+    dom_launches = 1 if dom == "primary" else max(1, round(m["launches"] / m["steps"]) - 2)
+    frame_bytes = kw["width"] * kw["height"] * 3
+    hbm = {"algorithmic_bytes_per_frame": frame_bytes, "achieved_gbs": frame_bytes / (m["ms_per_step"] * 1e-3) / 1e9,
+           "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src}
+    traffic = NCU_TRAFFIC_BYTES.get(m["workload"], (None, None)) if world == 1 else (None, None)
+    if st0["sphere_tests"] == 0 and st0["bvh_node_visits"] > 0:
+        # triangle scene: memory hierarchy (the whole BVH is cache resident; the fetch goes through L1)
+        b = fetch_bytes(st0)
+        gbs = b / (dom_ms * 1e-3) / 1e9
+        fl = algorithmic_flops(st0, m["primary_samples"] / world)
+        return {"bound": "l1", "achieved": gbs, "peak": bw["l1_gbs"], "unit": "GB/s", "frac": gbs / bw["l1_gbs"] if bw["l1_gbs"] > 0 else None,
+                "traffic": traffic[0], "traffic_source": traffic[1], "kernel": "primary_kernel (BVH line any-hit)", "kernel_ms_per_frame": dom_ms,
+                "kernel_launches_per_frame": dom_launches, "bytes_per_frame_algorithmic_this_rank": b,
+                "bytes_per_unit": "64 B per BVH node visit (both child boxes) + 48 B per triangle leaf test",
+                "levels": {"l1": {"achieved_gbs": gbs, "peak_gbs": bw["l1_gbs"]}, "l2": {"peak_gbs": bw["l2_gbs"]}, "shared": {"peak_gbs": bw["lds_gbs"]}, "hbm": hbm},
+                "fp32": {"tflops": fl / (dom_ms * 1e-3) / 1e12, "frac": fl / (dom_ms * 1e-3) / 1e12 / fp32_peak},
+                "peak_source": "ld.global.ca microbenchmark measured live in this run (skr_measure_bandwidth level 1)",
+                "note": "latency / divergence bound traversal: the 1.1 MB hierarchy is L1/L2 resident, HBM traffic is the frame"}
+    flops_alg = algorithmic_flops(st0, m["primary_samples"] / world)
+    flops_exec = algorithmic_flops(st0, m["primary_samples"] / world, executed=True)
+    achieved = flops_exec / (dom_ms * 1e-3) / 1e12
+    alg = flops_alg / (dom_ms * 1e-3) / 1e12
+    return {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+            "traffic": traffic[0], "traffic_source": traffic[1], "kernel": "primary_kernel" if dom == "primary" else "shade_expand_kernel",
+            "kernel_ms_per_frame": dom_ms, "kernel_launches_per_frame": dom_launches, "flops_per_frame_executed_this_rank": flops_exec,
+            "algorithmic": {"tflops": alg, "frac": alg / fp32_peak, "flops_per_frame_this_rank": flops_alg,
+                            "sphere_tests_algorithmic": st0["sphere_tests"], "sphere_tests_executed": st0["sphere_tests_executed"],
+                            "note": "the reference algorithm's arithmetic (every sphere per query); conservative bundle culling skips tests that "
+                                    "provably fail, so `achieved` counts only what the FP32 pipe executed"},
+            "peak_source": "FFMA microbenchmark measured live in this run (skr_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
+            "note": "compute-bound FP32 CUDA-core path (no dense contraction -> tensor cores unused); algorithmic HBM traffic is the RGB8 frame only",
+            "hbm": hbm}
+
+
+def frame_split_text(m, world):
+    if world == 1:
+        return "single GPU, whole frame"
+    if m["p2p"]:
+        return (f"{world} ranks, interleaved 32x32 tiles; finished pixels stored straight into rank 0's frame over NVLink "
+                "(skr_render_peers_device, torch symmetric memory), one symmetric-memory barrier per frame")
+    return f"{world} ranks, interleaved 32x32 tiles, one NCCL all-gather of RGB8 tiles per frame + de-interleave kernel"
 
 
 def main_gpu(args, rank, world, local_rank):
@@ -331,79 +479,71 @@ def main_gpu(args, rank, world, local_rank):
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
     fp32_peak = r.measure_fp32_peak(4096)
+    bw = {"lds_gbs": r.measure_bandwidth(0), "l1_gbs": r.measure_bandwidth(1), "l2_gbs": r.measure_bandwidth(2)}
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
     m = measure_gpu(S, torch, dist, r, args.workload, steps, warmup, rank, world, flush_buf)
     clocks = sampler.stop(m["t_begin"], m["t_end"])
 
-    others = {}
-    if args.all_configs and world == 1:
+    results = {args.workload: m}
+    if not args.only_headline:
         for w in WORKLOADS:
-            if w == args.workload:
-                continue
-            k = 3 if w == "c5" else 10
-            o = measure_gpu(S, torch, dist, r, w, k, 3, rank, world, flush_buf, want_e2e=False)
-            fl = algorithmic_flops(o["stats"], o["primary_samples"])
-            others[w] = {"workload": o["desc"], "ms_per_frame": o["ms_per_step"], "ms_per_frame_median": o["ms_per_step_median"],
-                         "ms_per_frame_min": o["ms_per_step_min"], "mrays_per_s": o["value"], "rays_per_frame": o["rays"],
-                         "fp32_tflops_algorithmic": fl / (o["ms_per_step"] * 1e-3) / 1e12, "frac_of_fp32_peak": fl / (o["ms_per_step"] * 1e-3) / 1e12 / fp32_peak,
-                         "kernel_launches_per_frame": o["launches"] / k}
+            if w not in results:
+                results[w] = measure_gpu(S, torch, dist, r, w, max(1, min(steps, MAX_STEPS[w])), 3, rank, world, flush_buf)
 
-    cpu = None
+    cpu = {}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(args.workload, 12.0, 1, 0)
+        for w in results:
+            head = w == args.workload
+            o2 = cpu_reference_run(w, 8.0 if head else CPU_BUDGET_S[w], 1, 0)
+            o0 = cpu_reference_run(w, CPU_BUDGET_S[w], 1, 0, unoptimised=True)
+            cpu[w] = (o2, o0)
 
     if rank == 0:
         peaks, peaks_src = load_peaks()
         st = m["stats"]
-        # roofline of the dominant kernel AS LAUNCHED ON RANK 0: its own share of the frame's work / its own duration
-        flops = algorithmic_flops(m["stats_rank0"], m["primary_samples"] / world)
-        # the dominant kernel: primary_kernel without --gillum, shade_expand_kernel with it
-        dom = "bounce" if m["kw"].get("monte_carlo") else "primary"
-        dom_ms = m["kernel_ms_per_step"][dom] or m["ms_per_step"]
-        dom_launches = 1 if dom == "primary" else max(1, round(m["launches"] / steps))
-        achieved = flops / (dom_ms * 1e-3) / 1e12
-        # what the kernels executed: bundle culling proves most sphere tests of a jittered pixel unnecessary
-        st0 = m["stats_rank0"]
-        flops_exec = flops - 25.0 * (st0["sphere_tests"] - st0["sphere_tests_executed"])
-        executed = flops_exec / (dom_ms * 1e-3) / 1e12
-        frame_bytes = m["kw"]["width"] * m["kw"]["height"] * 3
+
+        def cpu_block(w):
+            if w not in cpu:
+                return None
+            o2, o0 = cpu[w]
+            blk = {k: o2[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            blk["frame_s_extrapolated"] = o2["frame_s_extrapolated"]
+            if o0 is not None:
+                blk["reference_flags_build"] = {"value": o0["value"], "unit": "Mrays/s", "flags": "-g, no -O (src/Makefile:2)", "cores": o0["cores"],
+                                                "sample": o0["sample"], "frame_s_extrapolated": o0["frame_s_extrapolated"]}
+            return blk
+
+        configs = {}
+        for w in sorted(results):
+            o = results[w]
+            configs[w] = {"workload": o["desc"], "ms_per_frame": o["ms_per_step"], "ms_per_frame_median_this_rank": o["ms_per_step_median"],
+                          "ms_per_frame_min_this_rank": o["ms_per_step_min"], "mrays_per_s": o["value"], "rays_per_frame": o["rays"], "steps": o["steps"],
+                          "warmup": o["warmup"], "kernel_launches_per_frame": o["launches"] / o["steps"], "first_frame_ms": o["first_frame_ms"],
+                          "reserve_ms": o["reserve_ms"], "e2e": o.get("e2e"), "frame_split": frame_split_text(o, world),
+                          "roofline": roofline_of(o, world, peaks, peaks_src, fp32_peak, bw), "cpu_baseline": cpu_block(w)}
         line = {
             "metric": "Mrays/s", "value": m["value"], "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": m["desc"], "scene": m["scene"] + " (snapshot of the reference parser's Scene, tests/golden/scenes)", **m["kw"], "seed": SEED,
                        "rays_per_frame": m["rays"], "closest_hit_rays": st["closest_hit_rays"], "shadow_rays": st["shadow_rays"],
                        "l2": "flushed between steps with a 256 MiB memset, outside the per-step CUDA events", "timing": "CUDA events per step on the library stream, summed; max over ranks",
-                       "frame_split": ("single GPU, whole frame" if world == 1 else
-                                       f"{world} ranks, interleaved 32x32 tiles; finished pixels stored straight into every rank's frame over NVLink "
-                                       "(skr_render_peers_device, torch symmetric memory), one symmetric-memory barrier per frame" if m["p2p"] else
-                                       f"{world} ranks, interleaved 32x32 tiles, one NCCL all-gather of RGB8 tiles per frame + de-interleave kernel"),
+                       "frame_split": frame_split_text(m, world),
                        "ms_per_step_median_this_rank": m["ms_per_step_median"], "ms_per_step_min_this_rank": m["ms_per_step_min"],
                        "wall_ms_per_step_incl_flush": m["wall_ms_per_step"]},
             "clocks": clocks,
             "e2e": m.get("e2e"),
             "gpu_launches": m["launches"],
-            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[0] if world == 1 else None,
-                         "traffic_source": NCU_TRAFFIC_BYTES.get(args.workload, (None, None))[1], "kernel": "primary_kernel" if dom == "primary" else "shade_expand_kernel",
-                         "kernel_ms_per_frame": dom_ms, "kernel_launches_per_frame": dom_launches,
-                         "flops_per_frame_algorithmic_this_rank": flops,
-                         "executed": {"tflops": executed, "frac": executed / fp32_peak, "flops_per_frame_this_rank": flops_exec,
-                                      "sphere_tests_algorithmic": st0["sphere_tests"], "sphere_tests_executed": st0["sphere_tests_executed"],
-                                      "note": "`achieved` counts the reference algorithm's arithmetic (every sphere per query); conservative bundle culling "
-                                              "skips tests that provably fail, so the FP32 pipe executed only this much"},
-                         "peak_source": "FFMA microbenchmark measured live in this run (skr_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
-                         "note": "compute-bound FP32 CUDA-core path (no dense contraction -> tensor cores unused); algorithmic HBM traffic is the RGB8 frame only",
-                         "hbm": {"algorithmic_bytes_per_frame": frame_bytes, "achieved_gbs": frame_bytes / (m["ms_per_step"] * 1e-3) / 1e9,
-                                 "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src}},
-            "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "roofline": roofline_of(m, world, peaks, peaks_src, fp32_peak, bw),
+            "cpu_baseline": None if args.workload not in cpu else {k: cpu[args.workload][0][k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "peaks_measured_live": {"fp32_tflops": fp32_peak, **bw, "hbm_gbs": peaks.get("hbm_gbs"), "hbm_source": peaks_src},
+            "configs": configs,
         }
-        if others:
-            line["other_configs"] = others
         emit(line)
     r.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -436,8 +576,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--all-configs", action="store_true", help="also measure the other BASELINE.json configs (N=1)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="headline workload (default: BASELINE.json configs[1])")
+    ap.add_argument("--only-headline", action="store_true", help="skip the `configs` block (the other BASELINE.json configs)")
+    ap.add_argument("--all-configs", action="store_true", help="(default now; kept for compatibility)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -22,6 +22,7 @@
 #ifndef SKR_H
 #define SKR_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -170,6 +171,16 @@ int skr_deinterleave_device(skr_ctx *ctx, const skr_options *opt, const void *d_
  * reads one while the next is being rendered.  1 <= n_frames <= 8.  Asynchronous like skr_render_device. */
 int skr_render_peers_device(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, skr_stats *stats);
 
+/* Frames straight into HOST memory (ABI 3).  A page-locked, device-mapped host buffer is a valid target of
+ * skr_render_peers_device: the kernel that finishes a pixel stores it over PCIe while the rest of the frame is still
+ * being traced, and with a frame split every GPU writes its own tiles over its OWN PCIe link -- no device frame, no
+ * gather, no D2H copy.  skr_pin_host page-locks and maps a caller-owned buffer (e.g. a shared-memory segment that several
+ * one-process-per-GPU ranks map) and returns the pointer to pass as d_frames[k]; it returns 0 when it registered the
+ * buffer (undo with skr_unpin_host), 1000 when the buffer was page-locked already (cudaHostAlloc, torch pin_memory:
+ * nothing to undo), another skr_status on error. */
+int skr_pin_host(skr_ctx *ctx, void *host, size_t bytes, void **d_ptr);
+int skr_unpin_host(skr_ctx *ctx, void *host);
+
 /* The library's stream as a cudaStream_t (so that callers can order their own work / events after it),
  * and a blocking wait for it. */
 void *skr_stream(skr_ctx *ctx);
@@ -178,6 +189,12 @@ int skr_sync(skr_ctx *ctx);
 /* FP32 FMA microbenchmark (register-resident FFMA chains on every SM): returns TFLOP/s, <0 on error.
  * Used by bench.py as the measured FP32 roofline denominator (MEASURED_PEAKS.json has none). */
 double skr_measure_fp32_peak(skr_ctx *ctx, int iters);
+
+/* Read-bandwidth microbenchmarks of the on-chip memory levels the BVH / primitive fetch goes through (ABI 3):
+ * level 0 = shared memory (LDS.128), 1 = L1 (ld.global.ca over a window resident in every SM's L1), 2 = L2
+ * (ld.global.cg over 64 MB).  Returns GB/s over all SMs, <0 on error.  Denominators for bench.py's triangle-path
+ * roofline (MEASURED_PEAKS.json has HBM only). */
+double skr_measure_bandwidth(skr_ctx *ctx, int level);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "libskr_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libskr_ref.so")
 REF_FRESNEL_SO = os.path.join(HERE, "_ref", "libskr_ref_fresnel.so")
+REF_O0_SO = os.path.join(HERE, "_ref", "libskr_ref_O0.so")  # the reference's own flags (src/Makefile:2: -g, no -O)
 REF_UNMODIFIED = os.path.join(HERE, "_ref", "raytracer_unmodified")
 REF_SCENES = os.path.join(HERE, "_ref", "scenes")
 
@@ -198,8 +199,8 @@ class Port:
 class Ref:
     """The reference's own compiled code (oracle/_ref)."""
 
-    def __init__(self, fresnel: bool = False):
-        path = REF_FRESNEL_SO if fresnel else REF_SO
+    def __init__(self, fresnel: bool = False, unoptimised: bool = False):
+        path = REF_FRESNEL_SO if fresnel else (REF_O0_SO if unoptimised else REF_SO)
         if not os.path.exists(path):
             build_ref()
         if not os.path.exists(path):

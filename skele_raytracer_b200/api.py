@@ -212,6 +212,10 @@ class Renderer:
         L.skr_sync.argtypes = [C.c_void_p]
         L.skr_measure_fp32_peak.restype = C.c_double
         L.skr_measure_fp32_peak.argtypes = [C.c_void_p, C.c_int]
+        L.skr_pin_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.skr_unpin_host.argtypes = [C.c_void_p, C.c_void_p]
+        L.skr_measure_bandwidth.restype = C.c_double
+        L.skr_measure_bandwidth.argtypes = [C.c_void_p, C.c_int]
         L.skr_abi_version.restype = C.c_int
         self.lib = L
         self.ctx = C.c_void_p()
@@ -292,6 +296,17 @@ class Renderer:
         self._check(self.lib.skr_deinterleave_device(self.ctx, C.byref(o), d_gathered, d_rgb8),
                     "skr_deinterleave_device")
 
+    def pin_host(self, host_ptr: int, nbytes: int):
+        """skr_pin_host -> (device pointer usable as a frame of render_peers_device, registered_here: bool)."""
+        d = C.c_void_p()
+        rc = self.lib.skr_pin_host(self.ctx, host_ptr, nbytes, C.byref(d))
+        if rc not in (0, 1000):
+            self._check(rc, "skr_pin_host")
+        return int(d.value or 0), rc == 0
+
+    def unpin_host(self, host_ptr: int) -> None:
+        self._check(self.lib.skr_unpin_host(self.ctx, host_ptr), "skr_unpin_host")
+
     def stream(self) -> int:
         return int(self.lib.skr_stream(self.ctx) or 0)
 
@@ -300,6 +315,10 @@ class Renderer:
 
     def measure_fp32_peak(self, iters: int = 4096) -> float:
         return float(self.lib.skr_measure_fp32_peak(self.ctx, iters))
+
+    def measure_bandwidth(self, level: int) -> float:
+        """GB/s of shared memory (0), L1 (1) or L2 (2) reads, measured by a microbenchmark on this device."""
+        return float(self.lib.skr_measure_bandwidth(self.ctx, level))
 
 
 def generate_rays_parallel(scene: Scene, option: Options, output: str, renderer: Renderer | None = None) -> np.ndarray:

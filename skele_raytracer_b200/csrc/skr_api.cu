@@ -19,6 +19,7 @@
 
 #include "skr_bvh_build.cuh"
 #include "skr_kernels.cuh"
+#include "skr_micro.cuh"
 
 namespace
 {
@@ -91,6 +92,7 @@ struct skr_ctx
 	unsigned *h_count = nullptr; // pinned
 
 	unsigned long long *d_counters = nullptr; // 9 (16 allocated)
+	unsigned *d_cursor = nullptr;			  // (next strip, CTAs done) of the persistent primary_kernel; self-resetting
 	int *d_err = nullptr;
 	int *h_err = nullptr; // pinned
 
@@ -207,32 +209,37 @@ void span_end(skr_ctx *ctx)
 // ---- kernel dispatch over the template flags -----------------------------------------------------
 // SMEM variants exist for every (TRIS, FOG); the global-memory fallback (scene blob > 64 KB) only as the general one.
 template <bool GI, bool STATS>
-void launch_primary(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, const Queue &q, long long lp0, long long n)
+void launch_primary(skr_ctx *ctx, const FrameParams &fp, const Queue &q, long long lp0, long long n)
 {
 	const SceneView &sv = ctx->sv;
 	cudaStream_t st		= ctx->stream;
 	const size_t sm		= ctx->smem_bytes;
+	// persistent: one wave of CTAs pulling strips of SKR_BLOCK pixels from ctx->d_cursor (see primary_kernel)
+	const long long strips = (n + SKR_BLOCK - 1) / SKR_BLOCK;
+	const long long wave   = (long long) ctx->sm_count * SKR_MIN_BLOCKS;
+	const unsigned blocks  = (unsigned) (strips < wave ? strips : wave);
+	unsigned *cur		   = ctx->d_cursor;
 	if(!sv.blob_in_smem)
 	{
-		primary_kernel<GI, STATS, false, true, true><<<blocks, SKR_BLOCK, 0, st>>>(sv, fp, q, lp0, n);
+		primary_kernel<GI, STATS, false, true, true><<<blocks, SKR_BLOCK, 0, st>>>(sv, fp, q, lp0, n, cur);
 		return;
 	}
 	const bool tris = sv.T > 0, fog = sv.F > 0;
 	if(tris && fog)
 	{
-		primary_kernel<GI, STATS, true, true, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n);
+		primary_kernel<GI, STATS, true, true, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n, cur);
 	}
 	else if(tris)
 	{
-		primary_kernel<GI, STATS, true, true, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n);
+		primary_kernel<GI, STATS, true, true, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n, cur);
 	}
 	else if(fog)
 	{
-		primary_kernel<GI, STATS, true, false, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n);
+		primary_kernel<GI, STATS, true, false, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n, cur);
 	}
 	else
 	{
-		primary_kernel<GI, STATS, true, false, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n);
+		primary_kernel<GI, STATS, true, false, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n, cur);
 	}
 }
 
@@ -785,9 +792,8 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	if(!tree || pl.levels == 0)
 	{
 		span_begin(ctx, CAT_PRIMARY);
-		const unsigned blocks = (unsigned) ((pl.npix_local + SKR_BLOCK - 1) / SKR_BLOCK);
 		Queue none{};
-		launch_primary<false, STATS>(ctx, blocks, fp, none, 0, pl.npix_local);
+		launch_primary<false, STATS>(ctx, fp, none, 0, pl.npix_local);
 		span_end(ctx);
 		ctx->launches++;
 		CK(cudaGetLastError());
@@ -800,7 +806,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		const long long n = pl.npix_local - lp0 < batch ? pl.npix_local - lp0 : batch;
 		CK(cudaMemsetAsync(q0.count, 0, sizeof(unsigned), st));
 		span_begin(ctx, CAT_PRIMARY);
-		launch_primary<true, STATS>(ctx, (unsigned) ((n + SKR_BLOCK - 1) / SKR_BLOCK), fp, q0, lp0, n);
+		launch_primary<true, STATS>(ctx, fp, q0, lp0, n);
 		span_end(ctx);
 		ctx->launches++;
 		ctx->chunks++;
@@ -859,6 +865,17 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	ctx->timing		 = !async;
 	pl.fp.counters = ctx->d_counters;
 	pl.fp.err	   = ctx->d_err;
+	{
+		// whole strips leave as 32-bit words when a strip is a 32 x 4 pixel block whose rows start on word boundaries
+		const auto al4 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0u; };
+		bool ok		   = pl.fp.tile == 32 && pl.fp.width % 4 == 0 && al4(pl.fp.rgb8);
+		for(int k = 0; k < pl.fp.n_peers; k++)
+		{
+			ok = ok && al4(pl.fp.peers[k]);
+		}
+		const char *no	  = getenv("SKR_NO_STRIP_WORDS");
+		pl.fp.strip_words = (ok && !(no && no[0] == '1')) ? 1 : 0;
+	}
 	// a single-kernel frame needs no per-kernel events (its span is the frame), no counter reset unless counters were
 	// asked for, and no reset of the error word (zero unless a frame failed; cleared again below when read non-zero)
 	ctx->timing = !async && tree;
@@ -1009,6 +1026,10 @@ int skr_init(int device, skr_ctx **out)
 	{
 		return bail(e, "cudaMalloc");
 	}
+	if((e = cudaMalloc(&c->d_cursor, 2 * sizeof(unsigned))) != cudaSuccess || (e = cudaMemset(c->d_cursor, 0, 2 * sizeof(unsigned))) != cudaSuccess)
+	{
+		return bail(e, "cudaMalloc");
+	}
 	if((e = cudaMalloc(&c->d_err, sizeof(int))) != cudaSuccess || (e = cudaMemset(c->d_err, 0, sizeof(int))) != cudaSuccess)
 	{
 		return bail(e, "cudaMalloc");
@@ -1058,6 +1079,7 @@ void skr_destroy(skr_ctx *ctx)
 	cudaFree(ctx->d_blob), cudaFree(ctx->d_tris_raw), cudaFree(ctx->d_tri_v), cudaFree(ctx->d_bvh), cudaFree(ctx->d_scratch);
 	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
 	cudaFree(ctx->d_arena);
+	cudaFree(ctx->d_cursor);
 	cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band), cudaFree(ctx->d_big);
 	if(ctx->copy_stream)
 	{
@@ -1130,6 +1152,7 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		return fail(ctx, SKR_ERR_ARG, "skr_scene_upload: null array with nonzero count");
 	}
 	ctx->have_scene = false;
+	CK(cudaMemsetAsync(ctx->d_cursor, 0, 2 * sizeof(unsigned), ctx->stream)); // (a frame that died mid-kernel may have left it armed)
 	const int S = sc->nspheres, T = sc->ntris, L = sc->nplights, D = sc->ndlights, F = sc->nfogs;
 	const int S4 = (S + 3) / 4 * 4;
 	SceneView &sv = ctx->sv;
@@ -1670,6 +1693,93 @@ double skr_measure_fp32_peak(skr_ctx *ctx, int iters)
 		}
 	}
 	cudaFree(d_out);
+	return best;
+}
+
+int skr_pin_host(skr_ctx *ctx, void *host, size_t bytes, void **d_ptr)
+{
+	REQUIRE_CTX();
+	if(!host || !bytes || !d_ptr)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_pin_host: null argument");
+	}
+	*d_ptr = nullptr;
+	cudaPointerAttributes a;
+	const bool known = cudaPointerGetAttributes(&a, host) == cudaSuccess && a.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if(!known)
+	{
+		CK(cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+	}
+	CK(cudaHostGetDevicePointer(d_ptr, host, 0));
+	return known ? 1000 : SKR_OK; // 1000: was page-locked already (nothing to undo)
+}
+
+int skr_unpin_host(skr_ctx *ctx, void *host)
+{
+	REQUIRE_CTX();
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaHostUnregister(host));
+	return SKR_OK;
+}
+
+double skr_measure_bandwidth(skr_ctx *ctx, int level)
+{
+	if(!ctx || cudaSetDevice(ctx->device) != cudaSuccess || level < 0 || level > 2)
+	{
+		return -1.0;
+	}
+	const int blocks = ctx->sm_count * 8, threads = 256;
+	const int iters	 = level == 2 ? 256 : 2048;
+	float *d_out	 = nullptr;
+	float4 *d_buf	 = nullptr;
+	// L1: every CTA walks the same 16 KB window, resident in each SM's L1; L2: one 64 MB buffer streamed by all CTAs
+	const size_t buf_f4 = level == 1 ? 1024 : level == 2 ? (size_t) (64u << 20) / 16 : 1;
+	if(cudaMalloc(&d_out, sizeof(float) * (size_t) blocks * threads) != cudaSuccess)
+	{
+		return -1.0;
+	}
+	if(cudaMalloc(&d_buf, sizeof(float4) * buf_f4) != cudaSuccess || cudaMemsetAsync(d_buf, 0, sizeof(float4) * buf_f4, ctx->stream) != cudaSuccess)
+	{
+		cudaFree(d_out);
+		return -1.0;
+	}
+	double best = 0.0;
+	for(int rep = 0; rep < 5; rep++)
+	{
+		cudaEventRecord(ctx->ev_x0, ctx->stream);
+		if(level == 0)
+		{
+			lds_bw_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
+		}
+		else if(level == 1)
+		{
+			gmem_bw_kernel<0><<<blocks, threads, 0, ctx->stream>>>(d_buf, 0xffffffffu, 0u, d_out, 0); // (loads the kernel)
+			gmem_bw_kernel<0><<<blocks, threads, 0, ctx->stream>>>(d_buf, 1023u, 0u, d_out, 8);		  // warm the window
+			cudaEventRecord(ctx->ev_x0, ctx->stream);
+			gmem_bw_kernel<0><<<blocks, threads, 0, ctx->stream>>>(d_buf, 1023u, 0u, d_out, iters);
+		}
+		else
+		{
+			gmem_bw_kernel<1><<<blocks, threads, 0, ctx->stream>>>(d_buf, (unsigned) (buf_f4 - 1), 4099u * 16u, d_out, iters);
+		}
+		cudaEventRecord(ctx->ev_x1, ctx->stream);
+		if(cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+		{
+			best = -1.0;
+			break;
+		}
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev_x0, ctx->ev_x1);
+		const double bytes = 16.0 * 8.0 * (double) iters * (double) blocks * threads;
+		const double gbs   = bytes / (ms * 1e-3) / 1e9;
+		if(rep > 0 && gbs > best)
+		{
+			best = gbs;
+		}
+	}
+	cudaFree(d_out);
+	cudaFree(d_buf);
 	return best;
 }
 

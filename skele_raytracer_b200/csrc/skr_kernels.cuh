@@ -56,6 +56,7 @@ struct FrameParams
 	float angle, aspect, inv_w, inv_h;
 	int cull;		  // 1: bundle culling (cull_pairs) for this frame: jittered, >= 4 samples per pixel, <= 64 spheres
 	float cull_delta; // bound on |d(r) - d(0.5)| over the jitter draw r of a pixel (ray directions are un-normalised)
+	int strip_words;  // 1: whole strips leave as 32-bit words (tile == 32, width % 4 == 0, 4-byte aligned frames)
 	uint2 key;
 	uint32_t node_base, slot_gi;
 	uint8_t *rgb8;	 // row-major frame or null
@@ -320,15 +321,40 @@ SKR_DEV float3 queue_hit_point(const float4 *__restrict__ B, const SceneView &sv
 // Template flags: GI (--gillum: push hits instead of shading), STATS (device counters), SMEM (scene blob staged in shared
 // memory), TRIS (scene has triangles: BVH code compiled in), FOG (scene has spherical fog: fog shading compiled in).
 // Sphere-only, fog-free scenes thus run a kernel without the traversal stack or the fog branch in its register budget.
+//
+// PERSISTENT: the grid is one wave of CTAs (SM count x SKR_MIN_BLOCKS, fewer for small frames); each CTA stages the
+// scene blob ONCE and then pulls strips of SKR_BLOCK local pixels -- with the default 32-pixel tiles a strip is a
+// 32 x 4 pixel row-block of one tile, its four warps the four 8 x 4 blocks -- from a device counter until the frame is
+// used up (the fetch of the next strip is issued before the current one is traced, so its latency is hidden).  A
+// 1080p frame is 16 200 strips: dynamic assignment balances sky against geometry without paying 16 200 CTA launches
+// and blob stagings.  The counter pair `cursor` = (next strip, CTAs done) resets itself: the last CTA to leave zeroes it.
+// Finished pixels of a strip are quantised into shared memory and leave as 32-bit words, 96 B per pixel row (full
+// 32 B sectors to HBM, to a peer GPU over NVLink or to page-locked host memory over PCIe), instead of 3 byte stores each.
 template <bool GI, bool STATS, bool SMEM, bool TRIS, bool FOG>
-__global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix)
+__global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix,
+																	 unsigned *cursor)
 {
 	extern __shared__ float4 smem[];
+	__shared__ unsigned s_next;
+	__shared__ uint32_t s_px[SKR_BLOCK * 3 / 4]; // one strip of RGB8: 4 rows x 96 B
 	const float4 *B = stage_scene<SMEM>(sv, smem);
 	Counters cnt;
 	zero(cnt);
-
-	const long long g  = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned nstrips = (unsigned) ((npix + SKR_BLOCK - 1) / SKR_BLOCK);
+	if(threadIdx.x == 0)
+	{
+		s_next = atomicAdd(cursor, 1u);
+	}
+	__syncthreads();
+	unsigned strip = s_next;
+	while(strip < nstrips)
+	{
+	__syncthreads(); // every thread has read s_next
+	if(threadIdx.x == 0)
+	{
+		s_next = atomicAdd(cursor, 1u); // the next strip's index is on its way while this one is traced
+	}
+	const long long g  = (long long) strip * SKR_BLOCK + threadIdx.x;
 	const long long lp = lp0 + g;
 	PixelId p		   = decode_pixel(fp, lp);
 	p.valid			   = p.valid && g < npix;
@@ -432,36 +458,97 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		}
 	}
 
-	if(p.valid)
+	if(GI)
 	{
-		if(GI)
+		if(p.valid)
 		{
 			accum_store(fp.accum, lp, sum);
 		}
-		else
+	}
+	else
+	{
+		if(fp.grid > 0)
 		{
-			if(fp.grid > 0)
+			const float n2 = (float) fp.spp; // image[y][x] /= (grid*grid), src/main.cpp:68
+			sum			   = f3(__fdiv_rn(sum.x, n2), __fdiv_rn(sum.y, n2), __fdiv_rn(sum.z, n2));
+		}
+		// The strip's first pixel (thread 0) fixes its place: 32 x 4 pixels at (x0, y0) when tiles are 32 wide.  Whole
+		// strips whose rows start on a word boundary leave as words; ragged ones pixel by pixel.
+		const PixelId p0 = decode_pixel(fp, lp0 + (long long) strip * SKR_BLOCK);
+		const bool words = fp.strip_words && p0.valid && p0.x + 32 <= fp.width && (long long) (strip + 1) * SKR_BLOCK <= npix;
+		if(words)
+		{
+			uint8_t *sb	  = reinterpret_cast<uint8_t *>(s_px);
+			const int row = (threadIdx.x & 31) >> 3, col = (threadIdx.x >> 5) * 8 + (threadIdx.x & 7);
+			uint8_t *o	  = sb + row * 96 + col * 3;
+			o[0]		  = quantise(sum.x);
+			o[1]		  = quantise(sum.y);
+			o[2]		  = quantise(sum.z);
+			if(fp.rgb32 && p.valid)
 			{
-				const float n2 = (float) fp.spp; // image[y][x] /= (grid*grid), src/main.cpp:68
-				sum			   = f3(__fdiv_rn(sum.x, n2), __fdiv_rn(sum.y, n2), __fdiv_rn(sum.z, n2));
+				float *f = fp.rgb32 + 3 * ((size_t) p.y * fp.width + p.x);
+				f[0]	 = sum.x;
+				f[1]	 = sum.y;
+				f[2]	 = sum.z;
 			}
+			if(fp.tiles8 && p.valid)
+			{
+				const int tpix = fp.tile * fp.tile;
+				uint8_t *t	   = fp.tiles8 + 3 * ((size_t) (lp / tpix) * tpix + (size_t) (p.y % fp.tile) * fp.tile + (p.x % fp.tile));
+				t[0] = o[0], t[1] = o[1], t[2] = o[2];
+			}
+			__syncthreads();
+			if(threadIdx.x < 96)
+			{
+				const int r = threadIdx.x / 24, w = threadIdx.x - r * 24;
+				if(p0.y + r < fp.height)
+				{
+					const size_t at	 = (((size_t) (p0.y + r) * fp.width + p0.x) * 3) / 4 + w;
+					const uint32_t v = s_px[r * 24 + w];
+					if(fp.rgb8)
+					{
+						reinterpret_cast<uint32_t *>(fp.rgb8)[at] = v;
+					}
+					for(int k = 0; k < fp.n_peers; k++)
+					{
+						reinterpret_cast<uint32_t *>(fp.peers[k])[at] = v;
+					}
+				}
+			}
+		}
+		else if(p.valid)
+		{
 			write_pixel(fp, lp, p, sum);
 		}
-	}
-	if(!GI && fp.band_flag)
-	{
-		__syncthreads(); // every pixel store of this CTA is issued
-		if(threadIdx.x == 0)
+		if(fp.band_flag)
 		{
-			__threadfence_system();
-			const unsigned b	= blockIdx.x / fp.band_ctas;
-			const unsigned left = gridDim.x - b * fp.band_ctas;
-			const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
-			if((atomicAdd(fp.band_count + b, 1u) + 1u) % want == 0u) // counters run on from frame to frame (same geometry)
+			__syncthreads(); // every pixel store of this strip is issued
+			if(threadIdx.x == 0)
 			{
 				__threadfence_system();
-				atomicExch(fp.band_flag + b, fp.band_seq);
+				const unsigned b	= strip / fp.band_ctas;
+				const unsigned left = nstrips - b * fp.band_ctas;
+				const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
+				if((atomicAdd(fp.band_count + b, 1u) + 1u) % want == 0u) // counters run on from frame to frame (same geometry)
+				{
+					__threadfence_system();
+					atomicExch(fp.band_flag + b, fp.band_seq);
+				}
 			}
+		}
+	}
+	__syncthreads(); // s_next is the next strip's; s_px may be overwritten
+	strip = s_next;
+	} // strips
+	if(threadIdx.x == 0)
+	{
+		// the last CTA to leave re-arms the counter pair for the next launch (every CTA's final fetch is behind it)
+		__threadfence();
+		if(atomicAdd(cursor + 1, 1u) == gridDim.x - 1u)
+		{
+			cursor[0] = 0u;
+			cursor[1] = 0u;
+			__threadfence();
 		}
 	}
 	flush_counters<STATS>(fp, cnt);
@@ -920,26 +1007,4 @@ __global__ void deinterleave_kernel(const uint8_t *__restrict__ gathered, uint8_
 	rgb8[3 * i + 0]	 = gathered[src + 0];
 	rgb8[3 * i + 1]	 = gathered[src + 1];
 	rgb8[3 * i + 2]	 = gathered[src + 2];
-}
-
-// FP32 FMA peak microbenchmark: 8 independent FFMA chains per thread, register resident.
-__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float a, float b)
-{
-	float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-	for(int i = 0; i < iters; i++)
-	{
-#pragma unroll
-		for(int k = 0; k < 16; k++)
-		{
-			x0 = fmaf(x0, a, b);
-			x1 = fmaf(x1, a, b);
-			x2 = fmaf(x2, a, b);
-			x3 = fmaf(x3, a, b);
-			x4 = fmaf(x4, a, b);
-			x5 = fmaf(x5, a, b);
-			x6 = fmaf(x6, a, b);
-			x7 = fmaf(x7, a, b);
-		}
-	}
-	out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
