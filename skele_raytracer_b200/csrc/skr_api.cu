@@ -214,10 +214,11 @@ void launch_primary(skr_ctx *ctx, const FrameParams &fp, const Queue &q, long lo
 	const SceneView &sv = ctx->sv;
 	cudaStream_t st		= ctx->stream;
 	const size_t sm		= ctx->smem_bytes;
-	// persistent: one wave of CTAs pulling strips of SKR_BLOCK pixels from ctx->d_cursor (see primary_kernel)
-	const long long strips = (n + SKR_BLOCK - 1) / SKR_BLOCK;
-	const long long wave   = (long long) ctx->sm_count * SKR_MIN_BLOCKS;
-	const unsigned blocks  = (unsigned) (strips < wave ? strips : wave);
+	// persistent: one wave of CTAs whose warps pull batches of 8 x 4 pixel blocks from ctx->d_cursor (see primary_kernel)
+	const long long batches = ((n + 31) / 32 + fp.fetch - 1) / fp.fetch;
+	const long long need	= (batches + SKR_BLOCK / 32 - 1) / (SKR_BLOCK / 32);
+	const long long wave	= (long long) ctx->sm_count * SKR_MIN_BLOCKS;
+	const unsigned blocks	= (unsigned) (need < wave ? need : wave);
 	unsigned *cur		   = ctx->d_cursor;
 	if(!sv.blob_in_smem)
 	{
@@ -576,6 +577,8 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		const char *nocull = getenv("SKR_NO_CULL");
 		fp.cull = (sv.off_cull >= 0 && fp.grid > 0 && fp.spp >= 4 && !(nocull && nocull[0] == '1') && std::isfinite(fp.cull_delta)) ? 1 : 0;
 	}
+	// blocks a warp takes per fetch: one where a block is long (jittered samples, BVH traversal), four where pixels are cheap
+	fp.fetch	 = (fp.spp >= 4 || ctx->sv.T > BRUTE_FORCE_TRIS) ? 1 : 4;
 	fp.node_base = (uint32_t) fp.n_gi + 1u + (fp.fresnel ? 2u * (uint32_t) (ctx->sv.L + ctx->sv.D) : 0u);
 	fp.slot_gi	 = 1u + (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
 	pl.tiles_local = (fp.tiles_total + world - 1) / world;
@@ -866,9 +869,9 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	pl.fp.counters = ctx->d_counters;
 	pl.fp.err	   = ctx->d_err;
 	{
-		// whole strips leave as 32-bit words when a strip is a 32 x 4 pixel block whose rows start on word boundaries
+		// whole 8 x 4 pixel blocks leave as 32-bit words when their rows start on word boundaries
 		const auto al4 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0u; };
-		bool ok		   = pl.fp.tile == 32 && pl.fp.width % 4 == 0 && al4(pl.fp.rgb8);
+		bool ok		   = pl.fp.width % 4 == 0 && al4(pl.fp.rgb8);
 		for(int k = 0; k < pl.fp.n_peers; k++)
 		{
 			ok = ok && al4(pl.fp.peers[k]);
@@ -1480,7 +1483,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 			}
 			pl.fp.band_count = ctx->d_band;
 			pl.fp.band_flag	 = ctx->d_band + MAX_BANDS;
-			pl.fp.band_ctas	 = (unsigned) rpb * (unsigned) fp.tiles_x * (unsigned) (tpix / SKR_BLOCK);
+			pl.fp.band_ctas	 = (unsigned) rpb * (unsigned) fp.tiles_x * (unsigned) (tpix / 32) / (unsigned) fp.fetch; // batches per band
 			pl.fp.band_seq	 = ++ctx->band_seq;
 		}
 	}
@@ -1489,7 +1492,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 	{
 		// the per-band CTA counters run on from frame to frame; reset when the band geometry changes (and now and then,
 		// far from 32-bit wrap-around) or after a frame that did not complete
-		const unsigned long long geom = ((unsigned long long) pl.fp.band_ctas << 32) | (unsigned) (pl.npix_local / SKR_BLOCK);
+		const unsigned long long geom = ((unsigned long long) pl.fp.band_ctas << 32) | (unsigned) (pl.npix_local / 32 / pl.fp.fetch);
 		if(geom != ctx->band_geom || (pl.fp.band_seq & 0xffffu) == 0u)
 		{
 			CK(cudaMemsetAsync(ctx->d_band, 0, sizeof(unsigned) * MAX_BANDS, ctx->stream));

@@ -56,7 +56,8 @@ struct FrameParams
 	float angle, aspect, inv_w, inv_h;
 	int cull;		  // 1: bundle culling (cull_pairs) for this frame: jittered, >= 4 samples per pixel, <= 64 spheres
 	float cull_delta; // bound on |d(r) - d(0.5)| over the jitter draw r of a pixel (ray directions are un-normalised)
-	int strip_words;  // 1: whole strips leave as 32-bit words (tile == 32, width % 4 == 0, 4-byte aligned frames)
+	int strip_words;  // 1: whole 8 x 4 blocks leave as 32-bit words (width % 4 == 0, 4-byte aligned frames)
+	int fetch;		  // blocks a warp of primary_kernel takes per fetch (1, or 4 when pixels are cheap)
 	uint2 key;
 	uint32_t node_base, slot_gi;
 	uint8_t *rgb8;	 // row-major frame or null
@@ -323,38 +324,42 @@ SKR_DEV float3 queue_hit_point(const float4 *__restrict__ B, const SceneView &sv
 // Sphere-only, fog-free scenes thus run a kernel without the traversal stack or the fog branch in its register budget.
 //
 // PERSISTENT: the grid is one wave of CTAs (SM count x SKR_MIN_BLOCKS, fewer for small frames); each CTA stages the
-// scene blob ONCE and then pulls strips of SKR_BLOCK local pixels -- with the default 32-pixel tiles a strip is a
-// 32 x 4 pixel row-block of one tile, its four warps the four 8 x 4 blocks -- from a device counter until the frame is
-// used up (the fetch of the next strip is issued before the current one is traced, so its latency is hidden).  A
-// 1080p frame is 16 200 strips: dynamic assignment balances sky against geometry without paying 16 200 CTA launches
-// and blob stagings.  The counter pair `cursor` = (next strip, CTAs done) resets itself: the last CTA to leave zeroes it.
-// Finished pixels of a strip are quantised into shared memory and leave as 32-bit words, 96 B per pixel row (full
-// 32 B sectors to HBM, to a peer GPU over NVLink or to page-locked host memory over PCIe), instead of 3 byte stores each.
+// scene blob ONCE, then every WARP on its own pulls 8 x 4 pixel blocks (`fp.fetch` consecutive blocks per fetch) from a
+// device counter until the frame is used up -- no barrier couples the warps of a CTA, a warp whose block was sky is
+// tracing its next block while its neighbour is still inside the dragon.  The fetch of the next batch is issued before
+// the current one is traced, so its latency is hidden.  A 1080p frame is 64 800 blocks: dynamic assignment balances sky
+// against geometry without paying 16 200 CTA launches and blob stagings.  The counter pair `cursor` = (next block, CTAs
+// done) resets itself: the last CTA to leave zeroes it.
+// Finished pixels of a block are quantised into shared memory and leave as 32-bit words, 24 B per pixel row (to HBM, to
+// a peer GPU over NVLink or to page-locked host memory over PCIe), instead of 3 byte stores each.
 template <bool GI, bool STATS, bool SMEM, bool TRIS, bool FOG>
 __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix,
 																	 unsigned *cursor)
 {
 	extern __shared__ float4 smem[];
-	__shared__ unsigned s_next;
-	__shared__ uint32_t s_px[SKR_BLOCK * 3 / 4]; // one strip of RGB8: 4 rows x 96 B
+	__shared__ uint32_t s_px[SKR_BLOCK / 32][24]; // per warp: one block of RGB8, 4 rows x 24 B
 	const float4 *B = stage_scene<SMEM>(sv, smem);
 	Counters cnt;
 	zero(cnt);
-	const unsigned nstrips = (unsigned) ((npix + SKR_BLOCK - 1) / SKR_BLOCK);
-	if(threadIdx.x == 0)
+	const unsigned lane	   = threadIdx.x & 31u;
+	const unsigned nblocks = (unsigned) ((npix + 31) / 32);
+	const unsigned fetch   = (unsigned) fp.fetch;
+	unsigned nxt		   = 0;
+	if(lane == 0)
 	{
-		s_next = atomicAdd(cursor, 1u);
+		nxt = atomicAdd(cursor, fetch);
 	}
-	__syncthreads();
-	unsigned strip = s_next;
-	while(strip < nstrips)
+	unsigned batch = __shfl_sync(0xffffffffu, nxt, 0);
+	while(batch < nblocks)
 	{
-	__syncthreads(); // every thread has read s_next
-	if(threadIdx.x == 0)
+	if(lane == 0)
 	{
-		s_next = atomicAdd(cursor, 1u); // the next strip's index is on its way while this one is traced
+		nxt = atomicAdd(cursor, fetch); // the next batch's index is on its way while this one is traced
 	}
-	const long long g  = (long long) strip * SKR_BLOCK + threadIdx.x;
+	const unsigned batch_end = batch + fetch < nblocks ? batch + fetch : nblocks;
+	for(unsigned blk = batch; blk < batch_end; blk++)
+	{
+	const long long g  = (long long) blk * 32 + lane;
 	const long long lp = lp0 + g;
 	PixelId p		   = decode_pixel(fp, lp);
 	p.valid			   = p.valid && g < npix;
@@ -472,18 +477,17 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			const float n2 = (float) fp.spp; // image[y][x] /= (grid*grid), src/main.cpp:68
 			sum			   = f3(__fdiv_rn(sum.x, n2), __fdiv_rn(sum.y, n2), __fdiv_rn(sum.z, n2));
 		}
-		// The strip's first pixel (thread 0) fixes its place: 32 x 4 pixels at (x0, y0) when tiles are 32 wide.  Whole
-		// strips whose rows start on a word boundary leave as words; ragged ones pixel by pixel.
-		const PixelId p0 = decode_pixel(fp, lp0 + (long long) strip * SKR_BLOCK);
-		const bool words = fp.strip_words && p0.valid && p0.x + 32 <= fp.width && (long long) (strip + 1) * SKR_BLOCK <= npix;
+		// The block's first pixel (lane 0) fixes its place: 8 x 4 pixels at (x0, y0).  Whole blocks whose rows start on a
+		// word boundary leave as words; ragged ones pixel by pixel.
+		const int x0 = __shfl_sync(0xffffffffu, p.x, 0), y0 = __shfl_sync(0xffffffffu, p.y, 0);
+		const bool words = fp.strip_words && __shfl_sync(0xffffffffu, (int) p.valid, 0) && x0 + 8 <= fp.width;
 		if(words)
 		{
-			uint8_t *sb	  = reinterpret_cast<uint8_t *>(s_px);
-			const int row = (threadIdx.x & 31) >> 3, col = (threadIdx.x >> 5) * 8 + (threadIdx.x & 7);
-			uint8_t *o	  = sb + row * 96 + col * 3;
-			o[0]		  = quantise(sum.x);
-			o[1]		  = quantise(sum.y);
-			o[2]		  = quantise(sum.z);
+			uint8_t *sb = reinterpret_cast<uint8_t *>(s_px[threadIdx.x >> 5]);
+			uint8_t *o	= sb + (lane >> 3) * 24 + (lane & 7) * 3;
+			o[0]		= quantise(sum.x);
+			o[1]		= quantise(sum.y);
+			o[2]		= quantise(sum.z);
 			if(fp.rgb32 && p.valid)
 			{
 				float *f = fp.rgb32 + 3 * ((size_t) p.y * fp.width + p.x);
@@ -497,14 +501,14 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 				uint8_t *t	   = fp.tiles8 + 3 * ((size_t) (lp / tpix) * tpix + (size_t) (p.y % fp.tile) * fp.tile + (p.x % fp.tile));
 				t[0] = o[0], t[1] = o[1], t[2] = o[2];
 			}
-			__syncthreads();
-			if(threadIdx.x < 96)
+			__syncwarp();
+			if(lane < 24)
 			{
-				const int r = threadIdx.x / 24, w = threadIdx.x - r * 24;
-				if(p0.y + r < fp.height)
+				const int r = lane / 6, w = lane - r * 6;
+				if(y0 + r < fp.height)
 				{
-					const size_t at	 = (((size_t) (p0.y + r) * fp.width + p0.x) * 3) / 4 + w;
-					const uint32_t v = s_px[r * 24 + w];
+					const size_t at	 = (((size_t) (y0 + r) * fp.width + x0) * 3) / 4 + w;
+					const uint32_t v = s_px[threadIdx.x >> 5][r * 6 + w];
 					if(fp.rgb8)
 					{
 						reinterpret_cast<uint32_t *>(fp.rgb8)[at] = v;
@@ -515,34 +519,38 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 					}
 				}
 			}
+			__syncwarp();
 		}
 		else if(p.valid)
 		{
 			write_pixel(fp, lp, p, sum);
 		}
-		if(fp.band_flag)
+	}
+	} // blocks of the batch
+	if(!GI && fp.band_flag)
+	{
+		// overlapped copy-out (skr_render): batches are counted per band of whole tile rows; the last one publishes the flag
+		__syncwarp();
+		if(lane == 0)
 		{
-			__syncthreads(); // every pixel store of this strip is issued
-			if(threadIdx.x == 0)
+			__threadfence_system();
+			const unsigned nb	= (nblocks + fetch - 1) / fetch; // batches of the launch
+			const unsigned b	= (batch / fetch) / fp.band_ctas;
+			const unsigned left = nb - b * fp.band_ctas;
+			const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
+			if((atomicAdd(fp.band_count + b, 1u) + 1u) % want == 0u) // counters run on from frame to frame (same geometry)
 			{
 				__threadfence_system();
-				const unsigned b	= strip / fp.band_ctas;
-				const unsigned left = nstrips - b * fp.band_ctas;
-				const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
-				if((atomicAdd(fp.band_count + b, 1u) + 1u) % want == 0u) // counters run on from frame to frame (same geometry)
-				{
-					__threadfence_system();
-					atomicExch(fp.band_flag + b, fp.band_seq);
-				}
+				atomicExch(fp.band_flag + b, fp.band_seq);
 			}
 		}
 	}
-	__syncthreads(); // s_next is the next strip's; s_px may be overwritten
-	strip = s_next;
-	} // strips
+	batch = __shfl_sync(0xffffffffu, nxt, 0);
+	} // batches
+	__syncthreads();
 	if(threadIdx.x == 0)
 	{
-		// the last CTA to leave re-arms the counter pair for the next launch (every CTA's final fetch is behind it)
+		// the last CTA to leave re-arms the counter pair for the next launch (every warp's final fetch is behind it)
 		__threadfence();
 		if(atomicAdd(cursor + 1, 1u) == gridDim.x - 1u)
 		{
@@ -600,6 +608,8 @@ SKR_DEV void leaf_shade_round(const float4 *__restrict__ B, const SceneView &sv,
 	r2.sample = __shfl_sync(0xffffffffu, rng.sample, src);
 	r2.node	  = __shfl_sync(0xffffffffu, rng.node, src) * fp.node_base + (meta >> 21) + 1u;
 	r2.key	  = fp.key;
+	long long fx = 0, fy = 0, fz = 0;
+	unsigned fl = 0;
 	if(act)
 	{
 		// exactly the arithmetic of a queued leaf entry (queue_hit_point + the shade-only branch of shade_expand_kernel)
@@ -611,17 +621,35 @@ SKR_DEV void leaf_shade_round(const float4 *__restrict__ B, const SceneView &sv,
 		const float3 kd = f3(B[sv.off_diff + sidx]);
 		const float3 direct	 = direct_light<STATS, FOG, false>(B, sv, fp.shadows != 0, r2, sidx, hp, n, cnt);
 		const float3 contrib = f3(s1) * kd * (direct * 0.318309886183790672f);
-		unsigned fl			 = 0;
-		const long long x = to_fixed(contrib.x, fl, 0), y = to_fixed(contrib.y, fl, 1), z = to_fixed(contrib.z, fl, 2);
-		unsigned long long *a = ls.acc + 4 * src;
-		atomicAdd(a + 0, (unsigned long long) x);
-		atomicAdd(a + 1, (unsigned long long) y);
-		atomicAdd(a + 2, (unsigned long long) z);
-		if(fl)
-		{
-			atomicOr(a + 3, (unsigned long long) fl);
-		}
+		fl = 0;
+		fx = to_fixed(contrib.x, fl, 0), fy = to_fixed(contrib.y, fl, 1), fz = to_fixed(contrib.z, fl, 2);
 	}
+	// Fold the round into the parents' accumulators WITHOUT shared-memory atomics (64-bit ones are CAS loops, and a
+	// parent's leaves collide on one address): lanes holding leaves of the same parent find each other (MATCH.ANY on the
+	// parent lane), their fixed-point terms are summed exactly by integer warp reductions (REDUX.SUM) on 16 / 16 / 32-bit
+	// limbs -- v = c 2^32 + b 2^16 + a; at most 32 terms, so no limb sum overflows -- and the lowest lane of each group
+	// adds the total.  Groups hold distinct parents and rounds are sequential in the warp: plain read-modify-write.
+	const unsigned peers = __match_any_sync(0xffffffffu, act ? (unsigned) src : 64u + lane);
+	const auto group_sum = [&](long long v) -> long long {
+		const unsigned a = __reduce_add_sync(peers, (unsigned) ((unsigned long long) v & 0xffffull));
+		const unsigned b = __reduce_add_sync(peers, (unsigned) (((unsigned long long) v >> 16) & 0xffffull));
+		const int c		 = __reduce_add_sync(peers, (int) (v >> 32));
+		return (long long) (((unsigned long long) (long long) c << 32) + ((unsigned long long) b << 16) + (unsigned long long) a);
+	};
+	const long long sx = group_sum(fx), sy = group_sum(fy), sz = group_sum(fz);
+	const unsigned sfl = __reduce_or_sync(peers, fl);
+	if(act && lane == (unsigned) (__ffs(peers) - 1))
+	{
+		ulonglong2 *a	= reinterpret_cast<ulonglong2 *>(ls.acc + 4 * src);
+		ulonglong2 p = a[0], q = a[1];
+		p.x += (unsigned long long) sx;
+		p.y += (unsigned long long) sy;
+		q.x += (unsigned long long) sz;
+		q.y |= (unsigned long long) sfl;
+		a[0] = p;
+		a[1] = q;
+	}
+	__syncwarp();
 }
 
 // shade whole rounds of 32 while that many are pending; keep the rest at the front of the ring
