@@ -173,6 +173,7 @@ skr_scene_desc HostScene::desc() const
 	d.spheres  = spheres.data();
 	d.ntris	   = ntris();
 	d.tris	   = tris.data();
+	d.tri_materials = tri_materials.size() == 14 * (size_t) ntris() && ntris() > 0 ? tri_materials.data() : nullptr;
 	d.nplights = nplights();
 	d.plights  = plights.data();
 	d.ndlights = ndlights();
@@ -269,6 +270,11 @@ bool parse_scn(const std::string &path, HostScene &scene, std::string &error, co
 			{
 				const float *v = scene.vertices.data() + 3 * (size_t) f[k];
 				scene.tris.insert(scene.tris.end(), v, v + 3);
+			}
+			{
+				const float rec[14] = {mat.ambient[0], mat.ambient[1], mat.ambient[2], mat.diffuse[0], mat.diffuse[1], mat.diffuse[2], mat.specular[0],
+									   mat.specular[1], mat.specular[2], mat.transmissive[0], mat.transmissive[1], mat.transmissive[2], mat.power, mat.ior};
+				scene.tri_materials.insert(scene.tri_materials.end(), rec, rec + 14);
 			}
 		}
 		else if(strcmp(command, "camera") == 0)

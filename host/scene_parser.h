@@ -18,6 +18,8 @@ struct HostScene
 	std::vector<float> spheres;	 // 18 per sphere
 	std::vector<float> vertices; // 3 per vertex (parse-time pool, like Scene::vertices)
 	std::vector<float> tris;	 // 9 per triangle
+	std::vector<float> tri_materials; // 14 per triangle: the current material at the `triangle` line (src/scene.cpp:80);
+									  // the reference never reads it, the opt-in shaded-triangles mode does
 	std::vector<float> plights;	 // 6 per light
 	std::vector<float> dlights;	 // 6 per light (stays empty unless keep_directional, see below)
 	std::vector<float> fogs;	 // 9 per fog

@@ -11,7 +11,7 @@
 //   * use_shadows starts false (the reference leaves it uninitialised, src/main.cpp:244);
 //   * the 640x480 / depth 1 / no-jsample overrides of src/main.cpp:21-24 are not applied;
 //   * new flags: --seed n (replaces srand(time(0))), --gpu i, --gpus N (frame split over N GPUs, NCCL gather; 0 = all visible),
-//     --stats, --fresnel, --verbose, --no-fog;
+//     --stats, --fresnel, --shade-triangles (beyond the reference: triangles lit with their own materials), --keep-directional, --verbose, --no-fog;
 //   * a failing CUDA/library call prints the message and exits 1 (the reference never exits nonzero).
 #include <chrono>
 #include <cstdio>
@@ -150,6 +150,10 @@ int main(int argc, char *argv[])
 		{
 			opt.fresnel = 1;
 		}
+		if(strcmp(argv[i], "--shade-triangles") == 0) // non-parity extension: triangles lit with their own materials
+		{
+			opt.shade_triangles = 1;
+		}
 		if(strcmp(argv[i], "--verbose") == 0)
 		{
 			popt.verbose = true;
@@ -157,6 +161,10 @@ int main(int argc, char *argv[])
 		if(strcmp(argv[i], "--no-fog") == 0)
 		{
 			popt.fog = false;
+		}
+		if(strcmp(argv[i], "--keep-directional") == 0) // store the directional_light lines the reference parser drops (src/scene.cpp:139-163)
+		{
+			popt.keep_directional = true;
 		}
 	}
 	if(!path)

@@ -48,7 +48,8 @@ typedef enum skr_status
  *   spheres   [nspheres][18]  Sphere (src/shapes.h:12-24) = SphereCollider (src/SphereCollider.h:8-12)
  *                             + Material (src/material.h:9-26):
  *                             cx cy cz r | ambient rgb | diffuse rgb | specular rgb | transmissive rgb | power ior
- *   tris      [ntris][9]      Triangle (src/shapes.h:27-33) v0 v1 v2 (its material is never read, src/raytrace.h:221-224)
+ *   tris      [ntris][9]      Triangle (src/shapes.h:27-33) v0 v1 v2 (its material is never read by the reference,
+ *                             src/raytrace.h:221-224; see tri_materials below)
  *   plights   [nplights][6]   PointLight (src/lights.h:18-22) position xyz | colour rgb
  *   dlights   [ndlights][6]   DirectionalLight (src/lights.h:12-16) direction xyz | colour rgb
  *                             (the reference parser never stores any, src/scene.cpp:139-163)
@@ -73,6 +74,10 @@ typedef struct skr_scene_desc
 	float camera[12];
 	float ambient[3];
 	float background[3];
+	/* ABI 3, optional (may be NULL): the Material of every triangle, [ntris][14] = ambient rgb | diffuse rgb | specular rgb |
+	 * transmissive rgb | power ior (src/shapes.h:27-33, src/scene.cpp:67-81).  The reference never reads it; only the
+	 * opt-in shaded-triangles mode (skr_options.shade_triangles) does. */
+	const float *tri_materials;
 } skr_scene_desc;
 
 /* Mirror of the reference's `Options` (src/utils.h:26-39) plus the per-frame
@@ -97,6 +102,12 @@ typedef struct skr_options
 	int32_t tile;			/* tile edge in pixels; 0 = default (32) */
 	int32_t collect_stats;	/* nonzero: count rays/tests on the device (slower; not for timed runs) */
 	int32_t queue_capacity; /* entries (52 B each) per wavefront queue level; 0 = default: sized to the frame, 1 M .. 128 M */
+	/* ABI 3.  0 = behaviour of HEAD: any triangle hit shades black (src/raytrace.h:221-224).  1 = opt-in, explicitly
+	 * NON-PARITY extension: triangles are shaded with their own Material -- closest hit on the actual
+	 * (un-mirrored) triangle in front of the ray, geometric normal facing the ray, the Blinn-Phong terms of
+	 * src/blinn_phong.h:47-134, shadow rays stopped by triangles as well as spheres; fog is ignored.  Not combinable
+	 * with monte_carlo / fresnel (SKR_ERR_ARG). */
+	int32_t shade_triangles;
 } skr_options;
 
 typedef struct skr_stats

@@ -46,6 +46,9 @@ class Scene:
     camera: np.ndarray = field(default_factory=lambda: np.zeros(12, np.float32))
     ambient: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
     background: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+    # NOT part of the reference's render path: per-triangle materials (14 floats: ambient3 diffuse3 specular3
+    # transmissive3 power ior), read only by this repository's shaded-triangles extension (skr_oracle_ext.inc)
+    tri_materials: np.ndarray | None = None
 
     def normalised(self) -> "Scene":
         def a(x, shape):
@@ -53,7 +56,8 @@ class Scene:
 
         return Scene(a(self.spheres, (-1, 18)), a(self.tris, (-1, 9)), a(self.plights, (-1, 6)),
                      a(self.dlights, (-1, 6)), a(self.fogs, (-1, 9)), a(self.camera, (12,)),
-                     a(self.ambient, (3,)), a(self.background, (3,)))
+                     a(self.ambient, (3,)), a(self.background, (3,)),
+                     None if self.tri_materials is None else a(self.tri_materials, (-1, 14)))
 
     # ---- snapshot files (tests/golden/scenes/*.npz) ----
     def save(self, path: str) -> None:
@@ -79,20 +83,21 @@ class Options:
     grid_size: int = 0
     use_shadows: bool = False
     fresnel: bool = False
+    shade_triangles: bool = False  # NOT reference behaviour (this repository's extension)
 
 
 class _SkroScene(C.Structure):
     _fields_ = [("nspheres", C.c_int), ("spheres", _f32p), ("ntris", C.c_int), ("tris", _f32p),
                 ("nplights", C.c_int), ("plights", _f32p), ("ndlights", C.c_int), ("dlights", _f32p),
                 ("nfogs", C.c_int), ("fogs", _f32p), ("camera", C.c_float * 12), ("ambient", C.c_float * 3),
-                ("background", C.c_float * 3)]
+                ("background", C.c_float * 3), ("tri_materials", _f32p)]
 
 
 class _SkroOptions(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fov", C.c_float), ("max_depth", C.c_int),
                 ("monte_carlo", C.c_int), ("num_path_traces", C.c_int), ("grid_size", C.c_int),
                 ("use_shadows", C.c_int), ("fresnel", C.c_int), ("rng_mode", C.c_int), ("seed", C.c_uint64),
-                ("threads", C.c_int), ("y0", C.c_int), ("y1", C.c_int)]
+                ("threads", C.c_int), ("y0", C.c_int), ("y1", C.c_int), ("shade_triangles", C.c_int)]
 
 
 class SkroStats(C.Structure):
@@ -154,13 +159,14 @@ class Port:
         cs.camera[:] = s.camera.tolist()
         cs.ambient[:] = s.ambient.tolist()
         cs.background[:] = s.background.tolist()
+        cs.tri_materials = _fp(s.tri_materials) if s.tri_materials is not None and len(s.tri_materials) == len(s.tris) else None
         return cs, s  # keep `s` alive
 
     @staticmethod
     def _opts(o: Options, rng_mode, seed, threads, y0, y1):
         return _SkroOptions(o.width, o.height, o.fov, o.max_depth, int(o.monte_carlo), o.num_path_traces,
                             o.grid_size, int(o.use_shadows), int(o.fresnel), rng_mode, seed, threads,
-                            0 if y0 is None else y0, o.height if y1 is None else y1)
+                            0 if y0 is None else y0, o.height if y1 is None else y1, int(o.shade_triangles))
 
     def max_threads(self) -> int:
         return int(self.lib.skro_max_threads())

@@ -645,6 +645,8 @@ static vec3 shade(ctx_t *c, vec3 o, vec3 d, int depth, uint32_t node)
 	return v3(0, 0, 0); /* any triangle hit shades black, src/raytrace.h:221-224 */
 }
 
+#include "skr_oracle_ext.inc" /* NOT reference behaviour: this repository's shaded-triangles extension */
+
 /* ---------------------------------------------------------- frame loop ---- */
 
 static void ctx_init(ctx_t *c, const skro_scene *scene, const skro_options *opt)
@@ -714,7 +716,7 @@ double skro_render(const skro_scene *scene, const skro_options *opt, float *rgb3
 							float u		= (2 * ((x + r) * inv_width) - 1) * angle * aspect_ratio;
 							float v		= (1 - 2 * ((y + r) * inv_height)) * angle;
 							vec3 ray_dir = add(add(cam_dir, muls(cam_right, u)), muls(cam_up, v)); /* never normalised, SURVEY F8 */
-							px			 = add(px, shade(&c, cam_pos, ray_dir, opt->max_depth, 0));
+							px			 = add(px, opt->shade_triangles ? shade_ext(&c, cam_pos, ray_dir, opt->max_depth) : shade(&c, cam_pos, ray_dir, opt->max_depth, 0));
 						}
 					}
 					px = divs(px, (float) (opt->grid_size * opt->grid_size));
@@ -725,7 +727,7 @@ double skro_render(const skro_scene *scene, const skro_options *opt, float *rgb3
 					float u		 = (float) ((2 * ((x + 0.5) * inv_width) - 1) * angle * aspect_ratio);
 					float v		 = (float) ((1 - 2 * ((y + 0.5) * inv_height)) * angle);
 					vec3 ray_dir = add(add(cam_dir, muls(cam_right, u)), muls(cam_up, v));
-					px			 = shade(&c, cam_pos, ray_dir, opt->max_depth, 0);
+					px			 = opt->shade_triangles ? shade_ext(&c, cam_pos, ray_dir, opt->max_depth) : shade(&c, cam_pos, ray_dir, opt->max_depth, 0);
 				}
 				st3(image + 3 * ((size_t) y * width + x), px);
 			}

@@ -42,6 +42,8 @@ typedef struct skro_scene
 	float camera[12];  /* position | direction | up | right (none normalised) */
 	float ambient[3];
 	float background[3];
+	const float *tri_materials; /* optional, 14 floats per triangle (ambient3 diffuse3 specular3 transmissive3 power ior): read ONLY by
+								   the non-reference shaded-triangles extension (skr_oracle_ext.inc) */
 } skro_scene;
 
 enum
@@ -64,6 +66,7 @@ typedef struct skro_options
 	uint64_t seed;
 	int threads;
 	int y0, y1; /* row window [y0,y1) */
+	int shade_triangles; /* NOT reference behaviour: this repository's extension, see skr_oracle_ext.inc */
 } skro_options;
 
 typedef struct skro_stats

@@ -41,7 +41,7 @@ class _SceneDesc(C.Structure):
     _fields_ = [("nspheres", C.c_int32), ("spheres", _f32p), ("ntris", C.c_int32), ("tris", _f32p),
                 ("nplights", C.c_int32), ("plights", _f32p), ("ndlights", C.c_int32), ("dlights", _f32p),
                 ("nfogs", C.c_int32), ("fogs", _f32p), ("camera", C.c_float * 12), ("ambient", C.c_float * 3),
-                ("background", C.c_float * 3)]
+                ("background", C.c_float * 3), ("tri_materials", _f32p)]
 
 
 class _Options(C.Structure):
@@ -49,7 +49,7 @@ class _Options(C.Structure):
                 ("monte_carlo", C.c_int32), ("num_path_traces", C.c_int32), ("grid_size", C.c_int32),
                 ("use_shadows", C.c_int32), ("fresnel", C.c_int32), ("seed", C.c_uint64), ("rank", C.c_int32),
                 ("world", C.c_int32), ("tile", C.c_int32), ("collect_stats", C.c_int32),
-                ("queue_capacity", C.c_int32)]
+                ("queue_capacity", C.c_int32), ("shade_triangles", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -76,6 +76,7 @@ class Scene:
     camera: np.ndarray = field(default_factory=lambda: np.zeros(12, np.float32))
     ambient: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
     background: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+    tri_materials: np.ndarray | None = None  # [ntris][14], only read by the shaded-triangles mode (see skr.h)
 
     def _norm(self) -> "Scene":
         def a(x, shape):
@@ -83,7 +84,7 @@ class Scene:
 
         return Scene(a(self.spheres, (-1, 18)), a(self.tris, (-1, 9)), a(self.plights, (-1, 6)),
                      a(self.dlights, (-1, 6)), a(self.fogs, (-1, 9)), a(self.camera, (12,)), a(self.ambient, (3,)),
-                     a(self.background, (3,)))
+                     a(self.background, (3,)), None if self.tri_materials is None else a(self.tri_materials, (-1, 14)))
 
     def _desc(self):
         s = self._norm()
@@ -93,6 +94,8 @@ class Scene:
         d.camera[:] = s.camera.tolist()
         d.ambient[:] = s.ambient.tolist()
         d.background[:] = s.background.tolist()
+        if s.tri_materials is not None and len(s.tri_materials) == len(s.tris) and len(s.tris):
+            d.tri_materials = s.tri_materials.ctypes.data_as(_f32p)
         return d, s
 
     def save(self, path: str) -> None:
@@ -127,11 +130,12 @@ class Options:
     tile: int = 0
     collect_stats: bool = False
     queue_capacity: int = 0
+    shade_triangles: bool = False  # opt-in NON-PARITY extension: triangles shaded with their own materials (skr.h)
 
     def _c(self) -> _Options:
         return _Options(self.width, self.height, self.fov, self.max_depth, int(self.monte_carlo), self.num_path_traces,
                         self.grid_size, int(self.use_shadows), int(self.fresnel), self.seed, self.rank, self.world,
-                        self.tile, int(self.collect_stats), self.queue_capacity)
+                        self.tile, int(self.collect_stats), self.queue_capacity, int(self.shade_triangles))
 
 
 _host = None
@@ -173,7 +177,8 @@ def parseScene(fileName: str, keep_directional: bool = False, fog: bool = True) 
 
         s = Scene(arr(d.spheres, d.nspheres, 18), arr(d.tris, d.ntris, 9), arr(d.plights, d.nplights, 6),
                   arr(d.dlights, d.ndlights, 6), arr(d.fogs, d.nfogs, 9), np.array(d.camera[:], np.float32),
-                  np.array(d.ambient[:], np.float32), np.array(d.background[:], np.float32))
+                  np.array(d.ambient[:], np.float32), np.array(d.background[:], np.float32),
+                  arr(d.tri_materials, d.ntris, 14) if d.tri_materials and d.ntris else None)
         s.film_resolution = (cnt[5], cnt[6])
         s.max_depth = cnt[7]
         s.unknown_commands = cnt[8]

@@ -20,6 +20,7 @@
 #include "skr_bvh_build.cuh"
 #include "skr_kernels.cuh"
 #include "skr_micro.cuh"
+#include "skr_shaded.cuh"
 
 namespace
 {
@@ -55,6 +56,33 @@ struct BvhGraphKey // compared with memcmp: no padding
 	const void *tris_raw, *tri_v, *bvh, *scratch;
 };
 
+// One triangle hierarchy: the triangles in LBVH leaf order, the nodes, the outsized-triangle list and the CUDA graph that
+// replays its build.  A context holds two: over the MIRRORED triangles for the reference's line any-hit query, and --
+// built on first use -- over the actual triangles for the opt-in shaded-triangles mode.
+struct BvhSet
+{
+	float4 *d_tri_v = nullptr;
+	float4 *d_bvh	= nullptr;
+	float4 *d_big	= nullptr; // BIG_TRI_CAP x 3 float4 + the int counter behind them
+	size_t tri_v_bytes = 0, bvh_bytes = 0;
+	BvhGraphKey graph_key{};
+	cudaGraphExec_t graph = nullptr;
+	bool graph_broken	  = false; // capture failed once: direct launches from then on
+	const float4 *bvh	  = nullptr; // result: nodes, or null = test every triangle (a handful, or SKR_NO_BVH=1)
+	bool valid			  = false;
+
+	void release()
+	{
+		cudaFree(d_tri_v), cudaFree(d_bvh), cudaFree(d_big);
+		if(graph)
+		{
+			cudaGraphExecDestroy(graph);
+		}
+		d_tri_v = d_bvh = d_big = nullptr;
+		graph					= nullptr;
+	}
+};
+
 struct skr_ctx
 {
 	int device = 0;
@@ -67,10 +95,12 @@ struct skr_ctx
 	SceneView sv{};
 	float4 *d_blob = nullptr;
 	float *d_tris_raw = nullptr;
-	float4 *d_tri_v = nullptr;
-	float4 *d_bvh = nullptr;
-	float4 *d_big = nullptr; // BIG_TRI_CAP x 3 float4 + the int counter behind them
-	size_t blob_bytes = 0, tris_raw_bytes = 0, tri_v_bytes = 0, bvh_bytes = 0, scratch_bytes = 0;
+	BvhSet bvh_main, bvh_shade;
+	float4 *d_tri_mat = nullptr; // 3 float4 per triangle (original order): (ambient (.) ka, power), (kd, ior), (ks, 0); shaded-triangles mode
+	size_t tri_mat_bytes = 0;
+	bool have_tri_mat = false;
+	int n_tris = 0;
+	size_t blob_bytes = 0, tris_raw_bytes = 0, scratch_bytes = 0;
 	char *d_scratch = nullptr; // LBVH build scratch, kept between uploads
 	size_t smem_bytes = 0;
 
@@ -108,11 +138,6 @@ struct skr_ctx
 	unsigned long long band_geom = 0; // geometry the band counters were last reset for
 	CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned) = nullptr;
 	CUresult (*write_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned) = nullptr;
-
-	// LBVH build replayed as a CUDA graph (build_bvh)
-	BvhGraphKey bvh_graph_key{};
-	cudaGraphExec_t bvh_graph = nullptr;
-	bool bvh_graph_broken = false; // capture failed once: direct launches from then on
 
 	unsigned launches = 0, chunks = 0;
 	bool async_pending = false; // a fire-and-forget frame was enqueued since the error word was last read
@@ -214,33 +239,44 @@ void launch_primary(skr_ctx *ctx, const FrameParams &fp, const Queue &q, long lo
 	const SceneView &sv = ctx->sv;
 	cudaStream_t st		= ctx->stream;
 	const size_t sm		= ctx->smem_bytes;
-	// persistent: one wave of CTAs whose warps pull batches of 8 x 4 pixel blocks from ctx->d_cursor (see primary_kernel)
+	// one 8 x 4 pixel block per warp.  CTAs of one warp for BVH scenes (per-block cost varies ~100x between sky and mesh: the
+	// hardware refills a finished warp's slot at once), four warps otherwise; SKR_PRIMARY_BLOCK overrides (A/B runs).
+	int threads = (!GI && sv.bvh != nullptr) ? 32 : SKR_BLOCK;
+	if(const char *e = getenv("SKR_PRIMARY_BLOCK"))
+	{
+		const int v = atoi(e);
+		if(v == 32 || v == 64 || v == 128)
+		{
+			threads = v;
+		}
+	}
+	const long long wpc		= threads / 32;
 	const long long batches = ((n + 31) / 32 + fp.fetch - 1) / fp.fetch;
-	const long long need	= (batches + SKR_BLOCK / 32 - 1) / (SKR_BLOCK / 32);
+	const long long need	= (batches + wpc - 1) / wpc;
 	const long long wave	= (long long) ctx->sm_count * SKR_MIN_BLOCKS;
-	const unsigned blocks	= (unsigned) (need < wave ? need : wave);
+	const unsigned blocks	= (unsigned) ((SKR_PRIMARY_MODE == 1 && need > wave) ? wave : need);
 	unsigned *cur		   = ctx->d_cursor;
 	if(!sv.blob_in_smem)
 	{
-		primary_kernel<GI, STATS, false, true, true><<<blocks, SKR_BLOCK, 0, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, false, true, true><<<blocks, threads, 0, st>>>(sv, fp, q, lp0, n, cur);
 		return;
 	}
 	const bool tris = sv.T > 0, fog = sv.F > 0;
 	if(tris && fog)
 	{
-		primary_kernel<GI, STATS, true, true, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, true, true, true><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n, cur);
 	}
 	else if(tris)
 	{
-		primary_kernel<GI, STATS, true, true, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, true, true, false><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n, cur);
 	}
 	else if(fog)
 	{
-		primary_kernel<GI, STATS, true, false, true><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, true, false, true><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n, cur);
 	}
 	else
 	{
-		primary_kernel<GI, STATS, true, false, false><<<blocks, SKR_BLOCK, sm, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, true, false, false><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n, cur);
 	}
 }
 
@@ -302,9 +338,13 @@ cudaError_t smem_attr_one(int bytes)
 	{
 		e = cudaFuncSetAttribute(shade_expand_kernel<STATS, true, TRIS, FOG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + SKR_LEAF_CTA_BYTES);
 	}
-	if(e == cudaSuccess && GI && TRIS && FOG) // once per STATS: the fresnel pass has no (TRIS, FOG) variants
+	if(e == cudaSuccess && GI && TRIS && FOG) // once per STATS: these have no (TRIS, FOG) variants
 	{
 		e = cudaFuncSetAttribute(fresnel_expand_kernel<STATS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+		if(e == cudaSuccess)
+		{
+			e = cudaFuncSetAttribute(shaded_tris_kernel<STATS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+		}
 	}
 	return e;
 }
@@ -334,35 +374,36 @@ int set_smem_attr(skr_ctx *ctx)
 	return SKR_OK;
 }
 
-int build_bvh(skr_ctx *ctx, int T)
+// Builds `set` over the ctx->d_tris_raw triangles: mirrored (reference query) or actual (shaded-triangles mode).
+// Leaves the count of outsized triangles in ctx->h_count once the stream has drained.
+int build_bvh(skr_ctx *ctx, int T, BvhSet &set, bool mirror)
 {
 	using namespace bvhb;
 	cudaStream_t st = ctx->stream;
 	const int B		= 256;
 	const int gridT = (T + B - 1) / B;
+	set.valid		= false;
+	set.bvh			= nullptr;
 	// persistent buffers grow on demand and are reused by later uploads (an e2e loop re-uploads the same scene)
-	CK(ensure(ctx->d_tri_v, ctx->tri_v_bytes, sizeof(float4) * 3 * (size_t) T));
+	CK(ensure(set.d_tri_v, set.tri_v_bytes, sizeof(float4) * 3 * (size_t) T));
 	const char *nobvh = getenv("SKR_NO_BVH");
 	// a handful of triangles (spheres1.scn has two): testing them all costs less per ray than a node visit, and the
 	// ~27 dependent launches of the build would dominate the upload (0.21 ms against 0.03 ms)
 	if((nobvh && nobvh[0] == '1') || T <= BRUTE_FORCE_TRIS)
 	{
-		iota_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, ctx->d_tri_v);
+		iota_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, set.d_tri_v);
 		CK(cudaGetLastError());
-		ctx->sv.bvh				 = nullptr;
-		ctx->sv.bvh_root_is_leaf = 0;
-		ctx->sv.nbig			 = 0;
-		*ctx->h_count			 = 0;
+		*ctx->h_count = 0;
+		set.valid	  = true;
 		return SKR_OK;
 	}
-	if(!ctx->d_big)
+	if(!set.d_big)
 	{
-		CK(cudaMalloc(&ctx->d_big, sizeof(float4) * 3 * BIG_TRI_CAP + 256));
+		CK(cudaMalloc(&set.d_big, sizeof(float4) * 3 * BIG_TRI_CAP + 256));
 	}
-	int *big_count	  = reinterpret_cast<int *>(ctx->d_big + 3 * BIG_TRI_CAP);
+	int *big_count	  = reinterpret_cast<int *>(set.d_big + 3 * BIG_TRI_CAP);
 	const int big_cap = T >= BIG_TRI_MIN_T ? BIG_TRI_CAP : 0;
-	ctx->sv.big_v	  = ctx->d_big;
-	CK(ensure(ctx->d_bvh, ctx->bvh_bytes, sizeof(float4) * 4 * (size_t) (T - 1)));
+	CK(ensure(set.d_bvh, set.bvh_bytes, sizeof(float4) * 4 * (size_t) (T - 1)));
 	const int nwarps  = (T + SORT_ITEMS_PER_WARP - 1) / SORT_ITEMS_PER_WARP;
 	const int sblocks = (nwarps + SORT_WARPS - 1) / SORT_WARPS;
 
@@ -393,27 +434,27 @@ int build_bvh(skr_ctx *ctx, int T)
 
 	// The build is ~30 small dependent launches: launch-bound.  It is captured once into a CUDA graph and replayed while
 	// the triangle count and the buffers stay the same (an e2e loop re-uploads the same scene every frame).
-	const BvhGraphKey key{T, ctx->d_tris_raw, ctx->d_tri_v, ctx->d_bvh, ctx->d_scratch};
+	const BvhGraphKey key{T, ctx->d_tris_raw, set.d_tri_v, set.d_bvh, ctx->d_scratch};
 	const char *nograph = getenv("SKR_NO_GRAPH");
 	const bool use_graph = !(nograph && nograph[0] == '1');
-	if(use_graph && ctx->bvh_graph && memcmp(&key, &ctx->bvh_graph_key, sizeof key) == 0)
+	if(use_graph && set.graph && memcmp(&key, &set.graph_key, sizeof key) == 0)
 	{
-		CK(cudaGraphLaunch(ctx->bvh_graph, st));
-		CK(cudaMemcpyAsync(ctx->h_count, big_count, sizeof(int), cudaMemcpyDeviceToHost, st)); // read after the upload's sync
-		ctx->sv.bvh				 = ctx->d_bvh;
-		ctx->sv.bvh_root_is_leaf = 0;
+		CK(cudaGraphLaunch(set.graph, st));
+		CK(cudaMemcpyAsync(ctx->h_count, big_count, sizeof(int), cudaMemcpyDeviceToHost, st)); // read after the caller's sync
+		set.bvh	  = set.d_bvh;
+		set.valid = true;
 		return SKR_OK;
 	}
-	if(ctx->bvh_graph)
+	if(set.graph)
 	{
-		cudaGraphExecDestroy(ctx->bvh_graph);
-		ctx->bvh_graph = nullptr;
+		cudaGraphExecDestroy(set.graph);
+		set.graph = nullptr;
 	}
 	const auto enqueue_build = [&]() {
 		init_scene_box_kernel<<<1, 32, 0, st>>>(scene_box);
 		cudaMemsetAsync(big_count, 0, sizeof(int), st);
-		tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box);
-		morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0], ctx->d_tris_raw, big_count, ctx->d_big, big_cap);
+		tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box, mirror ? 1 : 0);
+		morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0], ctx->d_tris_raw, big_count, set.d_big, big_cap);
 		int cur = 0;
 		for(int pass = 0; pass < 8; pass++)
 		{
@@ -425,29 +466,29 @@ int build_bvh(skr_ctx *ctx, int T)
 		}
 		cudaMemsetAsync(flags, 0, sizeof(int) * T, st);
 		karras_kernel<<<gridT, B, 0, st>>>(keys[cur], T, children, parent);
-		refit_kernel<<<gridT, B, 0, st>>>(T, vals[cur], box_lo, box_hi, children, parent, node_lo, node_hi, flags, ctx->d_bvh);
-		gather_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, vals[cur], T, ctx->d_tri_v);
+		refit_kernel<<<gridT, B, 0, st>>>(T, vals[cur], box_lo, box_hi, children, parent, node_lo, node_hi, flags, set.d_bvh);
+		gather_tris_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, vals[cur], T, set.d_tri_v);
 	};
 	bool launched = false;
-	if(use_graph && !ctx->bvh_graph_broken && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
+	if(use_graph && !set.graph_broken && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
 	{
 		enqueue_build();
 		cudaGraph_t g = nullptr;
-		if(cudaStreamEndCapture(st, &g) == cudaSuccess && g && cudaGraphInstantiate(&ctx->bvh_graph, g, 0) == cudaSuccess &&
-		   cudaGraphLaunch(ctx->bvh_graph, st) == cudaSuccess)
+		if(cudaStreamEndCapture(st, &g) == cudaSuccess && g && cudaGraphInstantiate(&set.graph, g, 0) == cudaSuccess &&
+		   cudaGraphLaunch(set.graph, st) == cudaSuccess)
 		{
-			ctx->bvh_graph_key = key;
-			launched		   = true;
+			set.graph_key = key;
+			launched	  = true;
 		}
 		else
 		{
 			// capture / instantiation not possible here: launch the kernels one by one, now and from now on
-			if(ctx->bvh_graph)
+			if(set.graph)
 			{
-				cudaGraphExecDestroy(ctx->bvh_graph);
-				ctx->bvh_graph = nullptr;
+				cudaGraphExecDestroy(set.graph);
+				set.graph = nullptr;
 			}
-			ctx->bvh_graph_broken = true;
+			set.graph_broken = true;
 			cudaGetLastError();
 		}
 		if(g)
@@ -460,9 +501,29 @@ int build_bvh(skr_ctx *ctx, int T)
 		enqueue_build();
 	}
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(ctx->h_count, big_count, sizeof(int), cudaMemcpyDeviceToHost, st)); // read after the upload's sync
-	ctx->sv.bvh				 = ctx->d_bvh;
-	ctx->sv.bvh_root_is_leaf = 0;
+	CK(cudaMemcpyAsync(ctx->h_count, big_count, sizeof(int), cudaMemcpyDeviceToHost, st)); // read after the caller's sync
+	set.bvh	  = set.d_bvh;
+	set.valid = true;
+	return SKR_OK;
+}
+
+// The hierarchy over the ACTUAL triangles (shaded-triangles mode), built the first time a frame asks for it.
+int ensure_shade_bvh(skr_ctx *ctx)
+{
+	if(ctx->n_tris <= 0 || ctx->bvh_shade.valid)
+	{
+		return SKR_OK;
+	}
+	int rc = build_bvh(ctx, ctx->n_tris, ctx->bvh_shade, false);
+	if(rc)
+	{
+		return rc;
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->sv.tri_v2 = ctx->bvh_shade.d_tri_v;
+	ctx->sv.bvh2   = ctx->bvh_shade.bvh;
+	ctx->sv.big_v2 = ctx->bvh_shade.d_big;
+	ctx->sv.nbig2  = ctx->bvh_shade.bvh ? std::min((int) *ctx->h_count, BIG_TRI_CAP) : 0;
 	return SKR_OK;
 }
 
@@ -508,6 +569,7 @@ struct Plan
 	long long npix_local; // local pixels incl. padding (tiles_local * tile^2)
 	long long tiles_local;
 	int levels;		  // depth levels of the --gillum / fresnel tree (0: none)
+	bool shaded;	  // opt-in shaded-triangles mode (skr_shaded.cuh)
 	int qlevels;	  // queue levels needed: `levels`, or one less when the leaves are shaded in place
 	bool leaf_inline; // depth-1 hits are shaded by the warp that found them (shade_expand_kernel<..., LEAF>)
 };
@@ -530,6 +592,11 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	{
 		return fail(ctx, SKR_ERR_ARG, "skr_options: frame too large");
 	}
+	if(o->shade_triangles && (o->monte_carlo || o->fresnel))
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_options: shade_triangles (a non-parity extension) is not combined with monte_carlo / fresnel");
+	}
+	pl.shaded		= o->shade_triangles != 0;
 	const int world = o->world > 1 ? o->world : 1;
 	const int rank	= o->world > 1 ? o->rank : 0;
 	if(rank < 0 || rank >= world)
@@ -578,7 +645,7 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		fp.cull = (sv.off_cull >= 0 && fp.grid > 0 && fp.spp >= 4 && !(nocull && nocull[0] == '1') && std::isfinite(fp.cull_delta)) ? 1 : 0;
 	}
 	// blocks a warp takes per fetch: one where a block is long (jittered samples, BVH traversal), four where pixels are cheap
-	fp.fetch	 = (fp.spp >= 4 || ctx->sv.T > BRUTE_FORCE_TRIS) ? 1 : 4;
+	fp.fetch	 = SKR_PRIMARY_MODE == 1 ? ((fp.spp >= 4 || ctx->sv.T > BRUTE_FORCE_TRIS) ? 1 : 4) : 1;
 	fp.node_base = (uint32_t) fp.n_gi + 1u + (fp.fresnel ? 2u * (uint32_t) (ctx->sv.L + ctx->sv.D) : 0u);
 	fp.slot_gi	 = 1u + (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
 	pl.tiles_local = (fp.tiles_total + world - 1) / world;
@@ -742,6 +809,10 @@ int process_level(skr_ctx *ctx, const Plan &pl, int level, unsigned count, int d
 int prepare_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 {
 	FrameParams &fp = pl.fp;
+	if(pl.shaded)
+	{
+		return ensure_shade_bvh(ctx);
+	}
 	if(!((fp.gi || fp.fresnel) && pl.levels > 0))
 	{
 		return SKR_OK;
@@ -792,6 +863,23 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	FrameParams &fp = pl.fp;
 	cudaStream_t st = ctx->stream;
 	const bool tree = fp.gi || fp.fresnel;
+	if(pl.shaded)
+	{
+		span_begin(ctx, CAT_PRIMARY);
+		const unsigned blocks = (unsigned) ((pl.npix_local + SKR_BLOCK - 1) / SKR_BLOCK);
+		if(ctx->sv.blob_in_smem)
+		{
+			shaded_tris_kernel<STATS, true><<<blocks, SKR_BLOCK, ctx->smem_bytes, st>>>(ctx->sv, fp, pl.npix_local);
+		}
+		else
+		{
+			shaded_tris_kernel<STATS, false><<<blocks, SKR_BLOCK, 0, st>>>(ctx->sv, fp, pl.npix_local);
+		}
+		span_end(ctx);
+		ctx->launches++;
+		CK(cudaGetLastError());
+		return SKR_OK;
+	}
 	if(!tree || pl.levels == 0)
 	{
 		span_begin(ctx, CAT_PRIMARY);
@@ -871,7 +959,8 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	{
 		// whole 8 x 4 pixel blocks leave as 32-bit words when their rows start on word boundaries
 		const auto al4 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0u; };
-		bool ok		   = pl.fp.width % 4 == 0 && al4(pl.fp.rgb8);
+		// (only frames bound for another device or the host: byte stores into the local L2 cost nothing, the staging does)
+		bool ok		   = pl.fp.n_peers > 0 && pl.fp.width % 4 == 0 && al4(pl.fp.rgb8);
 		for(int k = 0; k < pl.fp.n_peers; k++)
 		{
 			ok = ok && al4(pl.fp.peers[k]);
@@ -1079,18 +1168,16 @@ void skr_destroy(skr_ctx *ctx)
 	{
 		cudaStreamSynchronize(ctx->stream);
 	}
-	cudaFree(ctx->d_blob), cudaFree(ctx->d_tris_raw), cudaFree(ctx->d_tri_v), cudaFree(ctx->d_bvh), cudaFree(ctx->d_scratch);
+	cudaFree(ctx->d_blob), cudaFree(ctx->d_tris_raw), cudaFree(ctx->d_scratch), cudaFree(ctx->d_tri_mat);
+	ctx->bvh_main.release();
+	ctx->bvh_shade.release();
 	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
 	cudaFree(ctx->d_arena);
 	cudaFree(ctx->d_cursor);
-	cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band), cudaFree(ctx->d_big);
+	cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band);
 	if(ctx->copy_stream)
 	{
 		cudaStreamDestroy(ctx->copy_stream);
-	}
-	if(ctx->bvh_graph)
-	{
-		cudaGraphExecDestroy(ctx->bvh_graph);
 	}
 	if(ctx->h_count)
 	{
@@ -1351,19 +1438,42 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 
 	sv.tri_v = nullptr;
 	sv.bvh	 = nullptr;
+	ctx->n_tris			 = T;
+	ctx->bvh_shade.valid = false; // rebuilt by the first shaded-triangles frame of this scene
+	ctx->have_tri_mat	 = false;
+	std::vector<float4> tmat;
 	if(T > 0)
 	{
 		CK(ensure(ctx->d_tris_raw, ctx->tris_raw_bytes, sizeof(float) * 9 * (size_t) T));
 		CK(cudaMemcpyAsync(ctx->d_tris_raw, sc->tris, sizeof(float) * 9 * (size_t) T, cudaMemcpyHostToDevice, ctx->stream));
-		rc = build_bvh(ctx, T);
+		rc = build_bvh(ctx, T, ctx->bvh_main, true);
 		if(rc)
 		{
 			return rc;
 		}
-		sv.tri_v = ctx->d_tri_v;
+		sv.tri_v = ctx->bvh_main.d_tri_v;
+		sv.bvh	 = ctx->bvh_main.bvh;
+		sv.big_v = ctx->bvh_main.d_big;
+		if(sc->tri_materials)
+		{
+			// (ambient_light (.) ka, power), (kd, ior), (ks, 0) per triangle, original order (shaded-triangles mode only)
+			tmat.resize(3 * (size_t) T);
+			for(int t = 0; t < T; t++)
+			{
+				const float *m		= sc->tri_materials + 14 * (size_t) t;
+				tmat[3 * t + 0]		= make_float4(sc->ambient[0] * m[0], sc->ambient[1] * m[1], sc->ambient[2] * m[2], m[12]);
+				tmat[3 * t + 1]		= make_float4(m[3], m[4], m[5], m[13]);
+				tmat[3 * t + 2]		= make_float4(m[6], m[7], m[8], 0.0f);
+			}
+			CK(ensure(ctx->d_tri_mat, ctx->tri_mat_bytes, sizeof(float4) * tmat.size()));
+			CK(cudaMemcpyAsync(ctx->d_tri_mat, tmat.data(), sizeof(float4) * tmat.size(), cudaMemcpyHostToDevice, ctx->stream));
+			ctx->have_tri_mat = true;
+		}
 	}
+	sv.tri_mat	= ctx->have_tri_mat ? ctx->d_tri_mat : nullptr;
+	sv.tris_raw = T > 0 ? ctx->d_tris_raw : nullptr;
 	CK(cudaStreamSynchronize(ctx->stream));
-	sv.nbig			= T > 0 ? std::min((int) *ctx->h_count, BIG_TRI_CAP) : 0;
+	sv.nbig			= (T > 0 && sv.bvh) ? std::min((int) *ctx->h_count, BIG_TRI_CAP) : 0;
 	ctx->have_scene = true;
 	return SKR_OK;
 }
@@ -1470,7 +1580,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 			return a.type == cudaMemoryTypeHost;
 		};
 		// (worth its ~0.04 ms of extra stream operations only when the kernel is long against the copy: jittered frames)
-		if(ctx->wait_value32 && pl.levels == 0 && fp.world == 1 && fp.spp >= 4 && tpix % SKR_BLOCK == 0 && npx * 3 >= (1u << 20) && !(no && no[0] == '1') &&
+		if(ctx->wait_value32 && pl.levels == 0 && !pl.shaded && fp.world == 1 && fp.spp >= 4 && tpix % SKR_BLOCK == 0 && npx * 3 >= (1u << 20) && !(no && no[0] == '1') &&
 		   (!rgb8 || pinned(rgb8)) && (!rgb32 || pinned(rgb32)) && (rgb8 || rgb32))
 		{
 			const int tile_rows = (opt->height + fp.tile - 1) / fp.tile;

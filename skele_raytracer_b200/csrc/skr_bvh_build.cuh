@@ -1,6 +1,7 @@
 // skr_bvh_build.cuh -- device-side LBVH construction at scene upload.
 //
-//   1. tri_bounds_kernel   : bounds of each MIRRORED triangle (v0, 2*v0-v1, v2) (see skr_bvh.cuh), slightly inflated,
+//   1. tri_bounds_kernel   : bounds of each MIRRORED triangle (v0, 2*v0-v1, v2) (see skr_bvh.cuh) -- or of the triangle
+//                            itself for the shaded-triangles hierarchy --, slightly inflated,
 //                            and the scene bounds (block reduce in shared memory + float atomics).
 //   2. morton_kernel       : 63-bit Morton code (21 bits/axis) of each box centre.  30-bit codes are not enough:
 //                            dragon.scn's ground quad stretches the scene box to +-20 while the model is 0.2 wide.
@@ -59,7 +60,7 @@ __global__ void init_scene_box_kernel(float *scene_box) // (min.xyz, max.xyz) = 
 }
 
 // tris: [T][9] floats as uploaded.  box_lo/box_hi: float4 per triangle.  scene_box: 6 floats (lo, hi), pre-set to +-FLT_MAX.
-__global__ void tri_bounds_kernel(const float *__restrict__ tris, int T, float4 *__restrict__ box_lo, float4 *__restrict__ box_hi, float *scene_box)
+__global__ void tri_bounds_kernel(const float *__restrict__ tris, int T, float4 *__restrict__ box_lo, float4 *__restrict__ box_hi, float *scene_box, int mirror)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	float3 lo = f3(3.0e38f, 3.0e38f, 3.0e38f), hi = f3(-3.0e38f, -3.0e38f, -3.0e38f);
@@ -67,7 +68,8 @@ __global__ void tri_bounds_kernel(const float *__restrict__ tris, int T, float4 
 	{
 		const float *t	= tris + 9 * (size_t) i;
 		const float3 v0 = f3(t[0], t[1], t[2]), v1 = f3(t[3], t[4], t[5]), v2 = f3(t[6], t[7], t[8]);
-		const float3 m1 = f3(2.0f * v0.x - v1.x, 2.0f * v0.y - v1.y, 2.0f * v0.z - v1.z); // mirrored vertex
+		// mirrored vertex (the reference's query, skr_bvh.cuh), or the vertex itself (shaded-triangles mode)
+		const float3 m1 = mirror ? f3(2.0f * v0.x - v1.x, 2.0f * v0.y - v1.y, 2.0f * v0.z - v1.z) : v1;
 		lo				= f3(fminf(fminf(v0.x, m1.x), v2.x), fminf(fminf(v0.y, m1.y), v2.y), fminf(fminf(v0.z, m1.z), v2.z));
 		hi				= f3(fmaxf(fmaxf(v0.x, m1.x), v2.x), fmaxf(fmaxf(v0.y, m1.y), v2.y), fmaxf(fmaxf(v0.z, m1.z), v2.z));
 		// inflate: the reference's float u/v window can accept points a few ulps outside the exact triangle
@@ -155,7 +157,7 @@ __global__ void morton_kernel(float4 *box_lo, float4 *box_hi, const float *__res
 			if(slot < big_cap)
 			{
 				const float *t		= tris + 9 * (size_t) i;
-				big_v[3 * slot + 0] = make_float4(t[0], t[1], t[2], 0.0f);
+				big_v[3 * slot + 0] = make_float4(t[0], t[1], t[2], __int_as_float(i)); // w: original triangle index
 				big_v[3 * slot + 1] = make_float4(t[3], t[4], t[5], 0.0f);
 				big_v[3 * slot + 2] = make_float4(t[6], t[7], t[8], 0.0f);
 				box_lo[i] = box_hi[i] = make_float4(cx, cy, cz, 0.0f);
@@ -444,7 +446,7 @@ __global__ void gather_tris_kernel(const float *__restrict__ tris, const unsigne
 		return;
 	}
 	const float *t	 = tris + 9 * (size_t) sorted_ids[i];
-	tri_v[3 * i + 0] = make_float4(t[0], t[1], t[2], 0.0f);
+	tri_v[3 * i + 0] = make_float4(t[0], t[1], t[2], __int_as_float((int) sorted_ids[i])); // w: original triangle index
 	tri_v[3 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
 	tri_v[3 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
 }
@@ -457,7 +459,7 @@ __global__ void iota_tris_kernel(const float *__restrict__ tris, int n, float4 *
 		return;
 	}
 	const float *t	 = tris + 9 * (size_t) i;
-	tri_v[3 * i + 0] = make_float4(t[0], t[1], t[2], 0.0f);
+	tri_v[3 * i + 0] = make_float4(t[0], t[1], t[2], __int_as_float(i));
 	tri_v[3 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
 	tri_v[3 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
 }

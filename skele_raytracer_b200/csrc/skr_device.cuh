@@ -46,6 +46,11 @@ struct SceneView
 	const float4 *big_v; // 3 float4 per outsized triangle, tested before the hierarchy (skr_bvh_build.cuh: morton_kernel)
 	int nbig;
 	int bvh_root_is_leaf; // T == 1
+	// shaded-triangles mode (opt-in, beyond the reference): a second hierarchy over the ACTUAL triangles + their materials
+	const float4 *tri_v2, *bvh2, *big_v2;
+	int nbig2;
+	const float4 *tri_mat; // 3 float4 per triangle in ORIGINAL order, or null
+	const float *tris_raw; // the uploaded triangles, 9 floats each, ORIGINAL order
 	int *err;			  // device error word (bit 1: BVH traversal stack overflow)
 	float3 cam_pos, cam_dir, cam_up, cam_right, background;
 };

@@ -28,6 +28,13 @@
 #define SKR_MIN_BLOCKS 7
 #endif
 #define SKR_FIX_SCALE 4294967296.0f
+#ifndef SKR_PRIMARY_MODE
+// 0 (default): the grid of primary_kernel covers the frame, one 8 x 4 pixel block per warp.
+// 1: persistent -- one wave of CTAs whose warps fetch blocks from a device counter.  Measured on B200 (round 2): slower
+//    (config 4: 0.42 ms against 0.31 ms, config 1: 0.062 against 0.057): the 64 800 fetches of a 1080p frame serialise on
+//    ONE L2 address, and CTAs of one warp (below) give the same dynamic refill in hardware without an atomic.
+#define SKR_PRIMARY_MODE 0
+#endif
 #ifndef SKR_GI_BATCH
 // GI children traced together (even): they share the per-sphere origin terms AND one queue reservation.  Measured on
 // B200 (config 3 / config 5): 2: 6.94 / 180.1 ms, 4: 6.57 / 169.0 ms, 8: 7.51 / 190.1 ms (spills).
@@ -323,15 +330,12 @@ SKR_DEV float3 queue_hit_point(const float4 *__restrict__ B, const SceneView &sv
 // memory), TRIS (scene has triangles: BVH code compiled in), FOG (scene has spherical fog: fog shading compiled in).
 // Sphere-only, fog-free scenes thus run a kernel without the traversal stack or the fog branch in its register budget.
 //
-// PERSISTENT: the grid is one wave of CTAs (SM count x SKR_MIN_BLOCKS, fewer for small frames); each CTA stages the
-// scene blob ONCE, then every WARP on its own pulls 8 x 4 pixel blocks (`fp.fetch` consecutive blocks per fetch) from a
-// device counter until the frame is used up -- no barrier couples the warps of a CTA, a warp whose block was sky is
-// tracing its next block while its neighbour is still inside the dragon.  The fetch of the next batch is issued before
-// the current one is traced, so its latency is hidden.  A 1080p frame is 64 800 blocks: dynamic assignment balances sky
-// against geometry without paying 16 200 CTA launches and blob stagings.  The counter pair `cursor` = (next block, CTAs
-// done) resets itself: the last CTA to leave zeroes it.
-// Finished pixels of a block are quantised into shared memory and leave as 32-bit words, 24 B per pixel row (to HBM, to
-// a peer GPU over NVLink or to page-locked host memory over PCIe), instead of 3 byte stores each.
+// Launch shape: one 8 x 4 pixel block per WARP; the CTA size is chosen per frame by the host (launch_primary): CTAs of
+// ONE warp where block costs vary wildly (BVH scenes: a sky warp retires at once and the hardware refills its slot with the
+// next block, instead of idling beside a sibling that is still inside the mesh), CTAs of four warps otherwise (the scene
+// blob is staged per CTA).  (SKR_PRIMARY_MODE 1 = persistent CTAs fetching blocks from a device counter: see above.)
+// Finished pixels bound for another device or for page-locked host memory (skr_render_peers_device) are quantised into
+// shared memory and leave as 32-bit words, 24 B per pixel row of the block, instead of 3 byte stores each.
 template <bool GI, bool STATS, bool SMEM, bool TRIS, bool FOG>
 __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix,
 																	 unsigned *cursor)
@@ -343,8 +347,9 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 	zero(cnt);
 	const unsigned lane	   = threadIdx.x & 31u;
 	const unsigned nblocks = (unsigned) ((npix + 31) / 32);
-	const unsigned fetch   = (unsigned) fp.fetch;
-	unsigned nxt		   = 0;
+#if SKR_PRIMARY_MODE == 1
+	const unsigned fetch = (unsigned) fp.fetch;
+	unsigned nxt = 0;
 	if(lane == 0)
 	{
 		nxt = atomicAdd(cursor, fetch);
@@ -356,6 +361,13 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 	{
 		nxt = atomicAdd(cursor, fetch); // the next batch's index is on its way while this one is traced
 	}
+#else
+	// static: the grid covers the frame, warp w of CTA b takes block b * (warps per CTA) + w
+	const unsigned fetch = 1u;
+	const unsigned batch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(batch < nblocks)
+	{
+#endif
 	const unsigned batch_end = batch + fetch < nblocks ? batch + fetch : nblocks;
 	for(unsigned blk = batch; blk < batch_end; blk++)
 	{
@@ -480,7 +492,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		// The block's first pixel (lane 0) fixes its place: 8 x 4 pixels at (x0, y0).  Whole blocks whose rows start on a
 		// word boundary leave as words; ragged ones pixel by pixel.
 		const int x0 = __shfl_sync(0xffffffffu, p.x, 0), y0 = __shfl_sync(0xffffffffu, p.y, 0);
-		const bool words = fp.strip_words && __shfl_sync(0xffffffffu, (int) p.valid, 0) && x0 + 8 <= fp.width;
+		const bool words = fp.strip_words && __shfl_sync(0xffffffffu, (int) p.valid, 0) && x0 + 8 <= fp.width; // (uniform)
 		if(words)
 		{
 			uint8_t *sb = reinterpret_cast<uint8_t *>(s_px[threadIdx.x >> 5]);
@@ -545,6 +557,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			}
 		}
 	}
+#if SKR_PRIMARY_MODE == 1
 	batch = __shfl_sync(0xffffffffu, nxt, 0);
 	} // batches
 	__syncthreads();
@@ -559,6 +572,9 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			__threadfence();
 		}
 	}
+#else
+	}
+#endif
 	flush_counters<STATS>(fp, cnt);
 }
 
@@ -578,7 +594,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 //                                               meta = sphere | parent lane << 16 | child index << 21
 //                   32 x 4 x u64                per parent lane: fixed-point sum r, g, b + flags
 #define SKR_LEAF_SLOTS (32 + 32 * SKR_GI_BATCH)
-#define SKR_LEAF_WARP_BYTES (SKR_LEAF_SLOTS * 32 + 32 * 4 * 8)
+#define SKR_LEAF_WARP_BYTES (SKR_LEAF_SLOTS * 32 + 32 * 4 * 8 + 32 * 4 * 4)
 #define SKR_LEAF_CTA_BYTES ((SKR_BLOCK / 32) * SKR_LEAF_WARP_BYTES)
 #define SKR_LEAF_MAX_CHILDREN 2047
 
@@ -586,8 +602,96 @@ struct LeafStage
 {
 	float4 *slot;			 // this warp's ring
 	unsigned long long *acc; // this warp's 32 x 4 parent accumulators
+	unsigned *acc2;			 // 32 x 4 u32 more (SKR_LEAF_ACC == 3)
 	unsigned pending;		 // warp-uniform
 };
+
+// Fold one round's fixed-point terms into the parents' accumulators in shared memory (every lane calls; `act` lanes hold
+// a term for parent lane `src`).  SKR_LEAF_ACC picks the mechanism (measured on B200):
+//   1  64-bit shared-memory atomics (compile to ATOMS.CAST.SPIN loops; a parent's leaves collide on one address)
+//   2  MATCH.ANY on the parent lane + REDUX.SUM over each group on 16/16/32-bit limbs, group leader adds
+//   3  native 32-bit shared-memory atomics on 16/16/32-bit limbs (accumulator = 3 x u32 per channel, carries folded at the end)
+//   0  nothing (timing experiments only: the image is wrong)
+#ifndef SKR_LEAF_ACC
+#define SKR_LEAF_ACC 1
+#endif
+SKR_DEV void leaf_accumulate(const LeafStage &ls, bool act, unsigned lane, int src, long long fx, long long fy, long long fz, unsigned fl)
+{
+#if SKR_LEAF_ACC == 1
+	if(act)
+	{
+		unsigned long long *a = ls.acc + 4 * src;
+		atomicAdd(a + 0, (unsigned long long) fx);
+		atomicAdd(a + 1, (unsigned long long) fy);
+		atomicAdd(a + 2, (unsigned long long) fz);
+		if(fl)
+		{
+			atomicOr(a + 3, (unsigned long long) fl);
+		}
+	}
+#elif SKR_LEAF_ACC == 2
+	const unsigned peers = __match_any_sync(0xffffffffu, act ? (unsigned) src : 64u + lane);
+	const auto group_sum = [&](long long v) -> long long {
+		const unsigned a = __reduce_add_sync(peers, (unsigned) ((unsigned long long) v & 0xffffull));
+		const unsigned b = __reduce_add_sync(peers, (unsigned) (((unsigned long long) v >> 16) & 0xffffull));
+		const int c		 = __reduce_add_sync(peers, (int) (v >> 32));
+		return (long long) (((unsigned long long) (long long) c << 32) + ((unsigned long long) b << 16) + (unsigned long long) a);
+	};
+	const long long sx = group_sum(fx), sy = group_sum(fy), sz = group_sum(fz);
+	const unsigned sfl = __reduce_or_sync(peers, fl);
+	if(act && lane == (unsigned) (__ffs(peers) - 1))
+	{
+		ulonglong2 *a = reinterpret_cast<ulonglong2 *>(ls.acc + 4 * src);
+		ulonglong2 p = a[0], q = a[1];
+		p.x += (unsigned long long) sx;
+		p.y += (unsigned long long) sy;
+		q.x += (unsigned long long) sz;
+		q.y |= (unsigned long long) sfl;
+		a[0] = p;
+		a[1] = q;
+	}
+	__syncwarp();
+#elif SKR_LEAF_ACC == 3
+	// acc viewed as 8 x u32 per parent: [x.a+b<<16 .. ] is NOT used; layout: u32[0..2] = x limbs (a, b, c), [3..5] = y, and the
+	// z limbs + flags live in the second half of the ring-side table (ls.acc2)
+	if(act)
+	{
+		unsigned *u = reinterpret_cast<unsigned *>(ls.acc) + 8 * src; // 32 B per parent: x.a x.b x.c y.a y.b y.c fl -
+		unsigned *w = ls.acc2 + 4 * src;							   // z.a z.b z.c -
+		atomicAdd(u + 0, (unsigned) ((unsigned long long) fx & 0xffffull));
+		atomicAdd(u + 1, (unsigned) (((unsigned long long) fx >> 16) & 0xffffull));
+		atomicAdd(u + 2, (unsigned) (int) (fx >> 32));
+		atomicAdd(u + 3, (unsigned) ((unsigned long long) fy & 0xffffull));
+		atomicAdd(u + 4, (unsigned) (((unsigned long long) fy >> 16) & 0xffffull));
+		atomicAdd(u + 5, (unsigned) (int) (fy >> 32));
+		atomicAdd(w + 0, (unsigned) ((unsigned long long) fz & 0xffffull));
+		atomicAdd(w + 1, (unsigned) (((unsigned long long) fz >> 16) & 0xffffull));
+		atomicAdd(w + 2, (unsigned) (int) (fz >> 32));
+		if(fl)
+		{
+			atomicOr(u + 6, fl);
+		}
+	}
+#endif
+}
+// the parent lane's total, as three fixed-point terms + flags
+SKR_DEV void leaf_total(const LeafStage &ls, unsigned lane, long long &x, long long &y, long long &z, unsigned &fl)
+{
+#if SKR_LEAF_ACC == 3
+	const unsigned *u = reinterpret_cast<const unsigned *>(ls.acc) + 8 * lane;
+	const unsigned *w = ls.acc2 + 4 * lane;
+	const auto join	  = [](unsigned a, unsigned b, unsigned c) {
+		  return (long long) (((unsigned long long) (long long) (int) c << 32) + ((unsigned long long) b << 16) + (unsigned long long) a);
+	};
+	x  = join(u[0], u[1], u[2]);
+	y  = join(u[3], u[4], u[5]);
+	z  = join(w[0], w[1], w[2]);
+	fl = u[6];
+#else
+	const unsigned long long *a = ls.acc + 4 * lane;
+	x = (long long) a[0], y = (long long) a[1], z = (long long) a[2], fl = (unsigned) a[3];
+#endif
+}
 
 // shade `count` (<= 32) staged leaf hits starting at slot `first`; every lane of the warp calls this
 template <bool STATS, bool FOG>
@@ -624,32 +728,7 @@ SKR_DEV void leaf_shade_round(const float4 *__restrict__ B, const SceneView &sv,
 		fl = 0;
 		fx = to_fixed(contrib.x, fl, 0), fy = to_fixed(contrib.y, fl, 1), fz = to_fixed(contrib.z, fl, 2);
 	}
-	// Fold the round into the parents' accumulators WITHOUT shared-memory atomics (64-bit ones are CAS loops, and a
-	// parent's leaves collide on one address): lanes holding leaves of the same parent find each other (MATCH.ANY on the
-	// parent lane), their fixed-point terms are summed exactly by integer warp reductions (REDUX.SUM) on 16 / 16 / 32-bit
-	// limbs -- v = c 2^32 + b 2^16 + a; at most 32 terms, so no limb sum overflows -- and the lowest lane of each group
-	// adds the total.  Groups hold distinct parents and rounds are sequential in the warp: plain read-modify-write.
-	const unsigned peers = __match_any_sync(0xffffffffu, act ? (unsigned) src : 64u + lane);
-	const auto group_sum = [&](long long v) -> long long {
-		const unsigned a = __reduce_add_sync(peers, (unsigned) ((unsigned long long) v & 0xffffull));
-		const unsigned b = __reduce_add_sync(peers, (unsigned) (((unsigned long long) v >> 16) & 0xffffull));
-		const int c		 = __reduce_add_sync(peers, (int) (v >> 32));
-		return (long long) (((unsigned long long) (long long) c << 32) + ((unsigned long long) b << 16) + (unsigned long long) a);
-	};
-	const long long sx = group_sum(fx), sy = group_sum(fy), sz = group_sum(fz);
-	const unsigned sfl = __reduce_or_sync(peers, fl);
-	if(act && lane == (unsigned) (__ffs(peers) - 1))
-	{
-		ulonglong2 *a	= reinterpret_cast<ulonglong2 *>(ls.acc + 4 * src);
-		ulonglong2 p = a[0], q = a[1];
-		p.x += (unsigned long long) sx;
-		p.y += (unsigned long long) sy;
-		q.x += (unsigned long long) sz;
-		q.y |= (unsigned long long) sfl;
-		a[0] = p;
-		a[1] = q;
-	}
-	__syncwarp();
+	leaf_accumulate(ls, act, lane, src, fx, fy, fz, fl);
 }
 
 // shade whole rounds of 32 while that many are pending; keep the rest at the front of the ring
@@ -712,10 +791,12 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 		char *base = reinterpret_cast<char *>(smem) + (SMEM ? (size_t) sv.blob_f4 * sizeof(float4) : 0) + (threadIdx.x >> 5) * SKR_LEAF_WARP_BYTES;
 		ls.slot	   = reinterpret_cast<float4 *>(base);
 		ls.acc	   = reinterpret_cast<unsigned long long *>(base + SKR_LEAF_SLOTS * 32);
+		ls.acc2	   = reinterpret_cast<unsigned *>(base + SKR_LEAF_SLOTS * 32 + 32 * 4 * 8);
 		ls.pending = 0;
 		const unsigned lane = threadIdx.x & 31u;
 		reinterpret_cast<ulonglong2 *>(ls.acc + 4 * lane)[0] = make_ulonglong2(0ull, 0ull);
 		reinterpret_cast<ulonglong2 *>(ls.acc + 4 * lane)[1] = make_ulonglong2(0ull, 0ull);
+		reinterpret_cast<uint4 *>(ls.acc2 + 4 * lane)[0]	 = make_uint4(0u, 0u, 0u, 0u);
 		__syncwarp();
 	}
 
@@ -881,8 +962,10 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 		const long long lp = encode_pixel(fp, x, y);
 		if constexpr(LEAF)
 		{
-			const unsigned long long *a = ls.acc + 4 * (threadIdx.x & 31u);
-			accum_add(fp.accum, lp, contrib, (long long) a[0], (long long) a[1], (long long) a[2], (unsigned) a[3]);
+			long long ex, ey, ez;
+			unsigned efl;
+			leaf_total(ls, threadIdx.x & 31u, ex, ey, ez, efl);
+			accum_add(fp.accum, lp, contrib, ex, ey, ez, efl);
 		}
 		else
 		{
