@@ -10,6 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -19,9 +22,30 @@ namespace
 thread_local std::string g_err;
 }
 
+// One persistent host thread per GPU (a --gillum frame schedules its wavefront with host read-backs, so every GPU needs
+// its own driver thread; spawning them per frame cost more than a 0.2 ms frame).
+struct Worker
+{
+	std::thread th;
+	std::mutex m;
+	std::condition_variable cv;
+	std::function<void()> job;
+	bool has_job = false, quit = false;
+};
+
 struct skr_mgpu
 {
 	int world = 0;
+	std::vector<Worker *> workers;
+	std::mutex done_m;
+	std::condition_variable done_cv;
+	int pending = 0;
+	// the caller's frame, page-locked and mapped so that every GPU's kernel can store its tiles straight into it
+	void *pinned_host = nullptr;
+	size_t pinned_bytes = 0;
+	bool pinned_by_us = false;
+	void *pinned_dev = nullptr;
+	bool direct = true; // default frame assembly: kernels store into the host frame (SKR_MGPU_NO_DIRECT=1: via GPU 0 / NCCL)
 	std::vector<skr_ctx *> ctx;
 	std::vector<ncclComm_t> comm;
 	std::vector<uint8_t *> d_tiles;	   // per GPU: its compact tiles
@@ -45,6 +69,80 @@ int fail(skr_mgpu *m, int code, const char *fmt, ...)
 	(m ? m->err : g_err) = buf;
 	return code;
 }
+void worker_main(skr_mgpu *m, int i)
+{
+	cudaSetDevice(i);
+	Worker *w = m->workers[i];
+	for(;;)
+	{
+		std::function<void()> job;
+		{
+			std::unique_lock<std::mutex> lk(w->m);
+			w->cv.wait(lk, [w] { return w->has_job || w->quit; });
+			if(w->quit)
+			{
+				return;
+			}
+			job		   = std::move(w->job);
+			w->has_job = false;
+		}
+		job();
+		{
+			std::lock_guard<std::mutex> lk(m->done_m);
+			m->pending--;
+		}
+		m->done_cv.notify_one();
+	}
+}
+// runs f(i) on every GPU's thread and waits for all of them
+void on_all(skr_mgpu *m, const std::function<void(int)> &f)
+{
+	{
+		std::lock_guard<std::mutex> lk(m->done_m);
+		m->pending = m->world;
+	}
+	for(int i = 0; i < m->world; i++)
+	{
+		Worker *w = m->workers[i];
+		{
+			std::lock_guard<std::mutex> lk(w->m);
+			w->job	   = [&f, i] { f(i); };
+			w->has_job = true;
+		}
+		w->cv.notify_one();
+	}
+	std::unique_lock<std::mutex> lk(m->done_m);
+	m->done_cv.wait(lk, [m] { return m->pending == 0; });
+}
+
+// Page-lock + map the caller's frame once (cached while the pointer and size stay the same); buffers that are already
+// page-locked (cudaHostAlloc, torch pin_memory) are used as they are.
+int pin_frame(skr_mgpu *m, uint8_t *rgb8, size_t bytes)
+{
+	if(m->pinned_host == rgb8 && m->pinned_bytes >= bytes && m->pinned_dev)
+	{
+		return SKR_OK;
+	}
+	cudaSetDevice(0);
+	if(m->pinned_by_us && m->pinned_host)
+	{
+		cudaHostUnregister(m->pinned_host);
+	}
+	m->pinned_host = nullptr;
+	m->pinned_dev  = nullptr;
+	void *d		   = nullptr;
+	const int rc   = skr_pin_host(m->ctx[0], rgb8, bytes, &d);
+	if(rc != SKR_OK && rc != 1000)
+	{
+		return rc;
+	}
+	m->pinned_host	= rgb8;
+	m->pinned_bytes = bytes;
+	m->pinned_by_us = rc == SKR_OK;
+	m->pinned_dev	= d;
+	return SKR_OK;
+}
+
 void sum_stats(skr_stats *stats, const std::vector<skr_stats> &st)
 {
 	memset(stats, 0, sizeof *stats);
@@ -70,6 +168,52 @@ void sum_stats(skr_stats *stats, const std::vector<skr_stats> &st)
 			stats->ms_resolve = s.ms_resolve;
 		}
 	}
+}
+
+// Default frame assembly: NO device frame at all.  Every GPU renders its interleaved tiles with skr_render_peers_device and
+// its kernel stores each finished pixel block straight into the caller's page-locked host frame -- every GPU over its OWN
+// PCIe link, while the rest of its tiles are still being traced.  When the GPUs' streams have drained the frame is whole.
+int render_direct(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stats *stats, size_t frame_bytes)
+{
+	const int W = m->world;
+	int rc0		= pin_frame(m, rgb8, frame_bytes);
+	if(rc0)
+	{
+		return fail(m, rc0, "skr_mgpu_render: cannot page-lock the frame: %s", skr_last_error(m->ctx[0]));
+	}
+	std::vector<int> rc(W, 0);
+	std::vector<std::string> msg(W);
+	std::vector<skr_stats> st(W);
+	const bool want_stats = stats != nullptr;
+	on_all(m, [&](int i) {
+		skr_options oi = *opt;
+		oi.world	   = W;
+		oi.rank		   = i;
+		memset(&st[i], 0, sizeof st[i]);
+		void *frames[1] = {m->pinned_dev};
+		rc[i]			= skr_render_peers_device(m->ctx[i], &oi, frames, 1, want_stats ? &st[i] : nullptr);
+		if(!rc[i])
+		{
+			rc[i] = skr_sync(m->ctx[i]);
+		}
+		if(rc[i])
+		{
+			msg[i] = skr_last_error(m->ctx[i]);
+		}
+	});
+	for(int i = 0; i < W; i++)
+	{
+		if(rc[i])
+		{
+			return fail(m, rc[i], "GPU %d: %s", i, msg[i].c_str());
+		}
+	}
+	if(stats)
+	{
+		sum_stats(stats, st);
+		stats->ms_d2h = 0.0f; // the copy-out is the kernels' own stores
+	}
+	return SKR_OK;
 }
 
 // Collective-free frame: every GPU renders its interleaved tiles with skr_render_peers_device and stores each finished
@@ -173,6 +317,24 @@ void skr_mgpu_destroy(skr_mgpu *m)
 	{
 		return;
 	}
+	for(Worker *w : m->workers)
+	{
+		{
+			std::lock_guard<std::mutex> lk(w->m);
+			w->quit = true;
+		}
+		w->cv.notify_one();
+		if(w->th.joinable())
+		{
+			w->th.join();
+		}
+		delete w;
+	}
+	m->workers.clear();
+	if(m->pinned_by_us && m->pinned_host && !m->ctx.empty())
+	{
+		skr_unpin_host(m->ctx[0], m->pinned_host);
+	}
 	for(int i = 0; i < (int) m->ctx.size(); i++)
 	{
 		cudaSetDevice(i);
@@ -231,10 +393,22 @@ int skr_mgpu_init(int n_gpus, skr_mgpu **out)
 	m->d_gathered.assign(n_gpus, nullptr);
 	m->cap_tiles.assign(n_gpus, 0);
 	m->comm.assign(n_gpus, nullptr);
+	{
+		const char *nd = getenv("SKR_MGPU_NO_DIRECT");
+		m->direct	   = !(nd && nd[0] == '1');
+	}
+	for(int i = 0; i < n_gpus; i++)
+	{
+		m->workers.push_back(new Worker());
+	}
+	for(int i = 0; i < n_gpus; i++)
+	{
+		m->workers[i]->th = std::thread(worker_main, m, i);
+	}
 	// peer path: every other GPU maps GPU 0's memory; its kernels then store finished pixels into GPU 0's frame
 	{
 		const char *no = getenv("SKR_MGPU_NO_P2P");
-		m->p2p		   = n_gpus > 1 && !(no && no[0] == '1');
+		m->p2p		   = !m->direct && n_gpus > 1 && !(no && no[0] == '1');
 		for(int i = 1; i < n_gpus && m->p2p; i++)
 		{
 			int can = 0;
@@ -253,7 +427,7 @@ int skr_mgpu_init(int n_gpus, skr_mgpu **out)
 		}
 		cudaSetDevice(0);
 	}
-	if(n_gpus > 1 && !m->p2p)
+	if(n_gpus > 1 && !m->p2p && !m->direct)
 	{
 		std::vector<int> devs(n_gpus);
 		for(int i = 0; i < n_gpus; i++)
@@ -279,15 +453,7 @@ int skr_mgpu_scene_upload(skr_mgpu *m, const skr_scene_desc *scene)
 		return fail(nullptr, SKR_ERR_ARG, "null handle");
 	}
 	std::vector<int> rc(m->world, 0);
-	std::vector<std::thread> th;
-	for(int i = 0; i < m->world; i++)
-	{
-		th.emplace_back([&, i]() { rc[i] = skr_scene_upload(m->ctx[i], scene); });
-	}
-	for(std::thread &t : th)
-	{
-		t.join();
-	}
+	on_all(m, [&](int i) { rc[i] = skr_scene_upload(m->ctx[i], scene); });
 	for(int i = 0; i < m->world; i++)
 	{
 		if(rc[i])
@@ -314,6 +480,10 @@ int skr_mgpu_render(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stat
 		return fail(m, SKR_ERR_ARG, "skr_mgpu_render: bad options");
 	}
 	const size_t frame_bytes = (size_t) opt->width * opt->height * 3;
+	if(m->direct)
+	{
+		return render_direct(m, opt, rgb8, stats, frame_bytes);
+	}
 	if(m->p2p)
 	{
 		return render_p2p(m, opt, rgb8, stats, frame_bytes);

@@ -2,14 +2,17 @@
  *
  * The reference has no multi-GPU path (its only parallelism is the OpenMP row loop, src/main.cpp:33); this is the
  * additive part (3) of the north star: interleaved image tiles across the GPUs of one box.  Frame assembly:
- *   - peer path (default when every GPU can map GPU 0's memory): skr_render_peers_device() on every GPU with GPU 0's
+ *   - direct path (default): the caller's host frame is page-locked and mapped (once; cudaHostRegister, or used as it is
+ *     when already page-locked) and every GPU's render kernel stores its finished pixel blocks straight into it over its
+ *     OWN PCIe link while it is still tracing -- no device frame, no gather, no D2H copy through one GPU;
+ *   - peer path (SKR_MGPU_NO_DIRECT=1, when every GPU can map GPU 0's memory): skr_render_peers_device() on every GPU with GPU 0's
  *     frame as the target -- the render kernels store each finished pixel straight into it over NVLink; no collective,
  *     no de-interleave pass, one D2H copy once all kernels are done;
- *   - NCCL path (otherwise, or SKR_MGPU_NO_P2P=1): skr_render_tiles_device(), ONE ncclAllGather of the quantised RGB8
+ *   - NCCL path (SKR_MGPU_NO_DIRECT=1 and no peer access, or SKR_MGPU_NO_P2P=1): skr_render_tiles_device(), ONE ncclAllGather of the quantised RGB8
  *     tiles, a de-interleave kernel, one D2H copy.
  * The scene is replicated; the RNG is keyed by pixel, so the frame is byte-identical for any GPU count and either path.
  *
- * One host thread per GPU drives its context (the --gillum wavefront schedules with host read-backs).  For the
+ * One persistent host thread per GPU drives its context (the --gillum wavefront schedules with host read-backs).  For the
  * one-process-per-GPU model (torchrun, MPI) use skr.h directly: skr_render_tiles_device + your all-gather +
  * skr_deinterleave_device (skele_raytracer_b200/distributed.py does that over torch.distributed).
  */

@@ -239,9 +239,9 @@ void launch_primary(skr_ctx *ctx, const FrameParams &fp, const Queue &q, long lo
 	const SceneView &sv = ctx->sv;
 	cudaStream_t st		= ctx->stream;
 	const size_t sm		= ctx->smem_bytes;
-	// one 8 x 4 pixel block per warp.  CTAs of one warp for BVH scenes (per-block cost varies ~100x between sky and mesh: the
-	// hardware refills a finished warp's slot at once), four warps otherwise; SKR_PRIMARY_BLOCK overrides (A/B runs).
-	int threads = (!GI && sv.bvh != nullptr) ? 32 : SKR_BLOCK;
+	// one 8 x 4 pixel block per warp, four warps per CTA.  SKR_PRIMARY_BLOCK overrides for A/B runs: measured on B200, CTAs of
+	// 1 / 2 / 4 warps: config 1 0.053 / 0.051 / 0.049 ms, config 2 1.034 / 1.025 / 1.026, config 4 0.310 / 0.308 / 0.303.
+	int threads = SKR_BLOCK;
 	if(const char *e = getenv("SKR_PRIMARY_BLOCK"))
 	{
 		const int v = atoi(e);

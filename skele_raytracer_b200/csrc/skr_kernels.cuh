@@ -230,6 +230,61 @@ SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, 
 	}
 }
 
+// One finished 8 x 4 pixel block (all 32 lanes of the warp call this; lane = pixel of the block, lane 0 its origin).
+// Frames bound for another device or for page-locked host memory (fp.strip_words) leave as 32-bit words: the block is
+// quantised into 96 B of shared memory (`stage`, this warp's), then 24 lanes store one word each, 24 B per pixel row --
+// instead of 3 byte stores per pixel across NVLink / PCIe.  Ragged blocks and local frames go pixel by pixel.
+SKR_DEV void write_block(const FrameParams &fp, long long lp, const PixelId &p, float3 c, uint32_t *stage)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const int x0 = __shfl_sync(0xffffffffu, p.x, 0), y0 = __shfl_sync(0xffffffffu, p.y, 0);
+	const bool words = fp.strip_words && __shfl_sync(0xffffffffu, (int) p.valid, 0) && x0 + 8 <= fp.width; // (uniform)
+	if(!words)
+	{
+		if(p.valid)
+		{
+			write_pixel(fp, lp, p, c);
+		}
+		return;
+	}
+	uint8_t *o = reinterpret_cast<uint8_t *>(stage) + (lane >> 3) * 24 + (lane & 7) * 3;
+	o[0]	   = quantise(c.x);
+	o[1]	   = quantise(c.y);
+	o[2]	   = quantise(c.z);
+	if(fp.rgb32 && p.valid)
+	{
+		float *f = fp.rgb32 + 3 * ((size_t) p.y * fp.width + p.x);
+		f[0]	 = c.x;
+		f[1]	 = c.y;
+		f[2]	 = c.z;
+	}
+	if(fp.tiles8 && p.valid)
+	{
+		const int tpix = fp.tile * fp.tile;
+		uint8_t *t	   = fp.tiles8 + 3 * ((size_t) (lp / tpix) * tpix + (size_t) (p.y % fp.tile) * fp.tile + (p.x % fp.tile));
+		t[0] = o[0], t[1] = o[1], t[2] = o[2];
+	}
+	__syncwarp();
+	if(lane < 24)
+	{
+		const int r = lane / 6, w = lane - r * 6;
+		if(y0 + r < fp.height)
+		{
+			const size_t at	 = (((size_t) (y0 + r) * fp.width + x0) * 3) / 4 + w;
+			const uint32_t v = stage[r * 6 + w];
+			if(fp.rgb8)
+			{
+				reinterpret_cast<uint32_t *>(fp.rgb8)[at] = v;
+			}
+			for(int k = 0; k < fp.n_peers; k++)
+			{
+				reinterpret_cast<uint32_t *>(fp.peers[k])[at] = v;
+			}
+		}
+	}
+	__syncwarp();
+}
+
 // Stage the scene blob into shared memory (all threads of the CTA).  SMEM is a template parameter so that the test
 // loops compile to LDS (not generic loads) in the common case; scenes too big for shared memory read the blob in place.
 template <bool SMEM>
@@ -330,10 +385,8 @@ SKR_DEV float3 queue_hit_point(const float4 *__restrict__ B, const SceneView &sv
 // memory), TRIS (scene has triangles: BVH code compiled in), FOG (scene has spherical fog: fog shading compiled in).
 // Sphere-only, fog-free scenes thus run a kernel without the traversal stack or the fog branch in its register budget.
 //
-// Launch shape: one 8 x 4 pixel block per WARP; the CTA size is chosen per frame by the host (launch_primary): CTAs of
-// ONE warp where block costs vary wildly (BVH scenes: a sky warp retires at once and the hardware refills its slot with the
-// next block, instead of idling beside a sibling that is still inside the mesh), CTAs of four warps otherwise (the scene
-// blob is staged per CTA).  (SKR_PRIMARY_MODE 1 = persistent CTAs fetching blocks from a device counter: see above.)
+// Launch shape: one 8 x 4 pixel block per WARP, four warps per CTA (the scene blob is staged per CTA).
+// (SKR_PRIMARY_MODE 1 = persistent CTAs fetching blocks from a device counter: measured slower, see above.)
 // Finished pixels bound for another device or for page-locked host memory (skr_render_peers_device) are quantised into
 // shared memory and leave as 32-bit words, 24 B per pixel row of the block, instead of 3 byte stores each.
 template <bool GI, bool STATS, bool SMEM, bool TRIS, bool FOG>
@@ -489,54 +542,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			const float n2 = (float) fp.spp; // image[y][x] /= (grid*grid), src/main.cpp:68
 			sum			   = f3(__fdiv_rn(sum.x, n2), __fdiv_rn(sum.y, n2), __fdiv_rn(sum.z, n2));
 		}
-		// The block's first pixel (lane 0) fixes its place: 8 x 4 pixels at (x0, y0).  Whole blocks whose rows start on a
-		// word boundary leave as words; ragged ones pixel by pixel.
-		const int x0 = __shfl_sync(0xffffffffu, p.x, 0), y0 = __shfl_sync(0xffffffffu, p.y, 0);
-		const bool words = fp.strip_words && __shfl_sync(0xffffffffu, (int) p.valid, 0) && x0 + 8 <= fp.width; // (uniform)
-		if(words)
-		{
-			uint8_t *sb = reinterpret_cast<uint8_t *>(s_px[threadIdx.x >> 5]);
-			uint8_t *o	= sb + (lane >> 3) * 24 + (lane & 7) * 3;
-			o[0]		= quantise(sum.x);
-			o[1]		= quantise(sum.y);
-			o[2]		= quantise(sum.z);
-			if(fp.rgb32 && p.valid)
-			{
-				float *f = fp.rgb32 + 3 * ((size_t) p.y * fp.width + p.x);
-				f[0]	 = sum.x;
-				f[1]	 = sum.y;
-				f[2]	 = sum.z;
-			}
-			if(fp.tiles8 && p.valid)
-			{
-				const int tpix = fp.tile * fp.tile;
-				uint8_t *t	   = fp.tiles8 + 3 * ((size_t) (lp / tpix) * tpix + (size_t) (p.y % fp.tile) * fp.tile + (p.x % fp.tile));
-				t[0] = o[0], t[1] = o[1], t[2] = o[2];
-			}
-			__syncwarp();
-			if(lane < 24)
-			{
-				const int r = lane / 6, w = lane - r * 6;
-				if(y0 + r < fp.height)
-				{
-					const size_t at	 = (((size_t) (y0 + r) * fp.width + x0) * 3) / 4 + w;
-					const uint32_t v = s_px[threadIdx.x >> 5][r * 6 + w];
-					if(fp.rgb8)
-					{
-						reinterpret_cast<uint32_t *>(fp.rgb8)[at] = v;
-					}
-					for(int k = 0; k < fp.n_peers; k++)
-					{
-						reinterpret_cast<uint32_t *>(fp.peers[k])[at] = v;
-					}
-				}
-			}
-			__syncwarp();
-		}
-		else if(p.valid)
-		{
-			write_pixel(fp, lp, p, sum);
-		}
+		write_block(fp, lp, p, sum, s_px[threadIdx.x >> 5]);
 	}
 	} // blocks of the batch
 	if(!GI && fp.band_flag)
@@ -694,8 +700,19 @@ SKR_DEV void leaf_total(const LeafStage &ls, unsigned lane, long long &x, long l
 }
 
 // shade `count` (<= 32) staged leaf hits starting at slot `first`; every lane of the warp calls this
+#ifndef SKR_LEAF_NOINLINE
+#define SKR_LEAF_NOINLINE 0
+#endif
+#ifndef SKR_LEAF_MIN_BLOCKS
+#define SKR_LEAF_MIN_BLOCKS SKR_MIN_BLOCKS
+#endif
 template <bool STATS, bool FOG>
-SKR_DEV void leaf_shade_round(const float4 *__restrict__ B, const SceneView &sv, const FrameParams &fp, const LeafStage &ls, unsigned first, unsigned count,
+#if SKR_LEAF_NOINLINE
+__device__ __noinline__ void leaf_shade_round(
+#else
+SKR_DEV void leaf_shade_round(
+#endif
+const float4 *__restrict__ B, const SceneView &sv, const FrameParams &fp, const LeafStage &ls, unsigned first, unsigned count,
 							  float3 o, const RngCtx &rng, Counters &cnt)
 {
 	const unsigned lane = threadIdx.x & 31u;
@@ -778,7 +795,7 @@ SKR_DEV void leaf_drain(const float4 *__restrict__ B, const SceneView &sv, const
 // ------------------------------------------------------------------------------------------------
 // LEAF: the children are leaves of the tree (depth 1) and are shaded in place, see above; `out` is unused.
 template <bool STATS, bool SMEM, bool TRIS, bool FOG, bool LEAF>
-__global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
+__global__ void __launch_bounds__(SKR_BLOCK, LEAF ? SKR_LEAF_MIN_BLOCKS : SKR_MIN_BLOCKS) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
 																  const Queue out, int expand)
 {
 	extern __shared__ float4 smem[];
@@ -1081,24 +1098,22 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 
 __global__ void __launch_bounds__(SKR_BLOCK) resolve_kernel(const FrameParams fp, long long lp0, long long npix)
 {
-	const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	if(g >= npix)
-	{
-		return;
-	}
+	__shared__ uint32_t s_px[SKR_BLOCK / 32][24];
+	const long long g  = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	const long long lp = lp0 + g;
-	const PixelId p	   = decode_pixel(fp, lp);
-	if(!p.valid)
+	PixelId p		   = decode_pixel(fp, lp);
+	p.valid			   = p.valid && g < npix;
+	float3 c		   = f3(0.0f, 0.0f, 0.0f);
+	if(p.valid)
 	{
-		return;
+		c = accum_load(fp.accum, lp);
+		if(fp.grid > 0)
+		{
+			const float n2 = (float) fp.spp;
+			c			   = f3(__fdiv_rn(c.x, n2), __fdiv_rn(c.y, n2), __fdiv_rn(c.z, n2));
+		}
 	}
-	float3 c = accum_load(fp.accum, lp);
-	if(fp.grid > 0)
-	{
-		const float n2 = (float) fp.spp;
-		c			   = f3(__fdiv_rn(c.x, n2), __fdiv_rn(c.y, n2), __fdiv_rn(c.z, n2));
-	}
-	write_pixel(fp, lp, p, c);
+	write_block(fp, lp, p, c, s_px[threadIdx.x >> 5]); // a warp = one 8 x 4 pixel block, like primary_kernel
 }
 
 // skr_deinterleave_device: gathered rank-major compact tiles -> row-major frame
