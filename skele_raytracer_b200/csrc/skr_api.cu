@@ -122,6 +122,9 @@ struct skr_ctx
 	unsigned *h_count = nullptr; // pinned
 
 	unsigned long long *d_counters = nullptr; // 9 (16 allocated)
+	float4 *d_cand_d = nullptr; // deferred triangle query: candidates (tri_deferred_kernel)
+	uint32_t *d_cand_lp = nullptr;
+	size_t cand_d_bytes = 0, cand_lp_bytes = 0;
 	unsigned *d_cursor = nullptr;			  // (next strip, CTAs done) of the persistent primary_kernel; self-resetting
 	int *d_err = nullptr;
 	int *h_err = nullptr; // pinned
@@ -570,6 +573,7 @@ struct Plan
 	long long tiles_local;
 	int levels;		  // depth levels of the --gillum / fresnel tree (0: none)
 	bool shaded;	  // opt-in shaded-triangles mode (skr_shaded.cuh)
+	bool defer;		  // triangle queries of the camera rays go through tri_deferred_kernel
 	int qlevels;	  // queue levels needed: `levels`, or one less when the leaves are shaded in place
 	bool leaf_inline; // depth-1 hits are shaded by the warp that found them (shade_expand_kernel<..., LEAF>)
 };
@@ -652,9 +656,19 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	pl.npix_local  = pl.tiles_local * tile * tile;
 	pl.levels	   = ((fp.gi || fp.fresnel) && fp.max_depth > 0) ? fp.max_depth : 0;
 	{
+		// deferred triangle query: single-sample frames without a wavefront tree, over a real hierarchy
+		const char *no = getenv("SKR_NO_DEFER");
+		pl.defer	   = !pl.shaded && !fp.gi && !fp.fresnel && fp.spp == 1 && fp.max_depth > 0 && ctx->sv.bvh != nullptr && !ctx->sv.bvh_root_is_leaf &&
+				   pl.npix_local <= 0xffffffffLL && !(no && no[0] == '1');
+	}
+	{
 		// leaves in place: plain --gillum trees (the fresnel pass pushes its own leaf children through the queue)
-		const char *no = getenv("SKR_NO_LEAF_INLINE");
-		pl.leaf_inline = pl.levels >= 2 && fp.gi && fp.n_gi > 0 && fp.n_gi <= SKR_LEAF_MAX_CHILDREN && !fp.fresnel && !(no && no[0] == '1');
+		// Worth it where shading a leaf is expensive against staging it, i.e. with shadow rays (config 5, 31 spheres x 2
+		// lights: 152 -> 145 ms); without them the queued consumer wins (config 3: 6.1 ms against 7.1).  SKR_LEAF_INLINE=1 /
+		// SKR_NO_LEAF_INLINE=1 force either path (the frame is bit-identical both ways).
+		const char *no = getenv("SKR_NO_LEAF_INLINE"), *yes = getenv("SKR_LEAF_INLINE");
+		const bool pays = fp.shadows != 0 || (yes && yes[0] == '1');
+		pl.leaf_inline	= pl.levels >= 2 && fp.gi && fp.n_gi > 0 && fp.n_gi <= SKR_LEAF_MAX_CHILDREN && !fp.fresnel && pays && !(no && no[0] == '1');
 		pl.qlevels	   = pl.leaf_inline ? pl.levels - 1 : pl.levels;
 	}
 	{
@@ -813,6 +827,16 @@ int prepare_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	{
 		return ensure_shade_bvh(ctx);
 	}
+	if(pl.defer)
+	{
+		CK(ensure(ctx->d_cand_d, ctx->cand_d_bytes, sizeof(float4) * (size_t) pl.npix_local));
+		CK(ensure(ctx->d_cand_lp, ctx->cand_lp_bytes, sizeof(uint32_t) * (size_t) pl.npix_local));
+		fp.cand_d	  = ctx->d_cand_d;
+		fp.cand_lp	  = ctx->d_cand_lp;
+		fp.cand_count = ctx->d_cursor + 2;
+		fp.defer	  = 1;
+		return SKR_OK;
+	}
 	if(!((fp.gi || fp.fresnel) && pl.levels > 0))
 	{
 		return SKR_OK;
@@ -885,8 +909,13 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		span_begin(ctx, CAT_PRIMARY);
 		Queue none{};
 		launch_primary<false, STATS>(ctx, fp, none, 0, pl.npix_local);
-		span_end(ctx);
 		ctx->launches++;
+		if(pl.defer)
+		{
+			tri_deferred_kernel<STATS><<<(unsigned) ctx->sm_count * 8u, SKR_BLOCK, 0, st>>>(ctx->sv, fp);
+			ctx->launches++;
+		}
+		span_end(ctx);
 		CK(cudaGetLastError());
 		return SKR_OK;
 	}
@@ -1118,7 +1147,7 @@ int skr_init(int device, skr_ctx **out)
 	{
 		return bail(e, "cudaMalloc");
 	}
-	if((e = cudaMalloc(&c->d_cursor, 2 * sizeof(unsigned))) != cudaSuccess || (e = cudaMemset(c->d_cursor, 0, 2 * sizeof(unsigned))) != cudaSuccess)
+	if((e = cudaMalloc(&c->d_cursor, 4 * sizeof(unsigned))) != cudaSuccess || (e = cudaMemset(c->d_cursor, 0, 4 * sizeof(unsigned))) != cudaSuccess)
 	{
 		return bail(e, "cudaMalloc");
 	}
@@ -1173,7 +1202,7 @@ void skr_destroy(skr_ctx *ctx)
 	ctx->bvh_shade.release();
 	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
 	cudaFree(ctx->d_arena);
-	cudaFree(ctx->d_cursor);
+	cudaFree(ctx->d_cursor), cudaFree(ctx->d_cand_d), cudaFree(ctx->d_cand_lp);
 	cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band);
 	if(ctx->copy_stream)
 	{
@@ -1242,7 +1271,7 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		return fail(ctx, SKR_ERR_ARG, "skr_scene_upload: null array with nonzero count");
 	}
 	ctx->have_scene = false;
-	CK(cudaMemsetAsync(ctx->d_cursor, 0, 2 * sizeof(unsigned), ctx->stream)); // (a frame that died mid-kernel may have left it armed)
+	CK(cudaMemsetAsync(ctx->d_cursor, 0, 4 * sizeof(unsigned), ctx->stream)); // (a frame that died mid-kernel may have left the counter pairs armed)
 	const int S = sc->nspheres, T = sc->ntris, L = sc->nplights, D = sc->ndlights, F = sc->nfogs;
 	const int S4 = (S + 3) / 4 * 4;
 	SceneView &sv = ctx->sv;

@@ -54,10 +54,111 @@ SKR_DEV bool tri_leaf_hit(const SceneView &sv, int leaf, float3 o, float3 d, flo
 	return tri_test_ref(o, d, f3(a), f3(b), f3(c), t) && t < tmax;
 }
 
+// The outsized triangles kept out of the hierarchy: any hit ends the query.
+template <bool STATS>
+SKR_DEV bool tri_big_hit(const SceneView &sv, float3 o, float3 d, float tmax, Counters &cnt)
+{
+	for(int k = 0; k < sv.nbig; k++)
+	{
+		const float4 a = __ldg(sv.big_v + 3 * k + 0), b = __ldg(sv.big_v + 3 * k + 1), c = __ldg(sv.big_v + 3 * k + 2);
+		if(STATS)
+		{
+			cnt.tt++;
+		}
+		float t;
+		if(tri_test_ref(o, d, f3(a), f3(b), f3(c), t) && t < tmax)
+		{
+			return true;
+		}
+	}
+	return false;
+}
+
+// Traversal state of one line query, so that the loop can be driven one node at a time (tri_deferred_kernel refills idle
+// lanes between steps) as well as to completion (tri_any_hit_line).
+struct TriWalk
+{
+	float3 o, d, inv;
+	float tmax;
+	int node, sp;
+};
+SKR_DEV void tri_walk_begin(TriWalk &w, float3 o, float3 d, float tmax)
+{
+	w.o	   = o;
+	w.d	   = d;
+	w.inv  = f3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
+	w.tmax = tmax;
+	w.node = 0;
+	w.sp   = 0;
+}
+// one node visit.  Returns 1: a triangle was hit (query over), 0: no node left (query over, no hit), -1: keep going.
+template <bool STATS>
+SKR_DEV int tri_walk_step(const SceneView &sv, TriWalk &w, int *stack, Counters &cnt)
+{
+	const float4 n0 = __ldg(sv.bvh + 4 * w.node + 0);
+	const float4 n1 = __ldg(sv.bvh + 4 * w.node + 1);
+	const float4 n2 = __ldg(sv.bvh + 4 * w.node + 2);
+	const float4 n3 = __ldg(sv.bvh + 4 * w.node + 3);
+	if(STATS)
+	{
+		cnt.nv++;
+	}
+	bool hl, hr;
+	line_hits_boxes(w.o, w.inv, w.tmax, n0, n1, n2, hl, hr);
+	const int cl = (int) f2u(n3.x), cr = (int) f2u(n3.y);
+	int next = -1; // next internal node to visit, if any
+	if(hl)
+	{
+		if(cl < 0)
+		{
+			if(tri_leaf_hit<STATS>(sv, ~cl, w.o, w.d, w.tmax, cnt))
+			{
+				return 1;
+			}
+		}
+		else
+		{
+			next = cl;
+		}
+	}
+	if(hr)
+	{
+		if(cr < 0)
+		{
+			if(tri_leaf_hit<STATS>(sv, ~cr, w.o, w.d, w.tmax, cnt))
+			{
+				return 1;
+			}
+		}
+		else if(next < 0)
+		{
+			next = cr;
+		}
+		else if(w.sp < SKR_BVH_STACK)
+		{
+			stack[w.sp++] = cr;
+		}
+		else
+		{
+			atomicOr(sv.err, 2); // deeper than any LBVH over 63-bit codes + index bits can be; reported, never silent
+		}
+	}
+	if(next < 0)
+	{
+		if(w.sp == 0)
+		{
+			return 0;
+		}
+		next = stack[--w.sp];
+	}
+	w.node = next;
+	return -1;
+}
+
 template <bool STATS>
 SKR_DEV bool tri_any_hit_line(const SceneView &sv, float3 o, float3 d, float tmax, Counters &cnt)
 {
-	if(sv.bvh == nullptr) // brute force (validation mode, SKR_NO_BVH=1)
+	if(sv.bvh == nullptr) // brute force (a handful of triangles, or validation mode SKR_NO_BVH=1)
 	{
 		for(int i = 0; i < sv.T; i++)
 		{
@@ -72,81 +173,40 @@ SKR_DEV bool tri_any_hit_line(const SceneView &sv, float3 o, float3 d, float tma
 	{
 		return tri_leaf_hit<STATS>(sv, 0, o, d, tmax, cnt);
 	}
-	for(int k = 0; k < sv.nbig; k++) // outsized triangles first: any hit ends the query
+	if(tri_big_hit<STATS>(sv, o, d, tmax, cnt)) // outsized triangles first
 	{
-		const float4 a = __ldg(sv.big_v + 3 * k + 0), b = __ldg(sv.big_v + 3 * k + 1), c = __ldg(sv.big_v + 3 * k + 2);
-		if(STATS)
-		{
-			cnt.tt++;
-		}
-		float t;
-		if(tri_test_ref(o, d, f3(a), f3(b), f3(c), t) && t < tmax)
-		{
-			return true;
-		}
+		return true;
 	}
-	const float3 inv = f3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
+	TriWalk w;
+	tri_walk_begin(w, o, d, tmax);
 	int stack[SKR_BVH_STACK];
-	int sp	 = 0;
-	int node = 0;
 	for(;;)
 	{
-		const float4 n0 = __ldg(sv.bvh + 4 * node + 0);
-		const float4 n1 = __ldg(sv.bvh + 4 * node + 1);
-		const float4 n2 = __ldg(sv.bvh + 4 * node + 2);
-		const float4 n3 = __ldg(sv.bvh + 4 * node + 3);
-		if(STATS)
+		const int r = tri_walk_step<STATS>(sv, w, stack, cnt);
+		if(r >= 0)
 		{
-			cnt.nv++;
+			return r == 1;
 		}
-		bool hl, hr;
-		line_hits_boxes(o, inv, tmax, n0, n1, n2, hl, hr);
-		const int cl = (int) f2u(n3.x), cr = (int) f2u(n3.y);
-		int next = -1; // next internal node to visit, if any
-		if(hl)
-		{
-			if(cl < 0)
-			{
-				if(tri_leaf_hit<STATS>(sv, ~cl, o, d, tmax, cnt))
-				{
-					return true;
-				}
-			}
-			else
-			{
-				next = cl;
-			}
-		}
-		if(hr)
-		{
-			if(cr < 0)
-			{
-				if(tri_leaf_hit<STATS>(sv, ~cr, o, d, tmax, cnt))
-				{
-					return true;
-				}
-			}
-			else if(next < 0)
-			{
-				next = cr;
-			}
-			else if(sp < SKR_BVH_STACK)
-			{
-				stack[sp++] = cr;
-			}
-			else
-			{
-				atomicOr(sv.err, 2); // deeper than any LBVH over 63-bit codes + index bits can be; reported, never silent
-			}
-		}
-		if(next < 0)
-		{
-			if(sp == 0)
-			{
-				return false;
-			}
-			next = stack[--sp];
-		}
-		node = next;
 	}
+}
+
+// DEFERRED query (single-sample camera rays of non --gillum frames, see tri_deferred_kernel): decide what can be decided
+// at once -- 1: a triangle is hit (an outsized one), 0: none can be (the line misses both boxes under the root) -- and
+// answer 2 for the rest: candidates, handed to tri_deferred_kernel as one dense work list.
+template <bool STATS>
+SKR_DEV int tri_any_hit_line_deferred(const SceneView &sv, float3 o, float3 d, float tmax, Counters &cnt)
+{
+	if(tri_big_hit<STATS>(sv, o, d, tmax, cnt))
+	{
+		return 1;
+	}
+	const float4 n0 = __ldg(sv.bvh + 0), n1 = __ldg(sv.bvh + 1), n2 = __ldg(sv.bvh + 2);
+	const float3 inv = f3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
+	bool hl, hr;
+	line_hits_boxes(o, inv, tmax, n0, n1, n2, hl, hr);
+	if(STATS && !(hl || hr))
+	{
+		cnt.nv++; // (a candidate's root visit is counted when tri_deferred_kernel walks it)
+	}
+	return (hl || hr) ? 2 : 0;
 }

@@ -774,9 +774,11 @@ SKR_DEV float3 gi_child_dir(float r1, float r2, float3 n, float3 nt, float3 nb)
 // One closest-hit query = the first half of shade() (src/raytrace.h:149-192).
 // Returns: -2 background, -1 triangle (black), >= 0 sphere index with t in tmin.
 // ------------------------------------------------------------------------------------------------
+// `cand` (PRIMARY only, optional): when non-null the triangle query is DEFERRED -- *cand is set for rays whose line
+// reaches the hierarchy under the root, and the ray is answered as if no triangle were hit; tri_deferred_kernel settles it.
 template <bool PRIMARY, bool STATS, bool TRIS>
 SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float3 o, float3 d, float &tmin, Counters &cnt, bool masked = false,
-						uint32_t pmask = 0)
+						uint32_t pmask = 0, bool *cand = nullptr)
 {
 	if(STATS)
 	{
@@ -784,9 +786,21 @@ SKR_DEV int closest_hit(const float4 *__restrict__ B, const SceneView &sv, float
 	}
 	const int s = (PRIMARY && masked) ? closest_sphere_masked<STATS, TRIS>(B + sv.off_pprim, pmask, sv.S, d, tmin, cnt)
 									  : closest_sphere<PRIMARY, STATS>(B, sv, o, d, tmin, cnt);
-	if(TRIS && sv.T > 0 && tri_any_hit_line<STATS>(sv, o, d, tmin, cnt))
+	if(TRIS && sv.T > 0)
 	{
-		return -1;
+		if(PRIMARY && cand)
+		{
+			const int r = tri_any_hit_line_deferred<STATS>(sv, o, d, tmin, cnt);
+			if(r == 1)
+			{
+				return -1;
+			}
+			*cand = r == 2;
+		}
+		else if(tri_any_hit_line<STATS>(sv, o, d, tmin, cnt))
+		{
+			return -1;
+		}
 	}
 	if(s < 0)
 	{

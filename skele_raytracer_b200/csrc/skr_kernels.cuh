@@ -77,6 +77,12 @@ struct FrameParams
 	// stream-ordered wait on the copy stream is parked on.  Null when unused.
 	unsigned *band_count, *band_flag;
 	unsigned band_ctas, band_seq;
+	// Deferred triangle query (single-sample frames over a real hierarchy, see tri_deferred_kernel): candidates = camera rays
+	// whose line reaches the hierarchy under the root; (direction, tmax) + local pixel index, counter pair (count, CTAs done)
+	float4 *cand_d;
+	uint32_t *cand_lp;
+	unsigned *cand_count;
+	int defer;
 	long long *accum; // SKR_ACC_STRIDE per local pixel (gi / fresnel frames only)
 	unsigned long long *counters; // 9 device counters (STATS)
 	int *err;
@@ -173,6 +179,75 @@ SKR_DEV void accum_add(long long *accum, long long lp, float3 c, long long ex = 
 	{
 		atomicOr(a + 3, (unsigned long long) fl);
 	}
+}
+// accum_add for a whole warp (all 32 lanes call; `valid` lanes hold a contribution for local pixel lp).  The entries a
+// warp of shade_expand_kernel holds are siblings and cousins: most of its lanes add to the SAME one or two pixels, and 96
+// reductions per warp would serialise on a handful of L2 addresses.  Lanes are therefore grouped into runs of equal
+// pixel; an exact integer prefix sum over the warp (5 shuffle steps per channel) gives every run's total as a difference
+// of two prefix values, and only the last lane of each run touches memory.  Integer arithmetic: the frame stays
+// bit-identical to per-lane atomics.  (SKR_ACC_SEGMENTED=0 compiles the per-lane form.)
+#ifndef SKR_ACC_SEGMENTED
+#define SKR_ACC_SEGMENTED 1
+#endif
+SKR_DEV void accum_add_warp(long long *accum, long long lp, float3 c, bool valid, long long ex = 0, long long ey = 0, long long ez = 0, unsigned efl = 0)
+{
+#if SKR_ACC_SEGMENTED
+	const unsigned lane = threadIdx.x & 31u;
+	unsigned fl			= valid ? efl : 0u;
+	long long x = 0, y = 0, z = 0;
+	if(valid)
+	{
+		x = to_fixed(c.x, fl, 0) + ex, y = to_fixed(c.y, fl, 1) + ey, z = to_fixed(c.z, fl, 2) + ez;
+	}
+	const long long key	 = valid ? lp : -1 - (long long) lane; // invalid lanes: runs of their own, never written
+	const long long prev = __shfl_up_sync(0xffffffffu, key, 1), next = __shfl_down_sync(0xffffffffu, key, 1);
+	const bool head		 = lane == 0 || prev != key;
+	const bool tail		 = lane == 31 || next != key;
+	const unsigned heads = __ballot_sync(0xffffffffu, head);
+	if(__any_sync(0xffffffffu, fl != 0u) || __popc(heads) > 20) // non-finite terms (rare), or nothing to merge: lane by lane
+	{
+		if(valid)
+		{
+			unsigned long long *a = reinterpret_cast<unsigned long long *>(accum + SKR_ACC_STRIDE * lp);
+			atomicAdd(a + 0, (unsigned long long) x);
+			atomicAdd(a + 1, (unsigned long long) y);
+			atomicAdd(a + 2, (unsigned long long) z);
+			if(fl)
+			{
+				atomicOr(a + 3, (unsigned long long) fl);
+			}
+		}
+		return;
+	}
+#pragma unroll
+	for(int off = 1; off < 32; off <<= 1)
+	{
+		const long long tx = __shfl_up_sync(0xffffffffu, x, off), ty = __shfl_up_sync(0xffffffffu, y, off), tz = __shfl_up_sync(0xffffffffu, z, off);
+		if((int) lane >= off)
+		{
+			x += tx, y += ty, z += tz;
+		}
+	}
+	const int start = 31 - __clz((int) (heads & (0xffffffffu >> (31u - lane)))); // head of this lane's run
+	const int from	= start > 0 ? start - 1 : 0;
+	long long bx = __shfl_sync(0xffffffffu, x, from), by = __shfl_sync(0xffffffffu, y, from), bz = __shfl_sync(0xffffffffu, z, from);
+	if(start == 0)
+	{
+		bx = by = bz = 0;
+	}
+	if(tail && valid)
+	{
+		unsigned long long *a = reinterpret_cast<unsigned long long *>(accum + SKR_ACC_STRIDE * lp);
+		atomicAdd(a + 0, (unsigned long long) (x - bx));
+		atomicAdd(a + 1, (unsigned long long) (y - by));
+		atomicAdd(a + 2, (unsigned long long) (z - bz));
+	}
+#else
+	if(valid)
+	{
+		accum_add(accum, lp, c, ex, ey, ez, efl);
+	}
+#endif
 }
 SKR_DEV float3 accum_load(const long long *accum, long long lp)
 {
@@ -370,6 +445,27 @@ SKR_DEV void queue_push(const Queue &q, bool want, float3 o, uint32_t pixel, flo
 		queue_store(q, base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u)), o, pixel, thr, node, sample, sphere, dir, t, err);
 	}
 }
+// candidate of the deferred triangle query; must be called by all 32 lanes
+SKR_DEV void cand_push(const FrameParams &fp, bool want, long long lp, float3 d, float tmax)
+{
+	const unsigned mask = __ballot_sync(0xffffffffu, want);
+	if(mask == 0u)
+	{
+		return;
+	}
+	unsigned base = 0;
+	if((threadIdx.x & 31) == 0)
+	{
+		base = atomicAdd(fp.cand_count, (unsigned) __popc(mask));
+	}
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if(want)
+	{
+		const unsigned idx = base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
+		fp.cand_d[idx]	   = make_float4(d.x, d.y, d.z, tmax);
+		fp.cand_lp[idx]	   = (uint32_t) lp;
+	}
+}
 // consumer side: the hit point of an entry, src/raytrace.h:197-204 (exact t, then P = o + d * t)
 SKR_DEV float3 queue_hit_point(const float4 *__restrict__ B, const SceneView &sv, const float4 &qa, const float4 &qd, int sidx)
 {
@@ -489,9 +585,14 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 
 		float t = 0.0f;
 		int h	= -3;
+		bool cand = false;
 		if(p.valid)
 		{
-			h = closest_hit<true, STATS, TRIS>(B, sv, o, d, t, cnt, cull, pmask);
+			h = closest_hit<true, STATS, TRIS>(B, sv, o, d, t, cnt, cull, pmask, (TRIS && !GI && fp.defer) ? &cand : nullptr);
+		}
+		if(TRIS && !GI && fp.defer)
+		{
+			cand_push(fp, cand, lp, d, t); // settled by tri_deferred_kernel: the pixel is written below as if no triangle were hit
 		}
 		if(h == -2)
 		{
@@ -973,20 +1074,23 @@ __global__ void __launch_bounds__(SKR_BLOCK, LEAF ? SKR_LEAF_MIN_BLOCKS : SKR_MI
 			leaf_drain<STATS, FOG>(B, sv, fp, ls, o, rng, cnt, true);
 		}
 	}
-	if(valid)
 	{
-		const int x = (int) (rng.pixel % (uint32_t) fp.width), y = (int) (rng.pixel / (uint32_t) fp.width);
-		const long long lp = encode_pixel(fp, x, y);
+		long long lp = 0;
+		if(valid)
+		{
+			const int x = (int) (rng.pixel % (uint32_t) fp.width), y = (int) (rng.pixel / (uint32_t) fp.width);
+			lp			= encode_pixel(fp, x, y);
+		}
 		if constexpr(LEAF)
 		{
 			long long ex, ey, ez;
 			unsigned efl;
 			leaf_total(ls, threadIdx.x & 31u, ex, ey, ez, efl);
-			accum_add(fp.accum, lp, contrib, ex, ey, ez, efl);
+			accum_add_warp(fp.accum, lp, contrib, valid, ex, ey, ez, efl);
 		}
 		else
 		{
-			accum_add(fp.accum, lp, contrib);
+			accum_add_warp(fp.accum, lp, contrib, valid);
 		}
 	}
 	flush_counters<STATS>(fp, cnt);
@@ -1092,6 +1196,89 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 		const int x = (int) (pixel % (uint32_t) fp.width), y = (int) (pixel / (uint32_t) fp.width);
 		const long long lp = encode_pixel(fp, x, y);
 		accum_add(fp.accum, lp, contrib);
+	}
+	flush_counters<STATS>(fp, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tri_deferred_kernel: the triangle half of shade() (src/raytrace.h:169-186) for the CANDIDATES primary_kernel set aside.
+//
+// In a frame like dragon.scn's most camera rays are settled by two outsized triangles or miss the model's bounds; the
+// few that reach the hierarchy walk 20-40 nodes each.  Traced in place they leave most lanes and most warp slots idle
+// (round 1: 18.7 of 32 lanes, 22 % of the warp slots, 0.29 ms).  Here they are ONE dense work list and the kernel is
+// persistent: a wave of CTAs, every warp owning the 32-ray groups w, w + W, w + 2W, ... of the list; each lane walks one
+// line, one node per loop iteration, and lanes whose query is over are REFILLED with the next rays of the warp's sequence
+// (as soon as 8 are idle) instead of waiting for the slowest lane.  A hit blackens the pixel primary_kernel wrote
+// (any accepted triangle shades black, src/raytrace.h:221-224); no hit leaves it.  Same arithmetic, same answer as the
+// in-place query (SKR_NO_DEFER=1; tested bit for bit).
+// ------------------------------------------------------------------------------------------------
+#define SKR_DEFER_REFILL 8
+template <bool STATS>
+__global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneView sv, const FrameParams fp)
+{
+	Counters cnt;
+	zero(cnt);
+	const unsigned count = *reinterpret_cast<volatile unsigned *>(fp.cand_count);
+	const unsigned lane	 = threadIdx.x & 31u;
+	const unsigned NW	 = gridDim.x * (blockDim.x >> 5);
+	const unsigned w	 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	unsigned pos		 = 0; // position in this warp's sequence (uniform)
+	bool active			 = false;
+	uint32_t lp			 = 0;
+	TriWalk wk;
+	wk.o = wk.d = wk.inv = f3(0.0f, 0.0f, 0.0f);
+	wk.tmax = 0.0f;
+	wk.node = wk.sp = 0;
+	int stack[SKR_BVH_STACK];
+	for(;;)
+	{
+		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+		const bool more		= (unsigned long long) ((pos >> 5) * NW + w) * 32ull < count;
+		if(more && (idle == 0xffffffffu || __popc(idle) >= SKR_DEFER_REFILL))
+		{
+			if(!active)
+			{
+				const unsigned my			= pos + __popc(idle & ((1u << lane) - 1u));
+				const unsigned long long g	= (unsigned long long) ((my >> 5) * NW + w) * 32ull + (my & 31u);
+				if(g < count)
+				{
+					const float4 c = __ldg(fp.cand_d + g);
+					lp			   = __ldg(fp.cand_lp + g);
+					tri_walk_begin(wk, sv.cam_pos, f3(c), c.w);
+					active = true;
+				}
+			}
+			pos += (unsigned) __popc(idle);
+		}
+		else if(idle == 0xffffffffu)
+		{
+			break;
+		}
+		if(active)
+		{
+			const int r = tri_walk_step<STATS>(sv, wk, stack, cnt);
+			if(r >= 0)
+			{
+				if(r == 1)
+				{
+					const PixelId p = decode_pixel(fp, (long long) lp);
+					write_pixel(fp, (long long) lp, p, f3(0.0f, 0.0f, 0.0f));
+				}
+				active = false;
+			}
+		}
+	}
+	__syncthreads();
+	if(threadIdx.x == 0)
+	{
+		// every CTA has read the count: the last one to leave re-arms the pair for the next frame
+		__threadfence();
+		if(atomicAdd(fp.cand_count + 1, 1u) == gridDim.x - 1u)
+		{
+			fp.cand_count[0] = 0u;
+			fp.cand_count[1] = 0u;
+			__threadfence();
+		}
 	}
 	flush_counters<STATS>(fp, cnt);
 }

@@ -298,6 +298,24 @@ def test_bvh_equals_brute_force(gpu, ntris):
     assert np.array_equal(a32, b32)
 
 
+@pytest.mark.parametrize("scene,kw", [("dragon", dict(width=1920, height=1080)), ("dragon", dict(width=333, height=187, fov=25.0)),
+                                      ("test", dict(width=640, height=360, use_shadows=True)), ("test", dict(width=200, height=120, rank=1, world=3, tile=16))])
+def test_deferred_triangle_query_equals_the_query_in_place(gpu, gscenes, scene, kw):
+    """Single-sample frames hand the camera rays that reach the hierarchy to tri_deferred_kernel (a dense, persistent,
+    lane-refilling traversal); the frame must be the one the in-place query gives (SKR_NO_DEFER=1), bit for bit."""
+    gpu.upload(gscenes[scene])
+    o = S.Options(collect_stats=True, **kw)
+    a32, a8, sa = gpu.render(o)
+    os.environ["SKR_NO_DEFER"] = "1"
+    try:
+        b32, b8, sb = gpu.render(o)
+    finally:
+        del os.environ["SKR_NO_DEFER"]
+    assert np.array_equal(a32.view(np.uint32), b32.view(np.uint32)) and np.array_equal(a8, b8)
+    assert sa.kernel_launches == sb.kernel_launches + 1 and sa.tri_tests == sb.tri_tests and sa.closest_hit_rays == sb.closest_hit_rays
+    assert sa.bvh_node_visits == sb.bvh_node_visits
+
+
 def test_bvh_dragon_1080p_equals_brute_force_window(gpu, port, scenes, gscenes):
     oo, go = opts(width=1920, height=1080)
     gpu.upload(gscenes["dragon"])
@@ -346,13 +364,13 @@ def test_gi_energy_bookkeeping_matches_ray_counts(gpu, gscenes):
     == primary samples + n * (hits that the reference would expand)."""
     gpu.upload(gscenes["bear"])
     w, h, n, depth = 320, 180, 8, 3
-    st = gpu.render(S.Options(width=w, height=h, max_depth=depth, monte_carlo=True, num_path_traces=n, collect_stats=True, seed=4),
+    st = gpu.render(S.Options(width=w, height=h, max_depth=depth, monte_carlo=True, num_path_traces=n, collect_stats=True, seed=4, use_shadows=True),
                     want_rgb8=False, want_rgb32=False)[2]
-    # depth-1 hits (the leaves) are shaded in place by the warp that found them, never queued
+    # depth-1 hits (the leaves) are shaded in place by the warp that found them (frames with shadow rays), never queued
     assert 0 < st.queue_entries < st.sphere_hits
     os.environ["SKR_NO_LEAF_INLINE"] = "1"
     try:
-        st2 = gpu.render(S.Options(width=w, height=h, max_depth=depth, monte_carlo=True, num_path_traces=n, collect_stats=True, seed=4),
+        st2 = gpu.render(S.Options(width=w, height=h, max_depth=depth, monte_carlo=True, num_path_traces=n, collect_stats=True, seed=4, use_shadows=True),
                          want_rgb8=False, want_rgb32=False)[2]
     finally:
         del os.environ["SKR_NO_LEAF_INLINE"]
@@ -551,7 +569,11 @@ def test_leaves_in_place_equal_leaves_through_the_queue(gpu, gscenes, scene, kw)
     frame (float bit patterns) and every device counter must equal the all-queued wavefront (SKR_NO_LEAF_INLINE=1)."""
     gpu.upload(gscenes[scene])
     o = S.Options(collect_stats=True, **kw)
-    a32, a8, sa = gpu.render(o)
+    os.environ["SKR_LEAF_INLINE"] = "1"      # (by default only frames with shadow rays take the in-place path)
+    try:
+        a32, a8, sa = gpu.render(o)
+    finally:
+        del os.environ["SKR_LEAF_INLINE"]
     os.environ["SKR_NO_LEAF_INLINE"] = "1"
     try:
         b32, b8, sb = gpu.render(o)
