@@ -411,6 +411,33 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
     return out
 
 
+def measure_native(S, torch, workload, n_gpus, steps):
+    """e2e through the shipped single-process multi-GPU C API (include/skr_mgpu.h): skr_mgpu_scene_upload + skr_mgpu_render
+    into pinned host memory every step, wall clock.  Run by rank 0 alone (it drives all n_gpus GPUs itself) while the other
+    ranks wait at a HOST barrier."""
+    import numpy as np  # noqa: F401
+
+    scene_name, kw, desc = WORKLOADS[workload]
+    scene = S.Scene.load(os.path.join(GOLD, scene_name + ".npz"))
+    opt = S.Options(seed=SEED, **kw)
+    m = S.MgpuRenderer(n_gpus)
+    try:
+        host = torch.empty((opt.height, opt.width, 3), dtype=torch.uint8).pin_memory().numpy()
+        for _ in range(2):
+            m.upload(scene)
+            m.render(opt, host)
+        t0 = time.time()
+        for _ in range(steps):
+            m.upload(scene)
+            m.render(opt, host)
+        t1 = time.time()
+        return {"ms_per_step": (t1 - t0) * 1e3 / steps, "steps": steps, "frame_nonzero": bool(host.any()),
+                "path": f"skr_mgpu_scene_upload + skr_mgpu_render (one process, {n_gpus} GPUs, every GPU stores its tiles into the pinned host frame "
+                        "over its own PCIe link), wall clock"}
+    finally:
+        m.close()
+
+
 def roofline_of(m, world, peaks, peaks_src, fp32_peak, bw):
     """Roofline of the dominant kernel AS LAUNCHED ON RANK 0: its own share of the frame's work / its own duration."""
     st0 = m["stats_rank0"]
@@ -469,11 +496,13 @@ def main_gpu(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     dist = None
+    host_group = None
     if world > 1:
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner to STDOUT; keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")  # host-side barriers (no kernel spinning on a GPU while rank 0 drives all of them)
     r = S.Renderer(local_rank)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     steps, warmup = max(1, args.steps), max(3, args.warmup)
@@ -491,6 +520,22 @@ def main_gpu(args, rank, world, local_rank):
         for w in WORKLOADS:
             if w not in results:
                 results[w] = measure_gpu(S, torch, dist, r, w, max(1, min(steps, MAX_STEPS[w])), 3, rank, world, flush_buf)
+
+    # the shipped single-process multi-GPU API over the same GPUs: rank 0 drives all of them, the others wait on the host
+    native = {}
+    if world > 1 and not args.no_native:
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
+        if rank == 0:
+            for w in results:
+                try:
+                    nv = measure_native(S, torch, w, world, max(3, min(results[w]["steps"], 10)))
+                    nv["value"] = results[w]["rays"] / (nv["ms_per_step"] * 1e-3) / 1e6
+                    nv["unit"] = "Mrays/s"
+                    native[w] = nv
+                except Exception as e:  # reported, never fatal for the distributed numbers
+                    native[w] = {"error": str(e)[:300]}
+        dist.barrier(group=host_group)
 
     cpu = {}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -521,7 +566,7 @@ def main_gpu(args, rank, world, local_rank):
             configs[w] = {"workload": o["desc"], "ms_per_frame": o["ms_per_step"], "ms_per_frame_median_this_rank": o["ms_per_step_median"],
                           "ms_per_frame_min_this_rank": o["ms_per_step_min"], "mrays_per_s": o["value"], "rays_per_frame": o["rays"], "steps": o["steps"],
                           "warmup": o["warmup"], "kernel_launches_per_frame": o["launches"] / o["steps"], "first_frame_ms": o["first_frame_ms"],
-                          "reserve_ms": o["reserve_ms"], "e2e": o.get("e2e"), "frame_split": frame_split_text(o, world),
+                          "reserve_ms": o["reserve_ms"], "e2e": o.get("e2e"), "e2e_native": native.get(w), "frame_split": frame_split_text(o, world),
                           "roofline": roofline_of(o, world, peaks, peaks_src, fp32_peak, bw), "cpu_baseline": cpu_block(w)}
         line = {
             "metric": "Mrays/s", "value": m["value"], "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -534,6 +579,7 @@ def main_gpu(args, rank, world, local_rank):
                        "wall_ms_per_step_incl_flush": m["wall_ms_per_step"]},
             "clocks": clocks,
             "e2e": m.get("e2e"),
+            "e2e_native": native.get(args.workload),
             "gpu_launches": m["launches"],
             "roofline": roofline_of(m, world, peaks, peaks_src, fp32_peak, bw),
             "cpu_baseline": None if args.workload not in cpu else {k: cpu[args.workload][0][k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -580,6 +626,7 @@ def main():
     ap.add_argument("--only-headline", action="store_true", help="skip the `configs` block (the other BASELINE.json configs)")
     ap.add_argument("--all-configs", action="store_true", help="(default now; kept for compatibility)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-native", action="store_true", help="skip e2e_native (skr_mgpu_render driven by rank 0) at N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

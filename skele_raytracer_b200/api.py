@@ -326,6 +326,59 @@ class Renderer:
         return float(self.lib.skr_measure_bandwidth(self.ctx, level))
 
 
+class MgpuRenderer:
+    """include/skr_mgpu.h: ONE process driving every GPU of the box (one host thread and one skr_ctx per GPU); the frame
+    arrives in host memory, every GPU storing its tiles over its own PCIe link."""
+
+    def __init__(self, n_gpus: int = 0):
+        path = os.path.join(_HERE, "libskr_mgpu.so")
+        if not os.path.exists(path):
+            raise SkrError(f"{path} is missing (built only where nccl.h is installed): `make -C host`")
+        C.CDLL(lib_path(), mode=C.RTLD_GLOBAL)
+        L = C.CDLL(path)
+        L.skr_mgpu_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.skr_mgpu_destroy.argtypes = [C.c_void_p]
+        L.skr_mgpu_last_error.restype = C.c_char_p
+        L.skr_mgpu_last_error.argtypes = [C.c_void_p]
+        L.skr_mgpu_world.argtypes = [C.c_void_p]
+        L.skr_mgpu_scene_upload.argtypes = [C.c_void_p, C.POINTER(_SceneDesc)]
+        L.skr_mgpu_render.argtypes = [C.c_void_p, C.POINTER(_Options), C.c_void_p, C.POINTER(Stats)]
+        self.lib = L
+        self.h = C.c_void_p()
+        rc = L.skr_mgpu_init(n_gpus, C.byref(self.h))
+        if rc:
+            self.h = None
+            raise SkrError(f"skr_mgpu_init failed ({rc}): {L.skr_mgpu_last_error(None).decode()}")
+
+    def world(self) -> int:
+        return int(self.lib.skr_mgpu_world(self.h))
+
+    def _check(self, rc, what):
+        if rc:
+            raise SkrError(f"{what} failed ({rc}): {self.lib.skr_mgpu_last_error(self.h).decode()}")
+
+    def upload(self, scene: Scene) -> None:
+        d, keep = scene._desc()
+        self._check(self.lib.skr_mgpu_scene_upload(self.h, C.byref(d)), "skr_mgpu_scene_upload")
+
+    def render(self, option: Options, rgb8: np.ndarray, want_stats: bool = False):
+        st = Stats() if want_stats else None
+        o = option._c()
+        self._check(self.lib.skr_mgpu_render(self.h, C.byref(o), rgb8.ctypes.data, C.byref(st) if want_stats else None), "skr_mgpu_render")
+        return st
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.skr_mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def generate_rays_parallel(scene: Scene, option: Options, output: str, renderer: Renderer | None = None) -> np.ndarray:
     """void generate_rays_parallel(Scene scene, Options option, char *output)  (reference src/main.cpp:19-104):
     renders the frame and writes the binary PPM.  Returns the RGB8 image as well."""

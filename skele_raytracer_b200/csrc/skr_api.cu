@@ -123,8 +123,8 @@ struct skr_ctx
 
 	unsigned long long *d_counters = nullptr; // 9 (16 allocated)
 	float4 *d_cand_d = nullptr; // deferred triangle query: candidates (tri_deferred_kernel)
-	uint32_t *d_cand_lp = nullptr;
-	size_t cand_d_bytes = 0, cand_lp_bytes = 0;
+	uint2 *d_cand_px = nullptr;
+	size_t cand_d_bytes = 0, cand_px_bytes = 0;
 	unsigned *d_cursor = nullptr;			  // (next strip, CTAs done) of the persistent primary_kernel; self-resetting
 	int *d_err = nullptr;
 	int *h_err = nullptr; // pinned
@@ -830,9 +830,9 @@ int prepare_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	if(pl.defer)
 	{
 		CK(ensure(ctx->d_cand_d, ctx->cand_d_bytes, sizeof(float4) * (size_t) pl.npix_local));
-		CK(ensure(ctx->d_cand_lp, ctx->cand_lp_bytes, sizeof(uint32_t) * (size_t) pl.npix_local));
+		CK(ensure(ctx->d_cand_px, ctx->cand_px_bytes, sizeof(uint2) * (size_t) pl.npix_local));
 		fp.cand_d	  = ctx->d_cand_d;
-		fp.cand_lp	  = ctx->d_cand_lp;
+		fp.cand_px	  = ctx->d_cand_px;
 		fp.cand_count = ctx->d_cursor + 2;
 		fp.defer	  = 1;
 		return SKR_OK;
@@ -1147,7 +1147,7 @@ int skr_init(int device, skr_ctx **out)
 	{
 		return bail(e, "cudaMalloc");
 	}
-	if((e = cudaMalloc(&c->d_cursor, 4 * sizeof(unsigned))) != cudaSuccess || (e = cudaMemset(c->d_cursor, 0, 4 * sizeof(unsigned))) != cudaSuccess)
+	if((e = cudaMalloc(&c->d_cursor, 8 * sizeof(unsigned))) != cudaSuccess || (e = cudaMemset(c->d_cursor, 0, 8 * sizeof(unsigned))) != cudaSuccess)
 	{
 		return bail(e, "cudaMalloc");
 	}
@@ -1202,7 +1202,7 @@ void skr_destroy(skr_ctx *ctx)
 	ctx->bvh_shade.release();
 	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
 	cudaFree(ctx->d_arena);
-	cudaFree(ctx->d_cursor), cudaFree(ctx->d_cand_d), cudaFree(ctx->d_cand_lp);
+	cudaFree(ctx->d_cursor), cudaFree(ctx->d_cand_d), cudaFree(ctx->d_cand_px);
 	cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band);
 	if(ctx->copy_stream)
 	{
@@ -1271,7 +1271,7 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		return fail(ctx, SKR_ERR_ARG, "skr_scene_upload: null array with nonzero count");
 	}
 	ctx->have_scene = false;
-	CK(cudaMemsetAsync(ctx->d_cursor, 0, 4 * sizeof(unsigned), ctx->stream)); // (a frame that died mid-kernel may have left the counter pairs armed)
+	CK(cudaMemsetAsync(ctx->d_cursor, 0, 8 * sizeof(unsigned), ctx->stream)); // (a frame that died mid-kernel may have left the counter pairs armed)
 	const int S = sc->nspheres, T = sc->ntris, L = sc->nplights, D = sc->ndlights, F = sc->nfogs;
 	const int S4 = (S + 3) / 4 * 4;
 	SceneView &sv = ctx->sv;

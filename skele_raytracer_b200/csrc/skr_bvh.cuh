@@ -190,9 +190,13 @@ SKR_DEV bool tri_any_hit_line(const SceneView &sv, float3 o, float3 d, float tma
 	}
 }
 
-// DEFERRED query (single-sample camera rays of non --gillum frames, see tri_deferred_kernel): decide what can be decided
-// at once -- 1: a triangle is hit (an outsized one), 0: none can be (the line misses both boxes under the root) -- and
-// answer 2 for the rest: candidates, handed to tri_deferred_kernel as one dense work list.
+// DEFERRED query (single-sample camera rays of non --gillum frames, see tri_deferred_kernel): walk at most SKR_DEFER_STEPS
+// nodes in place -- enough for the many lines that only graze the model's bounds -- and answer 1: a triangle is hit,
+// 0: none is, 2: undecided.  Undecided rays become candidates: tri_deferred_kernel walks them (from the root again) as
+// one dense work list.
+#ifndef SKR_DEFER_STEPS
+#define SKR_DEFER_STEPS 6
+#endif
 template <bool STATS>
 SKR_DEV int tri_any_hit_line_deferred(const SceneView &sv, float3 o, float3 d, float tmax, Counters &cnt)
 {
@@ -200,13 +204,24 @@ SKR_DEV int tri_any_hit_line_deferred(const SceneView &sv, float3 o, float3 d, f
 	{
 		return 1;
 	}
-	const float4 n0 = __ldg(sv.bvh + 0), n1 = __ldg(sv.bvh + 1), n2 = __ldg(sv.bvh + 2);
-	const float3 inv = f3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
-	bool hl, hr;
-	line_hits_boxes(o, inv, tmax, n0, n1, n2, hl, hr);
-	if(STATS && !(hl || hr))
+	TriWalk w;
+	tri_walk_begin(w, o, d, tmax);
+	int stack[SKR_DEFER_STEPS + 1];
+	Counters c2; // the prefix of an undecided walk is walked again by tri_deferred_kernel: counted there, not here
+	zero(c2);
+#pragma unroll 1
+	for(int k = 0; k < SKR_DEFER_STEPS; k++)
 	{
-		cnt.nv++; // (a candidate's root visit is counted when tri_deferred_kernel walks it)
+		const int r = tri_walk_step<STATS>(sv, w, stack, c2);
+		if(r >= 0)
+		{
+			if(STATS)
+			{
+				cnt.nv += c2.nv;
+				cnt.tt += c2.tt;
+			}
+			return r;
+		}
 	}
-	return (hl || hr) ? 2 : 0;
+	return 2;
 }

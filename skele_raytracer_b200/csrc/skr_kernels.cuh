@@ -80,8 +80,8 @@ struct FrameParams
 	// Deferred triangle query (single-sample frames over a real hierarchy, see tri_deferred_kernel): candidates = camera rays
 	// whose line reaches the hierarchy under the root; (direction, tmax) + local pixel index, counter pair (count, CTAs done)
 	float4 *cand_d;
-	uint32_t *cand_lp;
-	unsigned *cand_count;
+	uint2 *cand_px;		  // (y * width + x, index into the compact tile buffer)
+	unsigned *cand_count; // [0] candidates, [1] CTAs done, [2] fetch cursor of tri_deferred_kernel
 	int defer;
 	long long *accum; // SKR_ACC_STRIDE per local pixel (gi / fresnel frames only)
 	unsigned long long *counters; // 9 device counters (STATS)
@@ -446,7 +446,7 @@ SKR_DEV void queue_push(const Queue &q, bool want, float3 o, uint32_t pixel, flo
 	}
 }
 // candidate of the deferred triangle query; must be called by all 32 lanes
-SKR_DEV void cand_push(const FrameParams &fp, bool want, long long lp, float3 d, float tmax)
+SKR_DEV void cand_push(const FrameParams &fp, bool want, long long lp, const PixelId &p, float3 d, float tmax)
 {
 	const unsigned mask = __ballot_sync(0xffffffffu, want);
 	if(mask == 0u)
@@ -463,7 +463,9 @@ SKR_DEV void cand_push(const FrameParams &fp, bool want, long long lp, float3 d,
 	{
 		const unsigned idx = base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
 		fp.cand_d[idx]	   = make_float4(d.x, d.y, d.z, tmax);
-		fp.cand_lp[idx]	   = (uint32_t) lp;
+		const int tpix	   = fp.tile * fp.tile;
+		fp.cand_px[idx]	   = make_uint2((uint32_t) (p.y * fp.width + p.x),
+										(uint32_t) ((lp / tpix) * tpix + (long long) (p.y % fp.tile) * fp.tile + (p.x % fp.tile)));
 	}
 }
 // consumer side: the hit point of an entry, src/raytrace.h:197-204 (exact t, then P = o + d * t)
@@ -592,7 +594,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		}
 		if(TRIS && !GI && fp.defer)
 		{
-			cand_push(fp, cand, lp, d, t); // settled by tri_deferred_kernel: the pixel is written below as if no triangle were hit
+			cand_push(fp, cand, lp, p, d, t); // settled by tri_deferred_kernel: the pixel is written below as if no triangle were hit
 		}
 		if(h == -2)
 		{
@@ -718,9 +720,11 @@ struct LeafStage
 //   1  64-bit shared-memory atomics (compile to ATOMS.CAST.SPIN loops; a parent's leaves collide on one address)
 //   2  MATCH.ANY on the parent lane + REDUX.SUM over each group on 16/16/32-bit limbs, group leader adds
 //   3  native 32-bit shared-memory atomics on 16/16/32-bit limbs (accumulator = 3 x u32 per channel, carries folded at the end)
+//   4  runs of equal parent (the ring is filled parent by parent) summed by an integer prefix scan over the warp; one
+//      64-bit atomic triple per run
 //   0  nothing (timing experiments only: the image is wrong)
 #ifndef SKR_LEAF_ACC
-#define SKR_LEAF_ACC 1
+#define SKR_LEAF_ACC 4
 #endif
 SKR_DEV void leaf_accumulate(const LeafStage &ls, bool act, unsigned lane, int src, long long fx, long long fy, long long fz, unsigned fl)
 {
@@ -758,6 +762,46 @@ SKR_DEV void leaf_accumulate(const LeafStage &ls, bool act, unsigned lane, int s
 		a[1] = q;
 	}
 	__syncwarp();
+#elif SKR_LEAF_ACC == 4
+	// The ring is filled parent by parent (see the staging code), so a parent's leaves sit in consecutive lanes: runs of
+	// equal `src`.  An exact integer prefix sum over the warp gives each run's total as a difference of two prefix values;
+	// only the last lane of a run adds it (atomically: a parent's leaves of two different batches can share a round).
+	const int key		 = act ? src : -1 - (int) lane;
+	const int prev		 = __shfl_up_sync(0xffffffffu, key, 1), next = __shfl_down_sync(0xffffffffu, key, 1);
+	const bool head		 = lane == 0 || prev != key;
+	const bool tail		 = lane == 31 || next != key;
+	const unsigned heads = __ballot_sync(0xffffffffu, head);
+	long long x = fx, y = fy, z = fz;
+#pragma unroll
+	for(int off = 1; off < 32; off <<= 1)
+	{
+		const long long tx = __shfl_up_sync(0xffffffffu, x, off), ty = __shfl_up_sync(0xffffffffu, y, off), tz = __shfl_up_sync(0xffffffffu, z, off);
+		if((int) lane >= off)
+		{
+			x += tx, y += ty, z += tz;
+		}
+	}
+	const int start = 31 - __clz((int) (heads & (0xffffffffu >> (31u - lane))));
+	const int from	= start > 0 ? start - 1 : 0;
+	long long bx = __shfl_sync(0xffffffffu, x, from), by = __shfl_sync(0xffffffffu, y, from), bz = __shfl_sync(0xffffffffu, z, from);
+	if(start == 0)
+	{
+		bx = by = bz = 0;
+	}
+	if(act)
+	{
+		unsigned long long *a = ls.acc + 4 * src;
+		if(tail)
+		{
+			atomicAdd(a + 0, (unsigned long long) (x - bx));
+			atomicAdd(a + 1, (unsigned long long) (y - by));
+			atomicAdd(a + 2, (unsigned long long) (z - bz));
+		}
+		if(fl)
+		{
+			atomicOr(a + 3, (unsigned long long) fl);
+		}
+	}
 #elif SKR_LEAF_ACC == 3
 	// acc viewed as 8 x u32 per parent: [x.a+b<<16 .. ] is NOT used; layout: u32[0..2] = x limbs (a, b, c), [3..5] = y, and the
 	// z limbs + flags live in the second half of the ring-side table (ls.acc2)
@@ -999,19 +1043,26 @@ __global__ void __launch_bounds__(SKR_BLOCK, LEAF ? SKR_LEAF_MIN_BLOCKS : SKR_MI
 			}
 			if constexpr(LEAF)
 			{
-				unsigned at = ls.pending;
+				// parent by parent: lane L's hits of this batch take consecutive slots (leaf_accumulate sums runs of one parent)
+				const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+				unsigned idx	  = ls.pending;
+#pragma unroll
+				for(int k = 0; k < SKR_GI_BATCH; k++)
+				{
+					idx += (unsigned) __popc(m[k] & lt);
+				}
 #pragma unroll
 				for(int k = 0; k < SKR_GI_BATCH; k++)
 				{
 					if(h[k] >= 0)
 					{
-						const unsigned idx	 = at + __popc(m[k] & ((1u << (threadIdx.x & 31)) - 1u));
 						ls.slot[2 * idx]	 = make_float4(d[k].x, d[k].y, d[k].z, t[k]);
 						ls.slot[2 * idx + 1] = make_float4(w[k].x, w[k].y, w[k].z, u2f((uint32_t) h[k] | ((threadIdx.x & 31u) << 16) | ((uint32_t) (c + k) << 21)));
+						idx++;
 					}
-					at += (unsigned) __popc(m[k]);
 				}
-				ls.pending = at;
+				const unsigned at = ls.pending + total;
+				ls.pending		  = at;
 				if(at >= 32u)
 				{
 					leaf_drain<STATS, FOG>(B, sv, fp, ls, o, rng, cnt, false);
@@ -1203,16 +1254,38 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 // ------------------------------------------------------------------------------------------------
 // tri_deferred_kernel: the triangle half of shade() (src/raytrace.h:169-186) for the CANDIDATES primary_kernel set aside.
 //
-// In a frame like dragon.scn's most camera rays are settled by two outsized triangles or miss the model's bounds; the
-// few that reach the hierarchy walk 20-40 nodes each.  Traced in place they leave most lanes and most warp slots idle
+// In a frame like dragon.scn's most camera rays are settled by two outsized triangles or within a few nodes (primary_kernel
+// walks up to SKR_DEFER_STEPS in place); the rest walk 20-40 nodes each.  Traced in place they leave most lanes and most warp slots idle
 // (round 1: 18.7 of 32 lanes, 22 % of the warp slots, 0.29 ms).  Here they are ONE dense work list and the kernel is
-// persistent: a wave of CTAs, every warp owning the 32-ray groups w, w + W, w + 2W, ... of the list; each lane walks one
-// line, one node per loop iteration, and lanes whose query is over are REFILLED with the next rays of the warp's sequence
-// (as soon as 8 are idle) instead of waiting for the slowest lane.  A hit blackens the pixel primary_kernel wrote
+// persistent: a wave of CTAs; each lane walks one line, one node per loop iteration, and lanes whose query is over are
+// REFILLED with the next rays of the list (one atomic fetch per warp, as soon as 8 lanes are idle) instead of waiting for
+// the slowest lane.  A hit blackens the pixel primary_kernel wrote
 // (any accepted triangle shades black, src/raytrace.h:221-224); no hit leaves it.  Same arithmetic, same answer as the
 // in-place query (SKR_NO_DEFER=1; tested bit for bit).
 // ------------------------------------------------------------------------------------------------
 #define SKR_DEFER_REFILL 8
+SKR_DEV void write_black(const FrameParams &fp, uint2 px) // the pixel of a candidate whose line hit a triangle
+{
+	const size_t at = 3 * (size_t) px.x;
+	if(fp.rgb32)
+	{
+		fp.rgb32[at] = fp.rgb32[at + 1] = fp.rgb32[at + 2] = 0.0f;
+	}
+	if(fp.rgb8)
+	{
+		fp.rgb8[at] = fp.rgb8[at + 1] = fp.rgb8[at + 2] = 0;
+	}
+	for(int k = 0; k < fp.n_peers; k++)
+	{
+		uint8_t *o = fp.peers[k] + at;
+		o[0] = o[1] = o[2] = 0;
+	}
+	if(fp.tiles8)
+	{
+		uint8_t *o = fp.tiles8 + 3 * (size_t) px.y;
+		o[0] = o[1] = o[2] = 0;
+	}
+}
 template <bool STATS>
 __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneView sv, const FrameParams fp)
 {
@@ -1220,11 +1293,9 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 	zero(cnt);
 	const unsigned count = *reinterpret_cast<volatile unsigned *>(fp.cand_count);
 	const unsigned lane	 = threadIdx.x & 31u;
-	const unsigned NW	 = gridDim.x * (blockDim.x >> 5);
-	const unsigned w	 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	unsigned pos		 = 0; // position in this warp's sequence (uniform)
 	bool active			 = false;
-	uint32_t lp			 = 0;
+	bool more			 = true; // (uniform) the list may still hold rays
+	uint2 px			 = make_uint2(0u, 0u);
 	TriWalk wk;
 	wk.o = wk.d = wk.inv = f3(0.0f, 0.0f, 0.0f);
 	wk.tmax = 0.0f;
@@ -1233,22 +1304,27 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 	for(;;)
 	{
 		const unsigned idle = __ballot_sync(0xffffffffu, !active);
-		const bool more		= (unsigned long long) ((pos >> 5) * NW + w) * 32ull < count;
 		if(more && (idle == 0xffffffffu || __popc(idle) >= SKR_DEFER_REFILL))
 		{
+			// refill: the idle lanes take the next rays of the list (one fetch per warp)
+			unsigned base = 0;
+			if(lane == 0)
+			{
+				base = atomicAdd(fp.cand_count + 2, (unsigned) __popc(idle));
+			}
+			base = __shfl_sync(0xffffffffu, base, 0);
+			more = base + (unsigned) __popc(idle) < count;
 			if(!active)
 			{
-				const unsigned my			= pos + __popc(idle & ((1u << lane) - 1u));
-				const unsigned long long g	= (unsigned long long) ((my >> 5) * NW + w) * 32ull + (my & 31u);
+				const unsigned g = base + __popc(idle & ((1u << lane) - 1u));
 				if(g < count)
 				{
 					const float4 c = __ldg(fp.cand_d + g);
-					lp			   = __ldg(fp.cand_lp + g);
+					px			   = __ldg(fp.cand_px + g);
 					tri_walk_begin(wk, sv.cam_pos, f3(c), c.w);
 					active = true;
 				}
 			}
-			pos += (unsigned) __popc(idle);
 		}
 		else if(idle == 0xffffffffu)
 		{
@@ -1261,8 +1337,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 			{
 				if(r == 1)
 				{
-					const PixelId p = decode_pixel(fp, (long long) lp);
-					write_pixel(fp, (long long) lp, p, f3(0.0f, 0.0f, 0.0f));
+					write_black(fp, px);
 				}
 				active = false;
 			}
@@ -1271,12 +1346,13 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 	__syncthreads();
 	if(threadIdx.x == 0)
 	{
-		// every CTA has read the count: the last one to leave re-arms the pair for the next frame
+		// every CTA has read the count and made its last fetch: the last one to leave re-arms the counters for the next frame
 		__threadfence();
 		if(atomicAdd(fp.cand_count + 1, 1u) == gridDim.x - 1u)
 		{
 			fp.cand_count[0] = 0u;
 			fp.cand_count[1] = 0u;
+			fp.cand_count[2] = 0u;
 			__threadfence();
 		}
 	}
