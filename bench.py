@@ -583,6 +583,7 @@ def main_gpu(args, rank, world, local_rank):
             "gpu_launches": m["launches"],
             "roofline": roofline_of(m, world, peaks, peaks_src, fp32_peak, bw),
             "cpu_baseline": None if args.workload not in cpu else {k: cpu[args.workload][0][k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "build": S.build_info(),
             "peaks_measured_live": {"fp32_tflops": fp32_peak, **bw, "hbm_gbs": peaks.get("hbm_gbs"), "hbm_source": peaks_src},
             "configs": configs,
         }

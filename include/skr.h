@@ -142,6 +142,7 @@ int skr_init(int device, skr_ctx **out);
 void skr_destroy(skr_ctx *ctx);
 const char *skr_last_error(const skr_ctx *ctx); /* ctx may be NULL: last error of skr_init on this thread */
 int skr_abi_version(void);
+const char *skr_build_info(void); /* ABI 3: compiler, target architectures and tuning macros this binary was built with */
 
 /* Scene upload: AoS -> SoA device buffers (spheres/materials/lights), triangles flattened to
  * float4 vertex triples and a device-built LBVH (Morton codes, radix sort, Karras hierarchy, refit). */

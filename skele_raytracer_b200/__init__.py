@@ -6,5 +6,5 @@ path (`Scene`, `Options`, `parseScene`, `generate_rays_parallel`; reference src/
 src/main.cpp:19) used by the parity tests and bench.py.  It has no rendering code of its own and no CPU
 fallback: importing `api` without a built libskr.so raises.
 """
-from .api import (MgpuRenderer, Options, Renderer, Scene, SkrError, Stats, generate_rays_parallel, lib_path, parseScene,  # noqa: F401
-                  write_ppm)
+from .api import (MgpuRenderer, Options, Renderer, Scene, SkrError, Stats, build_info, generate_rays_parallel, lib_path,  # noqa: F401
+                  parseScene, write_ppm)

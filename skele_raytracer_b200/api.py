@@ -27,6 +27,13 @@ def lib_path() -> str:
     return os.path.join(_HERE, "libskr.so")
 
 
+def build_info() -> str:
+    """skr_build_info(): how the loaded libskr.so was compiled."""
+    L = _load("libskr.so")
+    L.skr_build_info.restype = C.c_char_p
+    return L.skr_build_info().decode()
+
+
 def _load(name: str) -> C.CDLL:
     path = os.path.join(_HERE, name)
     if name == "libskr.so" and os.environ.get("SKR_LIB"):  # developer override: A/B-test a differently built library

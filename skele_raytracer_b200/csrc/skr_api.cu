@@ -125,7 +125,7 @@ struct skr_ctx
 	float4 *d_cand_d = nullptr; // deferred triangle query: candidates (tri_deferred_kernel)
 	uint2 *d_cand_px = nullptr;
 	size_t cand_d_bytes = 0, cand_px_bytes = 0;
-	unsigned *d_cursor = nullptr;			  // (next strip, CTAs done) of the persistent primary_kernel; self-resetting
+	unsigned *d_cursor = nullptr;			  // device counters of the deferred triangle query (candidates, CTAs done, fetch cursor); self-resetting
 	int *d_err = nullptr;
 	int *h_err = nullptr; // pinned
 
@@ -254,32 +254,28 @@ void launch_primary(skr_ctx *ctx, const FrameParams &fp, const Queue &q, long lo
 		}
 	}
 	const long long wpc		= threads / 32;
-	const long long batches = ((n + 31) / 32 + fp.fetch - 1) / fp.fetch;
-	const long long need	= (batches + wpc - 1) / wpc;
-	const long long wave	= (long long) ctx->sm_count * SKR_MIN_BLOCKS;
-	const unsigned blocks	= (unsigned) ((SKR_PRIMARY_MODE == 1 && need > wave) ? wave : need);
-	unsigned *cur		   = ctx->d_cursor;
+	const unsigned blocks = (unsigned) (((n + 31) / 32 + wpc - 1) / wpc);
 	if(!sv.blob_in_smem)
 	{
-		primary_kernel<GI, STATS, false, true, true><<<blocks, threads, 0, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, false, true, true><<<blocks, threads, 0, st>>>(sv, fp, q, lp0, n);
 		return;
 	}
 	const bool tris = sv.T > 0, fog = sv.F > 0;
 	if(tris && fog)
 	{
-		primary_kernel<GI, STATS, true, true, true><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, true, true, true><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n);
 	}
 	else if(tris)
 	{
-		primary_kernel<GI, STATS, true, true, false><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, true, true, false><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n);
 	}
 	else if(fog)
 	{
-		primary_kernel<GI, STATS, true, false, true><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, true, false, true><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n);
 	}
 	else
 	{
-		primary_kernel<GI, STATS, true, false, false><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n, cur);
+		primary_kernel<GI, STATS, true, false, false><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n);
 	}
 }
 
@@ -388,7 +384,7 @@ int build_bvh(skr_ctx *ctx, int T, BvhSet &set, bool mirror)
 	set.valid		= false;
 	set.bvh			= nullptr;
 	// persistent buffers grow on demand and are reused by later uploads (an e2e loop re-uploads the same scene)
-	CK(ensure(set.d_tri_v, set.tri_v_bytes, sizeof(float4) * 3 * (size_t) T));
+	CK(ensure(set.d_tri_v, set.tri_v_bytes, sizeof(float4) * 4 * (size_t) T));
 	const char *nobvh = getenv("SKR_NO_BVH");
 	// a handful of triangles (spheres1.scn has two): testing them all costs less per ray than a node visit, and the
 	// ~27 dependent launches of the build would dominate the upload (0.21 ms against 0.03 ms)
@@ -648,8 +644,6 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		const char *nocull = getenv("SKR_NO_CULL");
 		fp.cull = (sv.off_cull >= 0 && fp.grid > 0 && fp.spp >= 4 && !(nocull && nocull[0] == '1') && std::isfinite(fp.cull_delta)) ? 1 : 0;
 	}
-	// blocks a warp takes per fetch: one where a block is long (jittered samples, BVH traversal), four where pixels are cheap
-	fp.fetch	 = SKR_PRIMARY_MODE == 1 ? ((fp.spp >= 4 || ctx->sv.T > BRUTE_FORCE_TRIS) ? 1 : 4) : 1;
 	fp.node_base = (uint32_t) fp.n_gi + 1u + (fp.fresnel ? 2u * (uint32_t) (ctx->sv.L + ctx->sv.D) : 0u);
 	fp.slot_gi	 = 1u + (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
 	pl.tiles_local = (fp.tiles_total + world - 1) / world;
@@ -833,7 +827,7 @@ int prepare_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		CK(ensure(ctx->d_cand_px, ctx->cand_px_bytes, sizeof(uint2) * (size_t) pl.npix_local));
 		fp.cand_d	  = ctx->d_cand_d;
 		fp.cand_px	  = ctx->d_cand_px;
-		fp.cand_count = ctx->d_cursor + 2;
+		fp.cand_count = ctx->d_cursor;
 		fp.defer	  = 1;
 		return SKR_OK;
 	}
@@ -1097,6 +1091,19 @@ int skr_abi_version(void)
 	return SKR_ABI_VERSION;
 }
 
+#define SKR_STR2(x) #x
+#define SKR_STR(x) SKR_STR2(x)
+const char *skr_build_info(void)
+{
+	// what this binary was compiled as (bench.py records it beside its numbers)
+	return "libskr abi " SKR_STR(SKR_ABI_VERSION) "; nvcc " SKR_STR(__CUDACC_VER_MAJOR__) "." SKR_STR(__CUDACC_VER_MINOR__) "." SKR_STR(__CUDACC_VER_BUILD__)
+#ifdef __CUDA_ARCH_LIST__
+		   "; arch list " SKR_STR(__CUDA_ARCH_LIST__)
+#endif
+		   "; block " SKR_STR(SKR_BLOCK) " x " SKR_STR(SKR_MIN_BLOCKS) " CTAs/SM; gi batch " SKR_STR(SKR_GI_BATCH) "; defer steps " SKR_STR(SKR_DEFER_STEPS)
+		   "; built " __DATE__ " " __TIME__;
+}
+
 const char *skr_last_error(const skr_ctx *ctx)
 {
 	return ctx ? ctx->err.c_str() : g_init_error.c_str();
@@ -1271,7 +1278,7 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 		return fail(ctx, SKR_ERR_ARG, "skr_scene_upload: null array with nonzero count");
 	}
 	ctx->have_scene = false;
-	CK(cudaMemsetAsync(ctx->d_cursor, 0, 8 * sizeof(unsigned), ctx->stream)); // (a frame that died mid-kernel may have left the counter pairs armed)
+	CK(cudaMemsetAsync(ctx->d_cursor, 0, 8 * sizeof(unsigned), ctx->stream)); // (a frame that died mid-kernel may have left the counters armed)
 	const int S = sc->nspheres, T = sc->ntris, L = sc->nplights, D = sc->ndlights, F = sc->nfogs;
 	const int S4 = (S + 3) / 4 * 4;
 	SceneView &sv = ctx->sv;
@@ -1622,7 +1629,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 			}
 			pl.fp.band_count = ctx->d_band;
 			pl.fp.band_flag	 = ctx->d_band + MAX_BANDS;
-			pl.fp.band_ctas	 = (unsigned) rpb * (unsigned) fp.tiles_x * (unsigned) (tpix / 32) / (unsigned) fp.fetch; // batches per band
+			pl.fp.band_ctas	 = (unsigned) rpb * (unsigned) fp.tiles_x * (unsigned) (tpix / 32); // blocks per band
 			pl.fp.band_seq	 = ++ctx->band_seq;
 		}
 	}
@@ -1631,7 +1638,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 	{
 		// the per-band CTA counters run on from frame to frame; reset when the band geometry changes (and now and then,
 		// far from 32-bit wrap-around) or after a frame that did not complete
-		const unsigned long long geom = ((unsigned long long) pl.fp.band_ctas << 32) | (unsigned) (pl.npix_local / 32 / pl.fp.fetch);
+		const unsigned long long geom = ((unsigned long long) pl.fp.band_ctas << 32) | (unsigned) (pl.npix_local / 32);
 		if(geom != ctx->band_geom || (pl.fp.band_seq & 0xffffu) == 0u)
 		{
 			CK(cudaMemsetAsync(ctx->d_band, 0, sizeof(unsigned) * MAX_BANDS, ctx->stream));

@@ -12,7 +12,7 @@
 // interleaved Left/Right so that the slab arithmetic of the two boxes runs as packed FP32x2 (FADD2/FMUL2):
 //   n0 = (Lmin.x, Rmin.x, Lmin.y, Rmin.y)  n1 = (Lmin.z, Rmin.z, Lmax.x, Rmax.x)
 //   n2 = (Lmax.y, Rmax.y, Lmax.z, Rmax.z)  n3 = (bits(left), bits(right), -, -)
-// child index >= 0: internal node; < 0: leaf ~idx, whose triangle is tri_v[3*idx .. 3*idx+2] (leaf order).
+// child index >= 0: internal node; < 0: leaf ~idx, whose triangle is tri_v[4*idx .. 4*idx+2] (leaf order, 64 B each).
 #pragma once
 
 #define SKR_BVH_STACK 96
@@ -43,9 +43,9 @@ SKR_DEV void line_hits_boxes(float3 o, float3 inv, float tmax, const float4 &n0,
 template <bool STATS>
 SKR_DEV bool tri_leaf_hit(const SceneView &sv, int leaf, float3 o, float3 d, float tmax, Counters &cnt)
 {
-	const float4 a = __ldg(sv.tri_v + 3 * leaf + 0);
-	const float4 b = __ldg(sv.tri_v + 3 * leaf + 1);
-	const float4 c = __ldg(sv.tri_v + 3 * leaf + 2);
+	float4 a, b;
+	ldg256(sv.tri_v + 4 * leaf, a, b); // 64 B per triangle (v0, v1, v2, -): one 256-bit + one 128-bit load
+	const float4 c = __ldg(sv.tri_v + 4 * leaf + 2);
 	if(STATS)
 	{
 		cnt.tt++;
@@ -80,7 +80,7 @@ struct TriWalk
 {
 	float3 o, d, inv;
 	float tmax;
-	int node, sp;
+	int node, sp, base; // stack entries [base, sp) are pending (base > 0 once entries have been given away, tri_deferred_kernel)
 };
 SKR_DEV void tri_walk_begin(TriWalk &w, float3 o, float3 d, float tmax)
 {
@@ -90,15 +90,15 @@ SKR_DEV void tri_walk_begin(TriWalk &w, float3 o, float3 d, float tmax)
 	w.tmax = tmax;
 	w.node = 0;
 	w.sp   = 0;
+	w.base = 0;
 }
 // one node visit.  Returns 1: a triangle was hit (query over), 0: no node left (query over, no hit), -1: keep going.
 template <bool STATS>
 SKR_DEV int tri_walk_step(const SceneView &sv, TriWalk &w, int *stack, Counters &cnt)
 {
-	const float4 n0 = __ldg(sv.bvh + 4 * w.node + 0);
-	const float4 n1 = __ldg(sv.bvh + 4 * w.node + 1);
-	const float4 n2 = __ldg(sv.bvh + 4 * w.node + 2);
-	const float4 n3 = __ldg(sv.bvh + 4 * w.node + 3);
+	float4 n0, n1, n2, n3;
+	ldg256(sv.bvh + 4 * w.node, n0, n1); // the 64 B node in two 256-bit loads
+	ldg256(sv.bvh + 4 * w.node + 2, n2, n3);
 	if(STATS)
 	{
 		cnt.nv++;
@@ -145,7 +145,7 @@ SKR_DEV int tri_walk_step(const SceneView &sv, TriWalk &w, int *stack, Counters 
 	}
 	if(next < 0)
 	{
-		if(w.sp == 0)
+		if(w.sp == w.base)
 		{
 			return 0;
 		}

@@ -12,7 +12,8 @@
 //                            finds its key range and split from common-prefix lengths (ties broken by index).
 //   5. refit_kernel        : bottom-up; the second thread to reach a node (atomic counter) merges the child boxes
 //                            and writes the 64-byte node with both child boxes in it.
-//   6. gather_kernel       : triangles re-laid in leaf order as 3 x float4 (128-bit loads in the leaf test).
+//   6. gather_kernel       : triangles re-laid in leaf order, 64 B each (v0 | original index, v1, v2, pad): one 256-bit and one
+//                            128-bit load in the leaf test.
 #pragma once
 #include "skr_math.cuh"
 
@@ -446,9 +447,10 @@ __global__ void gather_tris_kernel(const float *__restrict__ tris, const unsigne
 		return;
 	}
 	const float *t	 = tris + 9 * (size_t) sorted_ids[i];
-	tri_v[3 * i + 0] = make_float4(t[0], t[1], t[2], __int_as_float((int) sorted_ids[i])); // w: original triangle index
-	tri_v[3 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
-	tri_v[3 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
+	tri_v[4 * i + 0] = make_float4(t[0], t[1], t[2], __int_as_float((int) sorted_ids[i])); // w: original triangle index
+	tri_v[4 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
+	tri_v[4 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
+	tri_v[4 * i + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); // (64 B per triangle: 32-byte aligned for 256-bit loads)
 }
 
 __global__ void iota_tris_kernel(const float *__restrict__ tris, int n, float4 *__restrict__ tri_v)
@@ -459,9 +461,10 @@ __global__ void iota_tris_kernel(const float *__restrict__ tris, int n, float4 *
 		return;
 	}
 	const float *t	 = tris + 9 * (size_t) i;
-	tri_v[3 * i + 0] = make_float4(t[0], t[1], t[2], __int_as_float(i));
-	tri_v[3 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
-	tri_v[3 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
+	tri_v[4 * i + 0] = make_float4(t[0], t[1], t[2], __int_as_float(i));
+	tri_v[4 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
+	tri_v[4 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
+	tri_v[4 * i + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 } // namespace bvhb

@@ -41,7 +41,7 @@ struct SceneView
 	int blob_f4;		 // blob size in float4
 	int blob_in_smem;	 // 1: kernels stage the blob in shared memory
 	const float4 *blob;	 // device
-	const float4 *tri_v; // 3 float4 per triangle (v0, v1, v2), LBVH leaf order
+	const float4 *tri_v; // 4 float4 = 64 B per triangle (v0 | original index, v1, v2, pad), LBVH leaf order
 	const float4 *bvh;	 // 4 float4 per internal node (see skr_bvh.cuh)
 	const float4 *big_v; // 3 float4 per outsized triangle, tested before the hierarchy (skr_bvh_build.cuh: morton_kernel)
 	int nbig;

@@ -28,13 +28,6 @@
 #define SKR_MIN_BLOCKS 7
 #endif
 #define SKR_FIX_SCALE 4294967296.0f
-#ifndef SKR_PRIMARY_MODE
-// 0 (default): the grid of primary_kernel covers the frame, one 8 x 4 pixel block per warp.
-// 1: persistent -- one wave of CTAs whose warps fetch blocks from a device counter.  Measured on B200 (round 2): slower
-//    (config 4: 0.42 ms against 0.31 ms, config 1: 0.062 against 0.057): the 64 800 fetches of a 1080p frame serialise on
-//    ONE L2 address, and CTAs of one warp (below) give the same dynamic refill in hardware without an atomic.
-#define SKR_PRIMARY_MODE 0
-#endif
 #ifndef SKR_GI_BATCH
 // GI children traced together (even): they share the per-sphere origin terms AND one queue reservation.  Measured on
 // B200 (config 3 / config 5): 2: 6.94 / 180.1 ms, 4: 6.57 / 169.0 ms, 8: 7.51 / 190.1 ms (spills).
@@ -64,7 +57,6 @@ struct FrameParams
 	int cull;		  // 1: bundle culling (cull_pairs) for this frame: jittered, >= 4 samples per pixel, <= 64 spheres
 	float cull_delta; // bound on |d(r) - d(0.5)| over the jitter draw r of a pixel (ray directions are un-normalised)
 	int strip_words;  // 1: whole 8 x 4 blocks leave as 32-bit words (width % 4 == 0, 4-byte aligned frames)
-	int fetch;		  // blocks a warp of primary_kernel takes per fetch (1, or 4 when pixels are cheap)
 	uint2 key;
 	uint32_t node_base, slot_gi;
 	uint8_t *rgb8;	 // row-major frame or null
@@ -179,75 +171,6 @@ SKR_DEV void accum_add(long long *accum, long long lp, float3 c, long long ex = 
 	{
 		atomicOr(a + 3, (unsigned long long) fl);
 	}
-}
-// accum_add for a whole warp (all 32 lanes call; `valid` lanes hold a contribution for local pixel lp).  The entries a
-// warp of shade_expand_kernel holds are siblings and cousins: most of its lanes add to the SAME one or two pixels, and 96
-// reductions per warp would serialise on a handful of L2 addresses.  Lanes are therefore grouped into runs of equal
-// pixel; an exact integer prefix sum over the warp (5 shuffle steps per channel) gives every run's total as a difference
-// of two prefix values, and only the last lane of each run touches memory.  Integer arithmetic: the frame stays
-// bit-identical to per-lane atomics.  (SKR_ACC_SEGMENTED=0 compiles the per-lane form.)
-#ifndef SKR_ACC_SEGMENTED
-#define SKR_ACC_SEGMENTED 1
-#endif
-SKR_DEV void accum_add_warp(long long *accum, long long lp, float3 c, bool valid, long long ex = 0, long long ey = 0, long long ez = 0, unsigned efl = 0)
-{
-#if SKR_ACC_SEGMENTED
-	const unsigned lane = threadIdx.x & 31u;
-	unsigned fl			= valid ? efl : 0u;
-	long long x = 0, y = 0, z = 0;
-	if(valid)
-	{
-		x = to_fixed(c.x, fl, 0) + ex, y = to_fixed(c.y, fl, 1) + ey, z = to_fixed(c.z, fl, 2) + ez;
-	}
-	const long long key	 = valid ? lp : -1 - (long long) lane; // invalid lanes: runs of their own, never written
-	const long long prev = __shfl_up_sync(0xffffffffu, key, 1), next = __shfl_down_sync(0xffffffffu, key, 1);
-	const bool head		 = lane == 0 || prev != key;
-	const bool tail		 = lane == 31 || next != key;
-	const unsigned heads = __ballot_sync(0xffffffffu, head);
-	if(__any_sync(0xffffffffu, fl != 0u) || __popc(heads) > 20) // non-finite terms (rare), or nothing to merge: lane by lane
-	{
-		if(valid)
-		{
-			unsigned long long *a = reinterpret_cast<unsigned long long *>(accum + SKR_ACC_STRIDE * lp);
-			atomicAdd(a + 0, (unsigned long long) x);
-			atomicAdd(a + 1, (unsigned long long) y);
-			atomicAdd(a + 2, (unsigned long long) z);
-			if(fl)
-			{
-				atomicOr(a + 3, (unsigned long long) fl);
-			}
-		}
-		return;
-	}
-#pragma unroll
-	for(int off = 1; off < 32; off <<= 1)
-	{
-		const long long tx = __shfl_up_sync(0xffffffffu, x, off), ty = __shfl_up_sync(0xffffffffu, y, off), tz = __shfl_up_sync(0xffffffffu, z, off);
-		if((int) lane >= off)
-		{
-			x += tx, y += ty, z += tz;
-		}
-	}
-	const int start = 31 - __clz((int) (heads & (0xffffffffu >> (31u - lane)))); // head of this lane's run
-	const int from	= start > 0 ? start - 1 : 0;
-	long long bx = __shfl_sync(0xffffffffu, x, from), by = __shfl_sync(0xffffffffu, y, from), bz = __shfl_sync(0xffffffffu, z, from);
-	if(start == 0)
-	{
-		bx = by = bz = 0;
-	}
-	if(tail && valid)
-	{
-		unsigned long long *a = reinterpret_cast<unsigned long long *>(accum + SKR_ACC_STRIDE * lp);
-		atomicAdd(a + 0, (unsigned long long) (x - bx));
-		atomicAdd(a + 1, (unsigned long long) (y - by));
-		atomicAdd(a + 2, (unsigned long long) (z - bz));
-	}
-#else
-	if(valid)
-	{
-		accum_add(accum, lp, c, ex, ey, ez, efl);
-	}
-#endif
 }
 SKR_DEV float3 accum_load(const long long *accum, long long lp)
 {
@@ -484,12 +407,12 @@ SKR_DEV float3 queue_hit_point(const float4 *__restrict__ B, const SceneView &sv
 // Sphere-only, fog-free scenes thus run a kernel without the traversal stack or the fog branch in its register budget.
 //
 // Launch shape: one 8 x 4 pixel block per WARP, four warps per CTA (the scene blob is staged per CTA).
-// (SKR_PRIMARY_MODE 1 = persistent CTAs fetching blocks from a device counter: measured slower, see above.)
+// (Persistent CTAs whose warps fetch blocks from a device counter were measured and dropped: config 4 0.42 ms against 0.31,
+// config 1 0.062 against 0.057 -- the 64 800 fetches of a 1080p frame serialise on one L2 address.  DESIGN.md.)
 // Finished pixels bound for another device or for page-locked host memory (skr_render_peers_device) are quantised into
 // shared memory and leave as 32-bit words, 24 B per pixel row of the block, instead of 3 byte stores each.
 template <bool GI, bool STATS, bool SMEM, bool TRIS, bool FOG>
-__global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix,
-																	 unsigned *cursor)
+__global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix)
 {
 	extern __shared__ float4 smem[];
 	__shared__ uint32_t s_px[SKR_BLOCK / 32][24]; // per warp: one block of RGB8, 4 rows x 24 B
@@ -498,29 +421,9 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 	zero(cnt);
 	const unsigned lane	   = threadIdx.x & 31u;
 	const unsigned nblocks = (unsigned) ((npix + 31) / 32);
-#if SKR_PRIMARY_MODE == 1
-	const unsigned fetch = (unsigned) fp.fetch;
-	unsigned nxt = 0;
-	if(lane == 0)
-	{
-		nxt = atomicAdd(cursor, fetch);
-	}
-	unsigned batch = __shfl_sync(0xffffffffu, nxt, 0);
-	while(batch < nblocks)
-	{
-	if(lane == 0)
-	{
-		nxt = atomicAdd(cursor, fetch); // the next batch's index is on its way while this one is traced
-	}
-#else
-	// static: the grid covers the frame, warp w of CTA b takes block b * (warps per CTA) + w
-	const unsigned fetch = 1u;
-	const unsigned batch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if(batch < nblocks)
-	{
-#endif
-	const unsigned batch_end = batch + fetch < nblocks ? batch + fetch : nblocks;
-	for(unsigned blk = batch; blk < batch_end; blk++)
+	// the grid covers the frame: warp w of CTA b takes the 8 x 4 pixel block b * (warps per CTA) + w
+	const unsigned blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if(blk < nblocks)
 	{
 	const long long g  = (long long) blk * 32 + lane;
 	const long long lp = lp0 + g;
@@ -647,17 +550,15 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		}
 		write_block(fp, lp, p, sum, s_px[threadIdx.x >> 5]);
 	}
-	} // blocks of the batch
 	if(!GI && fp.band_flag)
 	{
-		// overlapped copy-out (skr_render): batches are counted per band of whole tile rows; the last one publishes the flag
+		// overlapped copy-out (skr_render): blocks are counted per band of whole tile rows; the last one publishes the flag
 		__syncwarp();
 		if(lane == 0)
 		{
 			__threadfence_system();
-			const unsigned nb	= (nblocks + fetch - 1) / fetch; // batches of the launch
-			const unsigned b	= (batch / fetch) / fp.band_ctas;
-			const unsigned left = nb - b * fp.band_ctas;
+			const unsigned b	= blk / fp.band_ctas;
+			const unsigned left = nblocks - b * fp.band_ctas;
 			const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
 			if((atomicAdd(fp.band_count + b, 1u) + 1u) % want == 0u) // counters run on from frame to frame (same geometry)
 			{
@@ -666,24 +567,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			}
 		}
 	}
-#if SKR_PRIMARY_MODE == 1
-	batch = __shfl_sync(0xffffffffu, nxt, 0);
-	} // batches
-	__syncthreads();
-	if(threadIdx.x == 0)
-	{
-		// the last CTA to leave re-arms the counter pair for the next launch (every warp's final fetch is behind it)
-		__threadfence();
-		if(atomicAdd(cursor + 1, 1u) == gridDim.x - 1u)
-		{
-			cursor[0] = 0u;
-			cursor[1] = 0u;
-			__threadfence();
-		}
 	}
-#else
-	}
-#endif
 	flush_counters<STATS>(fp, cnt);
 }
 
@@ -703,7 +587,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 //                                               meta = sphere | parent lane << 16 | child index << 21
 //                   32 x 4 x u64                per parent lane: fixed-point sum r, g, b + flags
 #define SKR_LEAF_SLOTS (32 + 32 * SKR_GI_BATCH)
-#define SKR_LEAF_WARP_BYTES (SKR_LEAF_SLOTS * 32 + 32 * 4 * 8 + 32 * 4 * 4)
+#define SKR_LEAF_WARP_BYTES (SKR_LEAF_SLOTS * 32 + 32 * 4 * 8)
 #define SKR_LEAF_CTA_BYTES ((SKR_BLOCK / 32) * SKR_LEAF_WARP_BYTES)
 #define SKR_LEAF_MAX_CHILDREN 2047
 
@@ -711,24 +595,15 @@ struct LeafStage
 {
 	float4 *slot;			 // this warp's ring
 	unsigned long long *acc; // this warp's 32 x 4 parent accumulators
-	unsigned *acc2;			 // 32 x 4 u32 more (SKR_LEAF_ACC == 3)
 	unsigned pending;		 // warp-uniform
 };
 
-// Fold one round's fixed-point terms into the parents' accumulators in shared memory (every lane calls; `act` lanes hold
-// a term for parent lane `src`).  SKR_LEAF_ACC picks the mechanism (measured on B200):
-//   1  64-bit shared-memory atomics (compile to ATOMS.CAST.SPIN loops; a parent's leaves collide on one address)
-//   2  MATCH.ANY on the parent lane + REDUX.SUM over each group on 16/16/32-bit limbs, group leader adds
-//   3  native 32-bit shared-memory atomics on 16/16/32-bit limbs (accumulator = 3 x u32 per channel, carries folded at the end)
-//   4  runs of equal parent (the ring is filled parent by parent) summed by an integer prefix scan over the warp; one
-//      64-bit atomic triple per run
-//   0  nothing (timing experiments only: the image is wrong)
-#ifndef SKR_LEAF_ACC
-#define SKR_LEAF_ACC 4
-#endif
-SKR_DEV void leaf_accumulate(const LeafStage &ls, bool act, unsigned lane, int src, long long fx, long long fy, long long fz, unsigned fl)
+// Fold one round's fixed-point terms into the parents' accumulators in shared memory: 64-bit shared-memory atomics
+// (ATOMS.CAST.SPIN loops).  Measured alternatives, all slower on B200 and kept out of the tree: MATCH.ANY +
+// REDUX.SUM per parent group (config 5: 215 ms against 145), native 32-bit atomics on 16/16/32-bit limbs (144.4 against
+// 144.7: no gain), parent-major staging + integer prefix scan with one atomic triple per run (150 against 146).
+SKR_DEV void leaf_accumulate(const LeafStage &ls, bool act, int src, long long fx, long long fy, long long fz, unsigned fl)
 {
-#if SKR_LEAF_ACC == 1
 	if(act)
 	{
 		unsigned long long *a = ls.acc + 4 * src;
@@ -740,124 +615,16 @@ SKR_DEV void leaf_accumulate(const LeafStage &ls, bool act, unsigned lane, int s
 			atomicOr(a + 3, (unsigned long long) fl);
 		}
 	}
-#elif SKR_LEAF_ACC == 2
-	const unsigned peers = __match_any_sync(0xffffffffu, act ? (unsigned) src : 64u + lane);
-	const auto group_sum = [&](long long v) -> long long {
-		const unsigned a = __reduce_add_sync(peers, (unsigned) ((unsigned long long) v & 0xffffull));
-		const unsigned b = __reduce_add_sync(peers, (unsigned) (((unsigned long long) v >> 16) & 0xffffull));
-		const int c		 = __reduce_add_sync(peers, (int) (v >> 32));
-		return (long long) (((unsigned long long) (long long) c << 32) + ((unsigned long long) b << 16) + (unsigned long long) a);
-	};
-	const long long sx = group_sum(fx), sy = group_sum(fy), sz = group_sum(fz);
-	const unsigned sfl = __reduce_or_sync(peers, fl);
-	if(act && lane == (unsigned) (__ffs(peers) - 1))
-	{
-		ulonglong2 *a = reinterpret_cast<ulonglong2 *>(ls.acc + 4 * src);
-		ulonglong2 p = a[0], q = a[1];
-		p.x += (unsigned long long) sx;
-		p.y += (unsigned long long) sy;
-		q.x += (unsigned long long) sz;
-		q.y |= (unsigned long long) sfl;
-		a[0] = p;
-		a[1] = q;
-	}
-	__syncwarp();
-#elif SKR_LEAF_ACC == 4
-	// The ring is filled parent by parent (see the staging code), so a parent's leaves sit in consecutive lanes: runs of
-	// equal `src`.  An exact integer prefix sum over the warp gives each run's total as a difference of two prefix values;
-	// only the last lane of a run adds it (atomically: a parent's leaves of two different batches can share a round).
-	const int key		 = act ? src : -1 - (int) lane;
-	const int prev		 = __shfl_up_sync(0xffffffffu, key, 1), next = __shfl_down_sync(0xffffffffu, key, 1);
-	const bool head		 = lane == 0 || prev != key;
-	const bool tail		 = lane == 31 || next != key;
-	const unsigned heads = __ballot_sync(0xffffffffu, head);
-	long long x = fx, y = fy, z = fz;
-#pragma unroll
-	for(int off = 1; off < 32; off <<= 1)
-	{
-		const long long tx = __shfl_up_sync(0xffffffffu, x, off), ty = __shfl_up_sync(0xffffffffu, y, off), tz = __shfl_up_sync(0xffffffffu, z, off);
-		if((int) lane >= off)
-		{
-			x += tx, y += ty, z += tz;
-		}
-	}
-	const int start = 31 - __clz((int) (heads & (0xffffffffu >> (31u - lane))));
-	const int from	= start > 0 ? start - 1 : 0;
-	long long bx = __shfl_sync(0xffffffffu, x, from), by = __shfl_sync(0xffffffffu, y, from), bz = __shfl_sync(0xffffffffu, z, from);
-	if(start == 0)
-	{
-		bx = by = bz = 0;
-	}
-	if(act)
-	{
-		unsigned long long *a = ls.acc + 4 * src;
-		if(tail)
-		{
-			atomicAdd(a + 0, (unsigned long long) (x - bx));
-			atomicAdd(a + 1, (unsigned long long) (y - by));
-			atomicAdd(a + 2, (unsigned long long) (z - bz));
-		}
-		if(fl)
-		{
-			atomicOr(a + 3, (unsigned long long) fl);
-		}
-	}
-#elif SKR_LEAF_ACC == 3
-	// acc viewed as 8 x u32 per parent: [x.a+b<<16 .. ] is NOT used; layout: u32[0..2] = x limbs (a, b, c), [3..5] = y, and the
-	// z limbs + flags live in the second half of the ring-side table (ls.acc2)
-	if(act)
-	{
-		unsigned *u = reinterpret_cast<unsigned *>(ls.acc) + 8 * src; // 32 B per parent: x.a x.b x.c y.a y.b y.c fl -
-		unsigned *w = ls.acc2 + 4 * src;							   // z.a z.b z.c -
-		atomicAdd(u + 0, (unsigned) ((unsigned long long) fx & 0xffffull));
-		atomicAdd(u + 1, (unsigned) (((unsigned long long) fx >> 16) & 0xffffull));
-		atomicAdd(u + 2, (unsigned) (int) (fx >> 32));
-		atomicAdd(u + 3, (unsigned) ((unsigned long long) fy & 0xffffull));
-		atomicAdd(u + 4, (unsigned) (((unsigned long long) fy >> 16) & 0xffffull));
-		atomicAdd(u + 5, (unsigned) (int) (fy >> 32));
-		atomicAdd(w + 0, (unsigned) ((unsigned long long) fz & 0xffffull));
-		atomicAdd(w + 1, (unsigned) (((unsigned long long) fz >> 16) & 0xffffull));
-		atomicAdd(w + 2, (unsigned) (int) (fz >> 32));
-		if(fl)
-		{
-			atomicOr(u + 6, fl);
-		}
-	}
-#endif
 }
 // the parent lane's total, as three fixed-point terms + flags
 SKR_DEV void leaf_total(const LeafStage &ls, unsigned lane, long long &x, long long &y, long long &z, unsigned &fl)
 {
-#if SKR_LEAF_ACC == 3
-	const unsigned *u = reinterpret_cast<const unsigned *>(ls.acc) + 8 * lane;
-	const unsigned *w = ls.acc2 + 4 * lane;
-	const auto join	  = [](unsigned a, unsigned b, unsigned c) {
-		  return (long long) (((unsigned long long) (long long) (int) c << 32) + ((unsigned long long) b << 16) + (unsigned long long) a);
-	};
-	x  = join(u[0], u[1], u[2]);
-	y  = join(u[3], u[4], u[5]);
-	z  = join(w[0], w[1], w[2]);
-	fl = u[6];
-#else
 	const unsigned long long *a = ls.acc + 4 * lane;
 	x = (long long) a[0], y = (long long) a[1], z = (long long) a[2], fl = (unsigned) a[3];
-#endif
 }
 
-// shade `count` (<= 32) staged leaf hits starting at slot `first`; every lane of the warp calls this
-#ifndef SKR_LEAF_NOINLINE
-#define SKR_LEAF_NOINLINE 0
-#endif
-#ifndef SKR_LEAF_MIN_BLOCKS
-#define SKR_LEAF_MIN_BLOCKS SKR_MIN_BLOCKS
-#endif
 template <bool STATS, bool FOG>
-#if SKR_LEAF_NOINLINE
-__device__ __noinline__ void leaf_shade_round(
-#else
-SKR_DEV void leaf_shade_round(
-#endif
-const float4 *__restrict__ B, const SceneView &sv, const FrameParams &fp, const LeafStage &ls, unsigned first, unsigned count,
+SKR_DEV void leaf_shade_round(const float4 *__restrict__ B, const SceneView &sv, const FrameParams &fp, const LeafStage &ls, unsigned first, unsigned count,
 							  float3 o, const RngCtx &rng, Counters &cnt)
 {
 	const unsigned lane = threadIdx.x & 31u;
@@ -890,7 +657,7 @@ const float4 *__restrict__ B, const SceneView &sv, const FrameParams &fp, const 
 		fl = 0;
 		fx = to_fixed(contrib.x, fl, 0), fy = to_fixed(contrib.y, fl, 1), fz = to_fixed(contrib.z, fl, 2);
 	}
-	leaf_accumulate(ls, act, lane, src, fx, fy, fz, fl);
+	leaf_accumulate(ls, act, src, fx, fy, fz, fl);
 }
 
 // shade whole rounds of 32 while that many are pending; keep the rest at the front of the ring
@@ -940,7 +707,7 @@ SKR_DEV void leaf_drain(const float4 *__restrict__ B, const SceneView &sv, const
 // ------------------------------------------------------------------------------------------------
 // LEAF: the children are leaves of the tree (depth 1) and are shaded in place, see above; `out` is unused.
 template <bool STATS, bool SMEM, bool TRIS, bool FOG, bool LEAF>
-__global__ void __launch_bounds__(SKR_BLOCK, LEAF ? SKR_LEAF_MIN_BLOCKS : SKR_MIN_BLOCKS) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
+__global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel(const SceneView sv, const FrameParams fp, const Queue in, unsigned start, unsigned count,
 																  const Queue out, int expand)
 {
 	extern __shared__ float4 smem[];
@@ -953,12 +720,10 @@ __global__ void __launch_bounds__(SKR_BLOCK, LEAF ? SKR_LEAF_MIN_BLOCKS : SKR_MI
 		char *base = reinterpret_cast<char *>(smem) + (SMEM ? (size_t) sv.blob_f4 * sizeof(float4) : 0) + (threadIdx.x >> 5) * SKR_LEAF_WARP_BYTES;
 		ls.slot	   = reinterpret_cast<float4 *>(base);
 		ls.acc	   = reinterpret_cast<unsigned long long *>(base + SKR_LEAF_SLOTS * 32);
-		ls.acc2	   = reinterpret_cast<unsigned *>(base + SKR_LEAF_SLOTS * 32 + 32 * 4 * 8);
 		ls.pending = 0;
 		const unsigned lane = threadIdx.x & 31u;
 		reinterpret_cast<ulonglong2 *>(ls.acc + 4 * lane)[0] = make_ulonglong2(0ull, 0ull);
 		reinterpret_cast<ulonglong2 *>(ls.acc + 4 * lane)[1] = make_ulonglong2(0ull, 0ull);
-		reinterpret_cast<uint4 *>(ls.acc2 + 4 * lane)[0]	 = make_uint4(0u, 0u, 0u, 0u);
 		__syncwarp();
 	}
 
@@ -1043,26 +808,19 @@ __global__ void __launch_bounds__(SKR_BLOCK, LEAF ? SKR_LEAF_MIN_BLOCKS : SKR_MI
 			}
 			if constexpr(LEAF)
 			{
-				// parent by parent: lane L's hits of this batch take consecutive slots (leaf_accumulate sums runs of one parent)
-				const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-				unsigned idx	  = ls.pending;
-#pragma unroll
-				for(int k = 0; k < SKR_GI_BATCH; k++)
-				{
-					idx += (unsigned) __popc(m[k] & lt);
-				}
+				unsigned at = ls.pending;
 #pragma unroll
 				for(int k = 0; k < SKR_GI_BATCH; k++)
 				{
 					if(h[k] >= 0)
 					{
+						const unsigned idx	 = at + __popc(m[k] & ((1u << (threadIdx.x & 31)) - 1u));
 						ls.slot[2 * idx]	 = make_float4(d[k].x, d[k].y, d[k].z, t[k]);
 						ls.slot[2 * idx + 1] = make_float4(w[k].x, w[k].y, w[k].z, u2f((uint32_t) h[k] | ((threadIdx.x & 31u) << 16) | ((uint32_t) (c + k) << 21)));
-						idx++;
 					}
+					at += (unsigned) __popc(m[k]);
 				}
-				const unsigned at = ls.pending + total;
-				ls.pending		  = at;
+				ls.pending = at;
 				if(at >= 32u)
 				{
 					leaf_drain<STATS, FOG>(B, sv, fp, ls, o, rng, cnt, false);
@@ -1125,23 +883,20 @@ __global__ void __launch_bounds__(SKR_BLOCK, LEAF ? SKR_LEAF_MIN_BLOCKS : SKR_MI
 			leaf_drain<STATS, FOG>(B, sv, fp, ls, o, rng, cnt, true);
 		}
 	}
+	if(valid)
 	{
-		long long lp = 0;
-		if(valid)
-		{
-			const int x = (int) (rng.pixel % (uint32_t) fp.width), y = (int) (rng.pixel / (uint32_t) fp.width);
-			lp			= encode_pixel(fp, x, y);
-		}
+		const int x = (int) (rng.pixel % (uint32_t) fp.width), y = (int) (rng.pixel / (uint32_t) fp.width);
+		const long long lp = encode_pixel(fp, x, y);
 		if constexpr(LEAF)
 		{
 			long long ex, ey, ez;
 			unsigned efl;
 			leaf_total(ls, threadIdx.x & 31u, ex, ey, ez, efl);
-			accum_add_warp(fp.accum, lp, contrib, valid, ex, ey, ez, efl);
+			accum_add(fp.accum, lp, contrib, ex, ey, ez, efl);
 		}
 		else
 		{
-			accum_add_warp(fp.accum, lp, contrib, valid);
+			accum_add(fp.accum, lp, contrib);
 		}
 	}
 	flush_counters<STATS>(fp, cnt);
@@ -1259,7 +1014,8 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 // (round 1: 18.7 of 32 lanes, 22 % of the warp slots, 0.29 ms).  Here they are ONE dense work list and the kernel is
 // persistent: a wave of CTAs; each lane walks one line, one node per loop iteration, and lanes whose query is over are
 // REFILLED with the next rays of the list (one atomic fetch per warp, as soon as 8 lanes are idle) instead of waiting for
-// the slowest lane.  A hit blackens the pixel primary_kernel wrote
+// the slowest lane; once the list is used up, busy lanes hand the oldest entry of their stack to idle lanes (see WORK
+// SPLITTING below).  A hit blackens the pixel primary_kernel wrote
 // (any accepted triangle shades black, src/raytrace.h:221-224); no hit leaves it.  Same arithmetic, same answer as the
 // in-place query (SKR_NO_DEFER=1; tested bit for bit).
 // ------------------------------------------------------------------------------------------------
@@ -1299,7 +1055,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 	TriWalk wk;
 	wk.o = wk.d = wk.inv = f3(0.0f, 0.0f, 0.0f);
 	wk.tmax = 0.0f;
-	wk.node = wk.sp = 0;
+	wk.node = wk.sp = wk.base = 0;
 	int stack[SKR_BVH_STACK];
 	for(;;)
 	{
@@ -1329,6 +1085,43 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 		else if(idle == 0xffffffffu)
 		{
 			break;
+		}
+		else if(idle != 0u && !more)
+		{
+			// WORK SPLITTING.  The list is used up and some lanes are idle while others are deep inside the mesh (a line that
+			// threads the model without an accepted hit walks thousands of nodes: the frame used to wait for ONE such lane).
+			// A busy lane gives the OLDEST entry of its stack -- the biggest pending subtree -- to an idle lane, which walks it
+			// for the same ray; the answers combine by OR (any accepted triangle blackens the pixel).
+			const unsigned donors = __ballot_sync(0xffffffffu, active && wk.sp > wk.base);
+			if(donors != 0u)
+			{
+				const unsigned lt = (1u << lane) - 1u;
+				const int n		  = min(__popc(idle), __popc(donors));
+				const int ri = __popc(idle & lt), rd = __popc(donors & lt);
+				const bool thief = !active && ri < n;
+				const int src	 = thief ? (int) __fns(donors, 0u, ri + 1) : (int) lane;
+				int give		 = 0;
+				if(active && wk.sp > wk.base && rd < n)
+				{
+					give = stack[wk.base];
+					wk.base++;
+				}
+				const int node = __shfl_sync(0xffffffffu, give, src);
+				const float ox = __shfl_sync(0xffffffffu, wk.o.x, src), oy = __shfl_sync(0xffffffffu, wk.o.y, src), oz = __shfl_sync(0xffffffffu, wk.o.z, src);
+				const float dx = __shfl_sync(0xffffffffu, wk.d.x, src), dy = __shfl_sync(0xffffffffu, wk.d.y, src), dz = __shfl_sync(0xffffffffu, wk.d.z, src);
+				const float ix = __shfl_sync(0xffffffffu, wk.inv.x, src), iy = __shfl_sync(0xffffffffu, wk.inv.y, src), iz = __shfl_sync(0xffffffffu, wk.inv.z, src);
+				const float tm = __shfl_sync(0xffffffffu, wk.tmax, src);
+				const unsigned pxx = __shfl_sync(0xffffffffu, px.x, src), pxy = __shfl_sync(0xffffffffu, px.y, src);
+				if(thief)
+				{
+					wk.o = f3(ox, oy, oz), wk.d = f3(dx, dy, dz), wk.inv = f3(ix, iy, iz);
+					wk.tmax = tm;
+					wk.node = node;
+					wk.sp = wk.base = 0;
+					px	   = make_uint2(pxx, pxy);
+					active = true;
+				}
+			}
 		}
 		if(active)
 		{

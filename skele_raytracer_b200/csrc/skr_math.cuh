@@ -75,3 +75,13 @@ SKR_DEV float sqrt_approx(float x)
 
 SKR_DEV float u2f(uint32_t u) { return __uint_as_float(u); }
 SKR_DEV uint32_t f2u(float f) { return __float_as_uint(f); }
+
+// 256-bit read-only global load (sm_100: LDG.E.256): 32 B per lane in ONE instruction.  The BVH walk is a gather -- every
+// lane its own node -- and what it is bound by is the number of load INSTRUCTIONS x lanes (one L1 tag lookup per lane per
+// instruction, not bytes): a 64 B node costs two of these instead of four LDG.128.  p must be 32-byte aligned.
+SKR_DEV void ldg256(const float4 *p, float4 &a, float4 &b)
+{
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+		: "l"(p));
+}

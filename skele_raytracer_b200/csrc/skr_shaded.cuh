@@ -64,7 +64,7 @@ SKR_DEV int tri_ray_query(const SceneView &sv, float3 o, float3 d, float &tbest,
 {
 	int hit = -1;
 	const auto leaf = [&](const float4 *v) -> bool {
-		const float4 a = __ldg(v + 0), b = __ldg(v + 1), c = __ldg(v + 2);
+		const float4 a = __ldg(v + 0), b = __ldg(v + 1), c = __ldg(v + 2); // (big_v: 48 B records, tri_v2: 64 B records)
 		if(STATS)
 		{
 			cnt.tt++;
@@ -82,7 +82,7 @@ SKR_DEV int tri_ray_query(const SceneView &sv, float3 o, float3 d, float &tbest,
 	{
 		for(int i = 0; i < sv.T; i++)
 		{
-			if(leaf(sv.tri_v2 + 3 * i) && ANY)
+			if(leaf(sv.tri_v2 + 4 * i) && ANY)
 			{
 				return hit;
 			}
@@ -102,10 +102,9 @@ SKR_DEV int tri_ray_query(const SceneView &sv, float3 o, float3 d, float &tbest,
 	int node = 0;
 	for(;;)
 	{
-		const float4 n0 = __ldg(sv.bvh2 + 4 * node + 0);
-		const float4 n1 = __ldg(sv.bvh2 + 4 * node + 1);
-		const float4 n2 = __ldg(sv.bvh2 + 4 * node + 2);
-		const float4 n3 = __ldg(sv.bvh2 + 4 * node + 3);
+		float4 n0, n1, n2, n3;
+		ldg256(sv.bvh2 + 4 * node, n0, n1);
+		ldg256(sv.bvh2 + 4 * node + 2, n2, n3);
 		if(STATS)
 		{
 			cnt.nv++;
@@ -118,7 +117,7 @@ SKR_DEV int tri_ray_query(const SceneView &sv, float3 o, float3 d, float &tbest,
 		{
 			if(cl < 0)
 			{
-				if(leaf(sv.tri_v2 + 3 * (~cl)) && ANY)
+				if(leaf(sv.tri_v2 + 4 * (~cl)) && ANY)
 				{
 					return hit;
 				}
@@ -132,7 +131,7 @@ SKR_DEV int tri_ray_query(const SceneView &sv, float3 o, float3 d, float &tbest,
 		{
 			if(cr < 0)
 			{
-				if(leaf(sv.tri_v2 + 3 * (~cr)) && ANY)
+				if(leaf(sv.tri_v2 + 4 * (~cr)) && ANY)
 				{
 					return hit;
 				}

@@ -312,8 +312,8 @@ def test_deferred_triangle_query_equals_the_query_in_place(gpu, gscenes, scene, 
     finally:
         del os.environ["SKR_NO_DEFER"]
     assert np.array_equal(a32.view(np.uint32), b32.view(np.uint32)) and np.array_equal(a8, b8)
-    assert sa.kernel_launches == sb.kernel_launches + 1 and sa.tri_tests == sb.tri_tests and sa.closest_hit_rays == sb.closest_hit_rays
-    assert sa.bvh_node_visits == sb.bvh_node_visits
+    # (node / leaf-test counts differ: split walks visit the hierarchy in another order and do not stop at a sibling's hit)
+    assert sa.kernel_launches == sb.kernel_launches + 1 and sa.closest_hit_rays == sb.closest_hit_rays
 
 
 def test_bvh_dragon_1080p_equals_brute_force_window(gpu, port, scenes, gscenes):
