@@ -499,6 +499,14 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		{
 			cand_push(fp, cand, lp, p, d, t); // settled by tri_deferred_kernel: the pixel is written below as if no triangle were hit
 		}
+#ifdef SKR_DEBUG_NV
+		if(STATS && !GI) // debugging aid (never in a shipped build): the frame shows node visits / leaf tests of each pixel's query
+		{
+			sum = f3((float) cnt.nv, (float) cnt.tt, 0.0f);
+			cnt.nv = cnt.tt = 0;
+			h = -3;
+		}
+#endif
 		if(h == -2)
 		{
 			sum += sv.background;
@@ -1012,12 +1020,12 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 // In a frame like dragon.scn's most camera rays are settled by two outsized triangles or within a few nodes (primary_kernel
 // walks up to SKR_DEFER_STEPS in place); the rest walk 20-40 nodes each.  Traced in place they leave most lanes and most warp slots idle
 // (round 1: 18.7 of 32 lanes, 22 % of the warp slots, 0.29 ms).  Here they are ONE dense work list and the kernel is
-// persistent: a wave of CTAs; each lane walks one line, one node per loop iteration, and lanes whose query is over are
-// REFILLED with the next rays of the list (one atomic fetch per warp, as soon as 8 lanes are idle) instead of waiting for
-// the slowest lane; once the list is used up, busy lanes hand the oldest entry of their stack to idle lanes (see WORK
-// SPLITTING below).  A hit blackens the pixel primary_kernel wrote
+// persistent: a wave of CTAs; each lane walks one line, one node per loop iteration.  Lanes whose query is over are
+// REFILLED from the list, 8 rays per fetch, and idle lanes beyond that take over part of a busy lane's walk (WORK
+// SPLITTING below): a warp never waits for its slowest ray, and the heavy rays -- neighbours in the image and in the list
+// -- end up spread over every warp of the grid.  A hit blackens the pixel primary_kernel wrote
 // (any accepted triangle shades black, src/raytrace.h:221-224); no hit leaves it.  Same arithmetic, same answer as the
-// in-place query (SKR_NO_DEFER=1; tested bit for bit).
+// in-place query (tested bit for bit).  OFF by default (SKR_DEFER=1): measured slower on config 4, see skr_api.cu make_plan.
 // ------------------------------------------------------------------------------------------------
 #define SKR_DEFER_REFILL 8
 SKR_DEV void write_black(const FrameParams &fp, uint2 px) // the pixel of a candidate whose line hit a triangle
@@ -1059,39 +1067,43 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 	int stack[SKR_BVH_STACK];
 	for(;;)
 	{
-		const unsigned idle = __ballot_sync(0xffffffffu, !active);
-		if(more && (idle == 0xffffffffu || __popc(idle) >= SKR_DEFER_REFILL))
+		unsigned idle = __ballot_sync(0xffffffffu, !active);
+		if(more && __popc(idle) >= SKR_DEFER_REFILL)
 		{
-			// refill: the idle lanes take the next rays of the list (one fetch per warp)
+			// REFILL: SKR_DEFER_REFILL idle lanes take the next rays of the list (one fetch per warp).  Never more at a time: the
+			// heavy rays of a frame sit next to each other in the list, and small bites spread them over all warps of the grid
+			// while the rest of a warp's lanes join in by work splitting (below).
 			unsigned base = 0;
 			if(lane == 0)
 			{
-				base = atomicAdd(fp.cand_count + 2, (unsigned) __popc(idle));
+				base = atomicAdd(fp.cand_count + 2, (unsigned) SKR_DEFER_REFILL);
 			}
 			base = __shfl_sync(0xffffffffu, base, 0);
-			more = base + (unsigned) __popc(idle) < count;
-			if(!active)
+			more = base + (unsigned) SKR_DEFER_REFILL < count;
+			const unsigned ri = (unsigned) __popc(idle & ((1u << lane) - 1u));
+			if(!active && ri < (unsigned) SKR_DEFER_REFILL && base + ri < count)
 			{
-				const unsigned g = base + __popc(idle & ((1u << lane) - 1u));
-				if(g < count)
-				{
-					const float4 c = __ldg(fp.cand_d + g);
-					px			   = __ldg(fp.cand_px + g);
-					tri_walk_begin(wk, sv.cam_pos, f3(c), c.w);
-					active = true;
-				}
+				const float4 c = __ldg(fp.cand_d + base + ri);
+				px			   = __ldg(fp.cand_px + base + ri);
+				tri_walk_begin(wk, sv.cam_pos, f3(c), c.w);
+				active = true;
 			}
+			idle = __ballot_sync(0xffffffffu, !active);
 		}
-		else if(idle == 0xffffffffu)
+		if(idle == 0xffffffffu)
 		{
-			break;
+			if(!more)
+			{
+				break;
+			}
+			continue; // (fewer than SKR_DEFER_REFILL cannot be idle when all are: the refill above runs next time round)
 		}
-		else if(idle != 0u && !more)
+		if(idle != 0u && (!more || __popc(idle) >= 4))
 		{
-			// WORK SPLITTING.  The list is used up and some lanes are idle while others are deep inside the mesh (a line that
-			// threads the model without an accepted hit walks thousands of nodes: the frame used to wait for ONE such lane).
-			// A busy lane gives the OLDEST entry of its stack -- the biggest pending subtree -- to an idle lane, which walks it
-			// for the same ray; the answers combine by OR (any accepted triangle blackens the pixel).
+			// WORK SPLITTING.  Some lanes are idle while others are deep inside the mesh (a line that threads the model without
+			// an accepted hit walks hundreds of nodes; the 32 rays of one warp used to be as slow as their slowest).  A busy lane
+			// gives the OLDEST entry of its stack -- the biggest pending subtree -- to an idle lane, which walks it for the
+			// same ray; the answers combine by OR (any accepted triangle blackens the pixel).
 			const unsigned donors = __ballot_sync(0xffffffffu, active && wk.sp > wk.base);
 			if(donors != 0u)
 			{
