@@ -380,15 +380,28 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
             t1 = time.time()
             path = "skr_scene_upload + skr_render (host arrays in, pinned host RGB8 out), wall clock"
         else:
-            # every rank: upload + render its tiles with the kernel storing straight into the shared page-locked host frame
-            # (its own PCIe link) + stream sync; a barrier over the ranks ends the step
+            # Every rank: upload + render its tiles; a finished pixel is stored (over NVLink, while the kernels trace) into the
+            # device buffer of the rank that OWNS its band of rows (skr_render_bands_device); after the symmetric-memory barrier
+            # each rank holds its band complete and copies it into ONE page-locked host frame shared by the ranks (a /dev/shm
+            # segment, skr_pin_host) over its own PCIe link; a second barrier ends the step.  Without peer mapping: the kernels
+            # store straight into the host frame.
             shf = SharedHostFrame(torch, dist, r, nbytes, rank, world)
+            rows = 0 if peer_frames is None else peer_frames.band_rows(base.height, world)
+            row_bytes = base.width * 3
 
             def e2e_step():
                 r.upload(scene)
-                st = r.render_peers_device(base, [shf.dev_ptr], want_stats=tree)
+                if peer_frames is None:
+                    st = r.render_peers_device(base, [shf.dev_ptr], want_stats=tree)
+                    r.sync()
+                    dist.barrier()
+                    return st
+                with torch.cuda.stream(ext):
+                    buf, st = peer_frames.render(r, base, rank, world, want_stats=tree, bands=True)
+                    y0, y1 = min(base.height, rank * rows), min(base.height, (rank + 1) * rows)
+                    r.copy_to_host(shf.host_ptr + y0 * row_bytes, buf.data_ptr() + y0 * row_bytes, (y1 - y0) * row_bytes)
+                    peer_frames.barrier_again()
                 r.sync()
-                dist.barrier()
                 return st
 
             e2e_step()
@@ -402,10 +415,18 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
             t = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t1 = t0 + float(t.item())
-            out["e2e_frame_nonzero"] = bool(shf.np.any()) if rank == 0 else None
+            dist.barrier()
+            if rank == 0:
+                # the frame the ranks assembled in host memory must be the frame one GPU renders
+                whole = torch.empty((base.height, base.width, 3), dtype=torch.uint8, device=dev)
+                r.render_device(dataclasses.replace(base, rank=0, world=1), whole.data_ptr(), 0)
+                out["e2e_frame_identical_to_one_gpu"] = bool((whole.cpu().numpy().reshape(-1) == shf.np).all())
             shf.close(dist, world)
-            path = ("per rank skr_scene_upload + skr_render_peers_device into ONE page-locked host frame shared by the ranks (each GPU stores its "
-                    "tiles over its own PCIe link), stream sync + barrier per step; wall clock, max over ranks")
+            path = ("per rank skr_scene_upload + skr_render_bands_device (pixels stored over NVLink into the band owner's memory), symmetric-memory "
+                    "barrier, each rank copies its band of rows into ONE page-locked host frame shared by the ranks over its own PCIe link, second "
+                    "barrier + stream sync; wall clock, max over ranks" if peer_frames is not None else
+                    "per rank skr_scene_upload + skr_render_peers_device storing straight into ONE page-locked host frame shared by the ranks, stream "
+                    "sync + barrier per step; wall clock, max over ranks")
         out["e2e"] = {"value": rays * n_e2e / (t1 - t0) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(sc_bytes) * world,
                       "d2h_bytes_per_step": int(nbytes), "ms_per_step": (t1 - t0) * 1e3 / n_e2e, "steps": n_e2e, "path": path}
     return out

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -45,7 +46,11 @@ struct skr_mgpu
 	size_t pinned_bytes = 0;
 	bool pinned_by_us = false;
 	void *pinned_dev = nullptr;
-	bool direct = true; // default frame assembly: kernels store into the host frame (SKR_MGPU_NO_DIRECT=1: via GPU 0 / NCCL)
+	bool direct = true; // kernels may store into the host frame (SKR_MGPU_NO_DIRECT=1: assembly via GPU 0 / NCCL as in round 1)
+	// default frame assembly where every GPU pair has peer access: row bands (render_bands)
+	bool bands = false;
+	std::vector<uint8_t *> d_band; // per GPU: a frame-sized buffer of which only the GPU's own band of rows is used
+	std::vector<size_t> cap_band;
 	std::vector<skr_ctx *> ctx;
 	std::vector<ncclComm_t> comm;
 	std::vector<uint8_t *> d_tiles;	   // per GPU: its compact tiles
@@ -170,7 +175,91 @@ void sum_stats(skr_stats *stats, const std::vector<skr_stats> &st)
 	}
 }
 
-// Default frame assembly: NO device frame at all.  Every GPU renders its interleaved tiles with skr_render_peers_device and
+// Default frame assembly on a box whose GPUs all see each other (NVLink): ROW BANDS.  Every GPU renders its interleaved
+// tiles (load balance) but stores each finished pixel block, over NVLink and while it is still tracing, into the memory of
+// the GPU that owns the block's band of rows (skr_render_bands_device).  When all kernels are done every GPU holds one
+// contiguous band of the frame and copies it to the host ITSELF: N copies over N PCIe links instead of one frame through
+// GPU 0's.
+int render_bands(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stats *stats, size_t frame_bytes)
+{
+	const int W = m->world;
+	pin_frame(m, rgb8, frame_bytes); // (a pageable destination works too, only slower: the copies stage through the driver)
+	for(int i = 0; i < W; i++)
+	{
+		if(m->cap_band[i] < frame_bytes)
+		{
+			cudaSetDevice(i);
+			cudaFree(m->d_band[i]);
+			m->d_band[i] = nullptr;
+			if(cudaMalloc(&m->d_band[i], frame_bytes) != cudaSuccess)
+			{
+				m->cap_band[i] = 0;
+				return fail(m, SKR_ERR_CUDA, "skr_mgpu_render: cudaMalloc(band buffer) failed on GPU %d", i);
+			}
+			m->cap_band[i] = frame_bytes;
+		}
+	}
+	const int rows		   = ((opt->height + W - 1) / W + 3) / 4 * 4;
+	const size_t row_bytes = (size_t) opt->width * 3;
+	std::vector<int> rc(W, 0);
+	std::vector<std::string> msg(W);
+	std::vector<skr_stats> st(W);
+	const bool want_stats = stats != nullptr;
+	std::vector<void *> frames(m->d_band.begin(), m->d_band.end());
+	on_all(m, [&](int i) {
+		skr_options oi = *opt;
+		oi.world	   = W;
+		oi.rank		   = i;
+		memset(&st[i], 0, sizeof st[i]);
+		rc[i] = skr_render_bands_device(m->ctx[i], &oi, frames.data(), W, rows, want_stats ? &st[i] : nullptr);
+		if(!rc[i])
+		{
+			rc[i] = skr_sync(m->ctx[i]);
+		}
+		if(rc[i])
+		{
+			msg[i] = skr_last_error(m->ctx[i]);
+		}
+	});
+	for(int i = 0; i < W; i++)
+	{
+		if(rc[i])
+		{
+			return fail(m, rc[i], "GPU %d: %s", i, msg[i].c_str());
+		}
+	}
+	// every kernel is done: each GPU copies its band out
+	on_all(m, [&](int i) {
+		const size_t y0 = std::min((size_t) opt->height, (size_t) i * rows), y1 = std::min((size_t) opt->height, (size_t) (i + 1) * rows);
+		if(y1 > y0)
+		{
+			rc[i] = skr_copy_to_host(m->ctx[i], rgb8 + y0 * row_bytes, m->d_band[i] + y0 * row_bytes, (y1 - y0) * row_bytes);
+			if(!rc[i])
+			{
+				rc[i] = skr_sync(m->ctx[i]);
+			}
+			if(rc[i])
+			{
+				msg[i] = skr_last_error(m->ctx[i]);
+			}
+		}
+	});
+	for(int i = 0; i < W; i++)
+	{
+		if(rc[i])
+		{
+			return fail(m, rc[i], "GPU %d: %s", i, msg[i].c_str());
+		}
+	}
+	if(stats)
+	{
+		sum_stats(stats, st);
+		stats->ms_d2h = 0.0f;
+	}
+	return SKR_OK;
+}
+
+// Frame assembly without peer access: NO device frame at all.  Every GPU renders its interleaved tiles with skr_render_peers_device and
 // its kernel stores each finished pixel block straight into the caller's page-locked host frame -- every GPU over its OWN
 // PCIe link, while the rest of its tiles are still being traced.  When the GPUs' streams have drained the frame is whole.
 int render_direct(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stats *stats, size_t frame_bytes)
@@ -347,6 +436,10 @@ void skr_mgpu_destroy(skr_mgpu *m)
 		{
 			cudaFree(m->d_frame);
 		}
+		if(i < (int) m->d_band.size())
+		{
+			cudaFree(m->d_band[i]);
+		}
 		if(i < (int) m->comm.size() && m->comm[i])
 		{
 			ncclCommDestroy(m->comm[i]);
@@ -404,6 +497,37 @@ int skr_mgpu_init(int n_gpus, skr_mgpu **out)
 	for(int i = 0; i < n_gpus; i++)
 	{
 		m->workers[i]->th = std::thread(worker_main, m, i);
+	}
+	m->d_band.assign(n_gpus, nullptr);
+	m->cap_band.assign(n_gpus, 0);
+	{
+		// row bands need every GPU to map every other GPU's memory
+		const char *nb = getenv("SKR_MGPU_NO_BANDS");
+		m->bands	   = m->direct && n_gpus > 1 && !(nb && nb[0] == '1');
+		for(int i = 0; i < n_gpus && m->bands; i++)
+		{
+			cudaSetDevice(i);
+			for(int j = 0; j < n_gpus && m->bands; j++)
+			{
+				if(i == j)
+				{
+					continue;
+				}
+				int can = 0;
+				if(cudaDeviceCanAccessPeer(&can, i, j) != cudaSuccess || !can)
+				{
+					m->bands = false;
+					break;
+				}
+				const cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+				if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+				{
+					m->bands = false;
+				}
+				cudaGetLastError();
+			}
+		}
+		cudaSetDevice(0);
 	}
 	// peer path: every other GPU maps GPU 0's memory; its kernels then store finished pixels into GPU 0's frame
 	{
@@ -480,6 +604,10 @@ int skr_mgpu_render(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stat
 		return fail(m, SKR_ERR_ARG, "skr_mgpu_render: bad options");
 	}
 	const size_t frame_bytes = (size_t) opt->width * opt->height * 3;
+	if(m->bands)
+	{
+		return render_bands(m, opt, rgb8, stats, frame_bytes);
+	}
 	if(m->direct)
 	{
 		return render_direct(m, opt, rgb8, stats, frame_bytes);

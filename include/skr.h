@@ -183,6 +183,14 @@ int skr_deinterleave_device(skr_ctx *ctx, const skr_options *opt, const void *d_
  * reads one while the next is being rendered.  1 <= n_frames <= 8.  Asynchronous like skr_render_device. */
 int skr_render_peers_device(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, skr_stats *stats);
 
+/* Frame split whose result leaves over EVERY GPU's PCIe link (ABI 3).  Like skr_render_peers_device, but a finished pixel
+ * goes to ONE of the frames: d_frames[min(y / rows_per_frame, n_frames - 1)], y its image row (every buffer is addressed
+ * as a whole H*W*3 frame; only its own band of rows is ever written).  With one frame per GPU of the box, after the ranks'
+ * barrier GPU k holds rows [k * rows_per_frame, (k + 1) * rows_per_frame) complete in its own memory -- whichever GPU
+ * rendered them, the stores crossed NVLink while the kernels were still tracing -- and copies that band to the host
+ * itself: the D2H of the frame is N parallel copies instead of one.  rows_per_frame: a positive multiple of 4. */
+int skr_render_bands_device(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, int rows_per_frame, skr_stats *stats);
+
 /* Frames straight into HOST memory (ABI 3).  A page-locked, device-mapped host buffer is a valid target of
  * skr_render_peers_device: the kernel that finishes a pixel stores it over PCIe while the rest of the frame is still
  * being traced, and with a frame split every GPU writes its own tiles over its OWN PCIe link -- no device frame, no
@@ -192,6 +200,9 @@ int skr_render_peers_device(skr_ctx *ctx, const skr_options *opt, void *const *d
  * nothing to undo), another skr_status on error. */
 int skr_pin_host(skr_ctx *ctx, void *host, size_t bytes, void **d_ptr);
 int skr_unpin_host(skr_ctx *ctx, void *host);
+/* Device -> host copy enqueued on the library's stream, i.e. behind the frames rendered so far (asynchronous when host_dst is
+ * page-locked; skr_sync() waits for it): how a rank copies its band of skr_render_bands_device out. */
+int skr_copy_to_host(skr_ctx *ctx, void *host_dst, const void *d_src, size_t bytes);
 
 /* The library's stream as a cudaStream_t (so that callers can order their own work / events after it),
  * and a blocking wait for it. */

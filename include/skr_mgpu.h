@@ -2,7 +2,11 @@
  *
  * The reference has no multi-GPU path (its only parallelism is the OpenMP row loop, src/main.cpp:33); this is the
  * additive part (3) of the north star: interleaved image tiles across the GPUs of one box.  Frame assembly:
- *   - direct path (default): the caller's host frame is page-locked and mapped (once; cudaHostRegister, or used as it is
+ *   - row bands (default where every GPU pair has peer access, i.e. NVLink boxes): every GPU renders its interleaved tiles
+ *     but stores each finished pixel block, over NVLink and while it is still tracing, into the memory of the GPU that OWNS
+ *     the block's band of rows (skr_render_bands_device); then every GPU copies its contiguous band to the host itself:
+ *     N copies over N PCIe links (SKR_MGPU_NO_BANDS=1 skips this path);
+ *   - direct path (no peer access): the caller's host frame is page-locked and mapped (once; cudaHostRegister, or used as it is
  *     when already page-locked) and every GPU's render kernel stores its finished pixel blocks straight into it over its
  *     OWN PCIe link while it is still tracing -- no device frame, no gather, no D2H copy through one GPU;
  *   - peer path (SKR_MGPU_NO_DIRECT=1, when every GPU can map GPU 0's memory): skr_render_peers_device() on every GPU with GPU 0's

@@ -219,6 +219,7 @@ class Renderer:
         L.skr_render_tiles_device.argtypes = [C.c_void_p, C.POINTER(_Options), C.c_void_p, C.POINTER(Stats)]
         L.skr_deinterleave_device.argtypes = [C.c_void_p, C.POINTER(_Options), C.c_void_p, C.c_void_p]
         L.skr_render_peers_device.argtypes = [C.c_void_p, C.POINTER(_Options), C.POINTER(C.c_void_p), C.c_int, C.POINTER(Stats)]
+        L.skr_render_bands_device.argtypes = [C.c_void_p, C.POINTER(_Options), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(Stats)]
         L.skr_stream.restype = C.c_void_p
         L.skr_stream.argtypes = [C.c_void_p]
         L.skr_sync.argtypes = [C.c_void_p]
@@ -226,6 +227,7 @@ class Renderer:
         L.skr_measure_fp32_peak.argtypes = [C.c_void_p, C.c_int]
         L.skr_pin_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.skr_unpin_host.argtypes = [C.c_void_p, C.c_void_p]
+        L.skr_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.skr_measure_bandwidth.restype = C.c_double
         L.skr_measure_bandwidth.argtypes = [C.c_void_p, C.c_int]
         L.skr_abi_version.restype = C.c_int
@@ -303,6 +305,15 @@ class Renderer:
                     "skr_render_peers_device")
         return st
 
+    def render_bands_device(self, option: Options, d_frames, rows_per_frame: int, want_stats: bool = True):
+        """skr_render_bands_device: a finished pixel of image row y goes to d_frames[min(y // rows_per_frame, len - 1)]."""
+        st = Stats() if want_stats else None
+        o = option._c()
+        arr = (C.c_void_p * len(d_frames))(*[int(p) for p in d_frames])
+        self._check(self.lib.skr_render_bands_device(self.ctx, C.byref(o), arr, len(d_frames), rows_per_frame, C.byref(st) if want_stats else None),
+                    "skr_render_bands_device")
+        return st
+
     def deinterleave_device(self, option: Options, d_gathered: int, d_rgb8: int) -> None:
         o = option._c()
         self._check(self.lib.skr_deinterleave_device(self.ctx, C.byref(o), d_gathered, d_rgb8),
@@ -315,6 +326,10 @@ class Renderer:
         if rc not in (0, 1000):
             self._check(rc, "skr_pin_host")
         return int(d.value or 0), rc == 0
+
+    def copy_to_host(self, host_ptr: int, d_ptr: int, nbytes: int) -> None:
+        """skr_copy_to_host: D2H on the library's stream (behind the frames rendered so far); sync() waits for it."""
+        self._check(self.lib.skr_copy_to_host(self.ctx, host_ptr, d_ptr, nbytes), "skr_copy_to_host")
 
     def unpin_host(self, host_ptr: int) -> None:
         self._check(self.lib.skr_unpin_host(self.ctx, host_ptr), "skr_unpin_host")

@@ -122,6 +122,19 @@ struct skr_ctx
 	unsigned *h_count = nullptr; // pinned
 
 	unsigned long long *d_counters = nullptr; // 9 (16 allocated)
+	// heavy-first launch order of the tiles (single-kernel frames), cached while scene and frame geometry stay the same
+	int *d_tile_order = nullptr;
+	size_t tile_order_bytes = 0;
+	std::vector<int> tile_order_host;
+	std::vector<float> host_spheres;
+	unsigned long long scene_gen = 0; // bumped by every skr_scene_upload
+	struct OrderKey
+	{
+		unsigned long long gen;
+		int width, height, tile, rank, world, rows_per_band;
+		float fov;
+	} order_key{};
+	bool order_valid = false;
 	float4 *d_cand_d = nullptr; // deferred triangle query: candidates (tri_deferred_kernel)
 	uint2 *d_cand_px = nullptr;
 	size_t cand_d_bytes = 0, cand_px_bytes = 0;
@@ -569,6 +582,7 @@ struct Plan
 	long long tiles_local;
 	int levels;		  // depth levels of the --gillum / fresnel tree (0: none)
 	bool shaded;	  // opt-in shaded-triangles mode (skr_shaded.cuh)
+	int rows_per_band; // tile rows per band of skr_render's overlapped copy-out (0: the frame does not leave in bands)
 	bool defer;		  // triangle queries of the camera rays go through tri_deferred_kernel
 	int qlevels;	  // queue levels needed: `levels`, or one less when the leaves are shaded in place
 	bool leaf_inline; // depth-1 hits are shaded by the warp that found them (shade_expand_kernel<..., LEAF>)
@@ -597,6 +611,7 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		return fail(ctx, SKR_ERR_ARG, "skr_options: shade_triangles (a non-parity extension) is not combined with monte_carlo / fresnel");
 	}
 	pl.shaded		= o->shade_triangles != 0;
+	pl.rows_per_band = 0;
 	const int world = o->world > 1 ? o->world : 1;
 	const int rank	= o->world > 1 ? o->rank : 0;
 	if(rank < 0 || rank >= world)
@@ -946,6 +961,94 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	return SKR_OK;
 }
 
+// Heavy-first launch order.  A frame that is ONE kernel ends with the tail of its last CTAs; in scan order those are the
+// bottom rows of the image -- the ground, the most expensive pixels of most scenes -- and with the frame split over 8 GPUs
+// (two waves of CTAs each) that tail was a third of the step.  The host classifies this rank's tiles: can any line
+// through a pixel of the tile pass a sphere's test?  (The bundle test of cull_pairs, skr_device.cuh, evaluated in double
+// for the cone around the tile's centre ray.)  Tiles that can go first, sky tiles last; within a band of tile rows when
+// the frame leaves in bands (skr_render's overlapped copy-out), so that bands still complete in order.  Purely a
+// permutation of the launch: every pixel computes what it computed before.
+int tile_launch_order(skr_ctx *ctx, const Plan &pl, int rows_per_band, FrameParams &fp)
+{
+	fp.tile_order = nullptr;
+	const char *no = getenv("SKR_NO_TILE_ORDER");
+	if(ctx->sv.S == 0 || ctx->sv.T > 0 || (no && no[0] == '1') || pl.tiles_local < 8)
+	{
+		return SKR_OK; // nothing to tell apart (no spheres), or triangles anywhere: keep scan order
+	}
+	skr_ctx::OrderKey key;
+	memset(&key, 0, sizeof key); // (compared with memcmp: padding included)
+	key.gen = ctx->scene_gen, key.width = fp.width, key.height = fp.height, key.tile = fp.tile, key.rank = fp.rank, key.world = fp.world;
+	key.rows_per_band = rows_per_band, key.fov = fp.angle;
+	if(!ctx->order_valid || memcmp(&key, &ctx->order_key, sizeof key) != 0)
+	{
+		const SceneView &sv = ctx->sv;
+		const auto ray		= [&](double x, double y, double *d) {
+			 const double u = (2.0 * (x * fp.inv_w) - 1.0) * fp.angle * fp.aspect, v = (1.0 - 2.0 * (y * fp.inv_h)) * fp.angle;
+			 d[0] = sv.cam_dir.x + u * sv.cam_right.x + v * sv.cam_up.x;
+			 d[1] = sv.cam_dir.y + u * sv.cam_right.y + v * sv.cam_up.y;
+			 d[2] = sv.cam_dir.z + u * sv.cam_right.z + v * sv.cam_up.z;
+		};
+		std::vector<int> heavy, light;
+		std::vector<int> &order = ctx->tile_order_host;
+		order.clear();
+		int band_of_last = -1;
+		const auto flush = [&]() {
+			order.insert(order.end(), heavy.begin(), heavy.end());
+			order.insert(order.end(), light.begin(), light.end());
+			heavy.clear();
+			light.clear();
+		};
+		for(long long lt = 0; lt < pl.tiles_local; lt++)
+		{
+			const long long gt = lt * fp.world + fp.rank;
+			if(gt >= fp.tiles_total)
+			{
+				light.push_back(fp.tiles_total); // padding slot: decode_pixel marks it invalid
+				continue;
+			}
+			const int tx = (int) (gt % fp.tiles_x), ty = (int) (gt / fp.tiles_x);
+			const int band = rows_per_band > 0 ? ty / rows_per_band : 0;
+			if(band != band_of_last)
+			{
+				flush();
+				band_of_last = band;
+			}
+			// cone of the tile: centre ray w, half angle beta from the farthest corner (+ one pixel for the jitter)
+			const double x0 = tx * fp.tile - 1.0, x1 = std::min(fp.width, (tx + 1) * fp.tile) + 1.0;
+			const double y0 = ty * fp.tile - 1.0, y1 = std::min(fp.height, (ty + 1) * fp.tile) + 1.0;
+			double w[3], c[3];
+			ray(0.5 * (x0 + x1), 0.5 * (y0 + y1), w);
+			const double ww = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+			double sin2 = 0.0;
+			for(int k = 0; k < 4; k++)
+			{
+				ray(k & 1 ? x1 : x0, k & 2 ? y1 : y0, c);
+				const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2], cw = c[0] * w[0] + c[1] * w[1] + c[2] * w[2];
+				sin2 = std::max(sin2, 1.0 - cw * cw / (cc * ww));
+			}
+			const double beta = 1.1 * asin(std::min(1.0, sqrt(std::max(0.0, sin2)))) + 1e-6;
+			bool sees = !(ww > 0.0) || !(beta < 0.7); // degenerate camera / very wide tiles: call it heavy
+			for(int s = 0; s < sv.S && !sees; s++)
+			{
+				const float *p	= ctx->host_spheres.data() + 18 * (size_t) s;
+				const double ux = (double) p[0] - sv.cam_pos.x, uy = (double) p[1] - sv.cam_pos.y, uz = (double) p[2] - sv.cam_pos.z;
+				const double uu = ux * ux + uy * uy + uz * uz, hw = ux * w[0] + uy * w[1] + uz * w[2];
+				const double X	= fabs((double) p[3]) * 1.01 + sqrt(uu) * beta + 1e-4 * (1.0 + sqrt(uu));
+				sees			= !(uu - hw * hw / ww > X * X);
+			}
+			(sees ? heavy : light).push_back((int) gt);
+		}
+		flush();
+		CK(ensure(ctx->d_tile_order, ctx->tile_order_bytes, sizeof(int) * order.size()));
+		CK(cudaMemcpyAsync(ctx->d_tile_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
+		ctx->order_key	 = key;
+		ctx->order_valid = true;
+	}
+	fp.tile_order = ctx->d_tile_order;
+	return SKR_OK;
+}
+
 // the device error word after the stream has drained (h_err holds a fresh copy): reported once, then cleared
 int check_error_word(skr_ctx *ctx, const char *what)
 {
@@ -991,6 +1094,14 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 		}
 		const char *no	  = getenv("SKR_NO_STRIP_WORDS");
 		pl.fp.strip_words = (ok && !(no && no[0] == '1')) ? 1 : 0;
+	}
+	if(!tree && !pl.shaded)
+	{
+		const int rc_order = tile_launch_order(ctx, pl, pl.rows_per_band, pl.fp);
+		if(rc_order)
+		{
+			return rc_order;
+		}
 	}
 	// a single-kernel frame needs no per-kernel events (its span is the frame), no counter reset unless counters were
 	// asked for, and no reset of the error word (zero unless a frame failed; cleared again below when read non-zero)
@@ -1210,7 +1321,7 @@ void skr_destroy(skr_ctx *ctx)
 	ctx->bvh_shade.release();
 	cudaFree(ctx->d_rgb8), cudaFree(ctx->d_rgb32), cudaFree(ctx->d_accum);
 	cudaFree(ctx->d_arena);
-	cudaFree(ctx->d_cursor), cudaFree(ctx->d_cand_d), cudaFree(ctx->d_cand_px);
+	cudaFree(ctx->d_cursor), cudaFree(ctx->d_cand_d), cudaFree(ctx->d_cand_px), cudaFree(ctx->d_tile_order);
 	cudaFree(ctx->d_counters), cudaFree(ctx->d_err), cudaFree(ctx->d_band);
 	if(ctx->copy_stream)
 	{
@@ -1512,6 +1623,8 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	CK(cudaStreamSynchronize(ctx->stream));
 	sv.nbig			= (T > 0 && sv.bvh) ? std::min((int) *ctx->h_count, BIG_TRI_CAP) : 0;
 	ctx->have_scene = true;
+	ctx->scene_gen++;
+	ctx->host_spheres.assign(sc->spheres, sc->spheres + 18 * (size_t) S); // (geometry for the tile classification of tile_launch_order)
 	return SKR_OK;
 }
 
@@ -1632,6 +1745,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 			pl.fp.band_flag	 = ctx->d_band + MAX_BANDS;
 			pl.fp.band_ctas	 = (unsigned) rpb * (unsigned) fp.tiles_x * (unsigned) (tpix / 32); // blocks per band
 			pl.fp.band_seq	 = ++ctx->band_seq;
+			pl.rows_per_band = rpb;
 		}
 	}
 	const size_t row8 = (size_t) opt->width * 3, row32 = row8 * sizeof(float);
@@ -1760,13 +1874,13 @@ int skr_render_tiles_device(skr_ctx *ctx, const skr_options *opt, void *d_tiles,
 	return render_common(ctx, opt, pl, stats);
 }
 
-int skr_render_peers_device(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, skr_stats *stats)
+static int render_to_frames(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, int rows_per_frame, skr_stats *stats, const char *who)
 {
 	REQUIRE_CTX();
 	REQUIRE_SCENE();
 	if(!d_frames || n_frames < 1 || n_frames > 8)
 	{
-		return fail(ctx, SKR_ERR_ARG, "skr_render_peers_device: between 1 and 8 frame pointers are required (got %d)", n_frames);
+		return fail(ctx, SKR_ERR_ARG, "%s: between 1 and 8 frame pointers are required (got %d)", who, n_frames);
 	}
 	Plan pl;
 	int rc = make_plan(ctx, opt, pl);
@@ -1778,12 +1892,27 @@ int skr_render_peers_device(skr_ctx *ctx, const skr_options *opt, void *const *d
 	{
 		if(!d_frames[k])
 		{
-			return fail(ctx, SKR_ERR_ARG, "skr_render_peers_device: frame pointer %d is null", k);
+			return fail(ctx, SKR_ERR_ARG, "%s: frame pointer %d is null", who, k);
 		}
 		pl.fp.peers[k] = static_cast<uint8_t *>(d_frames[k]);
 	}
-	pl.fp.n_peers = n_frames;
+	pl.fp.n_peers	= n_frames;
+	pl.fp.peer_rows = rows_per_frame;
 	return render_common(ctx, opt, pl, stats);
+}
+
+int skr_render_peers_device(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, skr_stats *stats)
+{
+	return render_to_frames(ctx, opt, d_frames, n_frames, 0, stats, "skr_render_peers_device");
+}
+
+int skr_render_bands_device(skr_ctx *ctx, const skr_options *opt, void *const *d_frames, int n_frames, int rows_per_frame, skr_stats *stats)
+{
+	if(rows_per_frame <= 0 || rows_per_frame % 4 != 0)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_render_bands_device: rows_per_frame must be a positive multiple of 4 (got %d)", rows_per_frame);
+	}
+	return render_to_frames(ctx, opt, d_frames, n_frames, rows_per_frame, stats, "skr_render_bands_device");
 }
 
 int skr_deinterleave_device(skr_ctx *ctx, const skr_options *opt, const void *d_gathered, void *d_rgb8)
@@ -1863,6 +1992,20 @@ int skr_pin_host(skr_ctx *ctx, void *host, size_t bytes, void **d_ptr)
 	}
 	CK(cudaHostGetDevicePointer(d_ptr, host, 0));
 	return known ? 1000 : SKR_OK; // 1000: was page-locked already (nothing to undo)
+}
+
+int skr_copy_to_host(skr_ctx *ctx, void *host_dst, const void *d_src, size_t bytes)
+{
+	REQUIRE_CTX();
+	if(!host_dst || !d_src)
+	{
+		return fail(ctx, SKR_ERR_ARG, "skr_copy_to_host: null pointer");
+	}
+	if(bytes)
+	{
+		CK(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	return SKR_OK;
 }
 
 int skr_unpin_host(skr_ctx *ctx, void *host)

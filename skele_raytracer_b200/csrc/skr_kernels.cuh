@@ -57,6 +57,9 @@ struct FrameParams
 	int cull;		  // 1: bundle culling (cull_pairs) for this frame: jittered, >= 4 samples per pixel, <= 64 spheres
 	float cull_delta; // bound on |d(r) - d(0.5)| over the jitter draw r of a pixel (ray directions are un-normalised)
 	int strip_words;  // 1: whole 8 x 4 blocks leave as 32-bit words (width % 4 == 0, 4-byte aligned frames)
+	// Launch order of this rank's tiles (single-kernel frames): global tile index per local slot, tiles that can see a sphere
+	// FIRST, so that the tail of the kernel is made of cheap sky tiles (tiles_local entries; padding slots = tiles_total), or null
+	const int *tile_order;
 	uint2 key;
 	uint32_t node_base, slot_gi;
 	uint8_t *rgb8;	 // row-major frame or null
@@ -64,6 +67,7 @@ struct FrameParams
 	uint8_t *tiles8; // compact tile-major buffer or null
 	uint8_t *peers[8]; // skr_render_peers_device: row-major RGB8 frames (one per GPU of the box, peer-mapped) or null
 	int n_peers;
+	int peer_rows; // 0: every pixel goes to ALL peers[]; > 0: to peers[min(y / peer_rows, n_peers - 1)] only (skr_render_bands_device)
 	// Copy-out overlapped with the kernel (skr_render, single-kernel frames): CTAs are grouped by blockIdx into bands of
 	// `band_ctas` (whole tile rows); the CTA that completes a band publishes band_seq in band_flag[band], which a
 	// stream-ordered wait on the copy stream is parked on.  Null when unused.
@@ -96,7 +100,8 @@ SKR_DEV PixelId decode_pixel(const FrameParams &fp, long long lp)
 	const int w = r >> 5, lane = r & 31;
 	const int wx = w % fp.wpr, wy = w / fp.wpr;
 	const int px = wx * 8 + (lane & 7), py = wy * 4 + (lane >> 3);
-	const long long gt = (long long) lt * fp.world + fp.rank;
+	// local tile -> global tile: interleaved over the ranks, visited in the order of fp.tile_order when the host supplied one
+	const long long gt = fp.tile_order ? (long long) __ldg(fp.tile_order + lt) : (long long) lt * fp.world + fp.rank;
 	PixelId p;
 	p.valid = gt < fp.tiles_total;
 	const int tx = (int) (gt % fp.tiles_x), ty = (int) (gt / fp.tiles_x);
@@ -208,7 +213,9 @@ SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, 
 		// peers travel over NVLink while the rest of the kernel is still tracing
 		const uint8_t r = quantise(c.x), g = quantise(c.y), b = quantise(c.z);
 		const size_t at = 3 * ((size_t) p.y * fp.width + p.x);
-		for(int k = 0; k < fp.n_peers; k++)
+		const int k0 = fp.peer_rows > 0 ? min(p.y / fp.peer_rows, fp.n_peers - 1) : 0;
+		const int k1 = fp.peer_rows > 0 ? k0 + 1 : fp.n_peers;
+		for(int k = k0; k < k1; k++)
 		{
 			uint8_t *o = fp.peers[k] + at;
 			o[0]	   = r;
@@ -219,7 +226,7 @@ SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, 
 	if(fp.tiles8)
 	{
 		const int tpix = fp.tile * fp.tile;
-		const long long lt = lp / tpix;
+		const long long lt = ((long long) (p.y / fp.tile) * fp.tiles_x + p.x / fp.tile) / fp.world; // slot in the compact buffer (whatever the launch order)
 		const int tx = p.x % fp.tile, ty = p.y % fp.tile;
 		uint8_t *o = fp.tiles8 + 3 * ((size_t) lt * tpix + (size_t) ty * fp.tile + tx);
 		o[0]	   = quantise(c.x);
@@ -258,8 +265,9 @@ SKR_DEV void write_block(const FrameParams &fp, long long lp, const PixelId &p, 
 	}
 	if(fp.tiles8 && p.valid)
 	{
-		const int tpix = fp.tile * fp.tile;
-		uint8_t *t	   = fp.tiles8 + 3 * ((size_t) (lp / tpix) * tpix + (size_t) (p.y % fp.tile) * fp.tile + (p.x % fp.tile));
+		const int tpix	   = fp.tile * fp.tile;
+		const long long lt = ((long long) (p.y / fp.tile) * fp.tiles_x + p.x / fp.tile) / fp.world;
+		uint8_t *t		   = fp.tiles8 + 3 * ((size_t) lt * tpix + (size_t) (p.y % fp.tile) * fp.tile + (p.x % fp.tile));
 		t[0] = o[0], t[1] = o[1], t[2] = o[2];
 	}
 	__syncwarp();
@@ -274,7 +282,9 @@ SKR_DEV void write_block(const FrameParams &fp, long long lp, const PixelId &p, 
 			{
 				reinterpret_cast<uint32_t *>(fp.rgb8)[at] = v;
 			}
-			for(int k = 0; k < fp.n_peers; k++)
+			const int k0 = fp.peer_rows > 0 ? min((y0 + r) / fp.peer_rows, fp.n_peers - 1) : 0;
+			const int k1 = fp.peer_rows > 0 ? k0 + 1 : fp.n_peers;
+			for(int k = k0; k < k1; k++)
 			{
 				reinterpret_cast<uint32_t *>(fp.peers[k])[at] = v;
 			}
@@ -388,7 +398,8 @@ SKR_DEV void cand_push(const FrameParams &fp, bool want, long long lp, const Pix
 		fp.cand_d[idx]	   = make_float4(d.x, d.y, d.z, tmax);
 		const int tpix	   = fp.tile * fp.tile;
 		fp.cand_px[idx]	   = make_uint2((uint32_t) (p.y * fp.width + p.x),
-										(uint32_t) ((lp / tpix) * tpix + (long long) (p.y % fp.tile) * fp.tile + (p.x % fp.tile)));
+										(uint32_t) ((((long long) (p.y / fp.tile) * fp.tiles_x + p.x / fp.tile) / fp.world) * tpix + (long long) (p.y % fp.tile) * fp.tile +
+													(p.x % fp.tile)));
 	}
 }
 // consumer side: the hit point of an entry, src/raytrace.h:197-204 (exact t, then P = o + d * t)
@@ -1039,10 +1050,15 @@ SKR_DEV void write_black(const FrameParams &fp, uint2 px) // the pixel of a cand
 	{
 		fp.rgb8[at] = fp.rgb8[at + 1] = fp.rgb8[at + 2] = 0;
 	}
-	for(int k = 0; k < fp.n_peers; k++)
 	{
-		uint8_t *o = fp.peers[k] + at;
-		o[0] = o[1] = o[2] = 0;
+		const int y	 = (int) (px.x / (unsigned) fp.width);
+		const int k0 = fp.peer_rows > 0 ? min(y / fp.peer_rows, fp.n_peers - 1) : 0;
+		const int k1 = fp.peer_rows > 0 ? k0 + 1 : fp.n_peers;
+		for(int k = k0; k < k1; k++)
+		{
+			uint8_t *o = fp.peers[k] + at;
+			o[0] = o[1] = o[2] = 0;
+		}
 	}
 	if(fp.tiles8)
 	{

@@ -79,13 +79,19 @@ class PeerFrames:
         except Exception:  # no P2P / symmetric memory in this environment
             return None
 
-    def render(self, renderer, option, rank: int, world: int, want_stats: bool = False, targets=None):
+    @staticmethod
+    def band_rows(height: int, world: int) -> int:
+        """Rows of the band each rank ends up holding (render(..., bands=True)): height / world rounded up to a multiple of 4."""
+        return ((height + world - 1) // world + 3) // 4 * 4
+
+    def render(self, renderer, option, rank: int, world: int, want_stats: bool = False, targets=None, bands: bool = False):
         """Enqueue one frame; returns (frame tensor view HxWx3, Stats or None).
 
         Stream contract: the render kernel runs on the LIBRARY's stream (renderer.stream()), and so does the
         symmetric-memory barrier that ends the frame -- this method enters that stream itself.  The caller's current
         stream is made to wait for the barrier, so work the caller enqueues next sees a whole frame; nothing here blocks
-        the host.  `targets`: ranks whose frames are filled (default: all; e.g. [0] when only rank 0 reads the frame)."""
+        the host.  `targets`: ranks whose frames are filled (default: all; e.g. [0] when only rank 0 reads the frame).
+        `bands`: instead, row band r of the image (band_rows() rows) is assembled in rank r's buffer only."""
         import dataclasses
 
         import torch
@@ -100,7 +106,17 @@ class PeerFrames:
         lib = torch.cuda.ExternalStream(renderer.stream(), device=self.bufs[k].device)
         lib.wait_stream(caller)  # the previous reader of this buffer (on the caller's stream) is done before it is overwritten
         with torch.cuda.stream(lib):
-            st = renderer.render_peers_device(opt, ptrs, want_stats=want_stats)
+            if bands:
+                # every rank ends up with ITS band of rows complete in its own memory (to copy out over its own PCIe link)
+                st = renderer.render_bands_device(opt, list(self.hdls[k].buffer_ptrs), self.band_rows(option.height, world), want_stats=want_stats)
+            else:
+                st = renderer.render_peers_device(opt, ptrs, want_stats=want_stats)
             self.hdls[k].barrier()
         caller.wait_stream(lib)
+        self.last = k
         return self.bufs[k].view(option.height, option.width, 3), st
+
+    def barrier_again(self):
+        """A second symmetric-memory barrier on the current stream, behind whatever was enqueued after render() (e.g. the
+        ranks' copies of their bands): when it has passed, every rank's work up to here is done."""
+        self.hdls[self.last].barrier(channel=1)

@@ -744,3 +744,59 @@ def test_cli_on_reference_scene_files_if_present(port, tmp_path):
         _, p8, _, _ = port.render(sc, O.Options(width=320, height=180, **kw), rng_mode=O.RNG_PHILOX, seed=4)
         got = np.frombuffer(out.read_bytes()[len(b"P6\n320 180\n255\n"):], np.uint8).reshape(180, 320, 3)
         assert (np.abs(got.astype(int) - p8.astype(int)) <= 1).all(axis=2).mean() >= 0.999, name
+
+
+# ---- launch order / band targets ------------------------------------------------------------------
+
+@pytest.mark.parametrize("scene,kw", [("spheres2", dict(width=1920, height=1080, grid_size=2, use_shadows=True, seed=5)),
+                                      ("bear", dict(width=1000, height=700, use_shadows=True)),
+                                      ("spheres1", dict(width=640, height=360, grid_size=2, rank=1, world=3, tile=16, seed=2))])
+def test_heavy_first_tile_order_is_only_a_permutation(gpu, gscenes, scene, kw):
+    """Single-kernel frames launch the tiles that can see a sphere first (the kernel's tail is then cheap sky tiles);
+    every pixel -- and the compact tile buffer of the frame split -- is what scan order gives (SKR_NO_TILE_ORDER=1)."""
+    import torch
+    gpu.upload(gscenes[scene])
+    o = S.Options(**kw)
+    a32, a8, _ = gpu.render(o)
+    ta = torch.zeros(gpu.tiles_bytes(o), dtype=torch.uint8, device="cuda")
+    gpu.render_tiles_device(o, ta.data_ptr())
+    os.environ["SKR_NO_TILE_ORDER"] = "1"
+    try:
+        b32, b8, _ = gpu.render(o)
+        tb = torch.zeros(gpu.tiles_bytes(o), dtype=torch.uint8, device="cuda")
+        gpu.render_tiles_device(o, tb.data_ptr())
+    finally:
+        del os.environ["SKR_NO_TILE_ORDER"]
+    assert np.array_equal(a32.view(np.uint32), b32.view(np.uint32)) and np.array_equal(a8, b8)
+    assert torch.equal(ta, tb)
+
+
+def test_render_bands_device_sends_each_row_band_to_its_owner(gpu, gscenes):
+    """skr_render_bands_device: a finished pixel of row y goes to frame min(y // rows, n - 1) only; the bands of the n frames
+    put together are the whole image (here: four local buffers standing in for the GPUs of a box, two ranks rendering)."""
+    import torch
+    kw = dict(width=200, height=90, grid_size=2, use_shadows=True, seed=2)
+    gpu.upload(gscenes["spheres2"])
+    _, full8, _ = gpu.render(S.Options(**kw), want_rgb32=False)
+    frames = [torch.full((90, 200, 3), 7, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    rows = 24
+    for r in range(2):
+        gpu.render_bands_device(S.Options(rank=r, world=2, tile=16, **kw), [f.data_ptr() for f in frames], rows)
+    gpu.sync()
+    for k, f in enumerate(frames):
+        y0, y1 = k * rows, (90 if k == 3 else (k + 1) * rows)
+        got = f.cpu().numpy()
+        assert np.array_equal(got[y0:y1], full8[y0:y1])
+        mask = np.ones(90, bool)
+        mask[y0:y1] = False
+        assert (got[mask] == 7).all()           # nothing outside its band
+    with pytest.raises(S.SkrError, match="multiple of 4"):
+        gpu.render_bands_device(S.Options(**kw), [frames[0].data_ptr()], 10)
+    # --gillum frames (resolve_kernel) take the same route
+    kw = dict(width=96, height=54, max_depth=2, monte_carlo=True, num_path_traces=3, seed=2)
+    _, full8, _ = gpu.render(S.Options(**kw), want_rgb32=False)
+    frames = [torch.zeros((54, 96, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    for r in range(2):
+        gpu.render_bands_device(S.Options(rank=r, world=2, **kw), [f.data_ptr() for f in frames], 28)
+    gpu.sync()
+    assert np.array_equal(frames[0].cpu().numpy()[:28], full8[:28]) and np.array_equal(frames[1].cpu().numpy()[28:], full8[28:])
