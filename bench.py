@@ -429,6 +429,8 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
                     "sync + barrier per step; wall clock, max over ranks")
         out["e2e"] = {"value": rays * n_e2e / (t1 - t0) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(sc_bytes) * world,
                       "d2h_bytes_per_step": int(nbytes), "ms_per_step": (t1 - t0) * 1e3 / n_e2e, "steps": n_e2e, "path": path}
+        if "e2e_frame_identical_to_one_gpu" in out:
+            out["e2e"]["host_frame_identical_to_one_gpu"] = out.pop("e2e_frame_identical_to_one_gpu")
     return out
 
 
