@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -32,6 +34,8 @@ struct Worker
 	std::condition_variable cv;
 	std::function<void()> job;
 	bool has_job = false, quit = false;
+	int taken = 0;				// value of `posted` when the worker last took a job
+	std::atomic<int> posted{0}; // bumped with every job: workers spin on it briefly before they sleep (frames are ~0.2 ms apart)
 };
 
 struct skr_mgpu
@@ -82,6 +86,11 @@ void worker_main(skr_mgpu *m, int i)
 	{
 		std::function<void()> job;
 		{
+			// spin for up to ~200 us (a condition-variable wake-up costs 20-50 us, a fifth of a frame), then sleep
+			const auto t0 = std::chrono::steady_clock::now();
+			while(w->posted.load(std::memory_order_acquire) == w->taken && std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200))
+			{
+			}
 			std::unique_lock<std::mutex> lk(w->m);
 			w->cv.wait(lk, [w] { return w->has_job || w->quit; });
 			if(w->quit)
@@ -90,6 +99,7 @@ void worker_main(skr_mgpu *m, int i)
 			}
 			job		   = std::move(w->job);
 			w->has_job = false;
+			w->taken   = w->posted.load(std::memory_order_acquire);
 		}
 		job();
 		{
@@ -114,7 +124,20 @@ void on_all(skr_mgpu *m, const std::function<void(int)> &f)
 			w->job	   = [&f, i] { f(i); };
 			w->has_job = true;
 		}
+		w->posted.fetch_add(1, std::memory_order_release);
 		w->cv.notify_one();
+	}
+	// the caller spins briefly too, then sleeps
+	{
+		const auto t0 = std::chrono::steady_clock::now();
+		while(std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(300))
+		{
+			std::lock_guard<std::mutex> lk(m->done_m);
+			if(m->pending == 0)
+			{
+				return;
+			}
+		}
 	}
 	std::unique_lock<std::mutex> lk(m->done_m);
 	m->done_cv.wait(lk, [m] { return m->pending == 0; });
@@ -206,6 +229,7 @@ int render_bands(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stats *
 	std::vector<skr_stats> st(W);
 	const bool want_stats = stats != nullptr;
 	std::vector<void *> frames(m->d_band.begin(), m->d_band.end());
+	std::atomic<int> arrived{0}, failed{0};
 	on_all(m, [&](int i) {
 		skr_options oi = *opt;
 		oi.world	   = W;
@@ -219,17 +243,19 @@ int render_bands(skr_mgpu *m, const skr_options *opt, uint8_t *rgb8, skr_stats *
 		if(rc[i])
 		{
 			msg[i] = skr_last_error(m->ctx[i]);
+			failed.fetch_add(1);
 		}
-	});
-	for(int i = 0; i < W; i++)
-	{
-		if(rc[i])
+		// every GPU's kernel must be done before any band is copied out: the driver threads meet here (they all run: one per
+		// GPU, all posted by on_all above)
+		arrived.fetch_add(1, std::memory_order_acq_rel);
+		while(arrived.load(std::memory_order_acquire) < W)
 		{
-			return fail(m, rc[i], "GPU %d: %s", i, msg[i].c_str());
+			std::this_thread::yield();
 		}
-	}
-	// every kernel is done: each GPU copies its band out
-	on_all(m, [&](int i) {
+		if(failed.load() != 0)
+		{
+			return;
+		}
 		const size_t y0 = std::min((size_t) opt->height, (size_t) i * rows), y1 = std::min((size_t) opt->height, (size_t) (i + 1) * rows);
 		if(y1 > y0)
 		{

@@ -267,7 +267,7 @@ void launch_primary(skr_ctx *ctx, const FrameParams &fp, const Queue &q, long lo
 		}
 	}
 	const long long wpc		= threads / 32;
-	const unsigned blocks = (unsigned) (((n + 31) / 32 + wpc - 1) / wpc);
+	const unsigned blocks = (unsigned) (((n + 31) / 32 * ((!GI && fp.split) ? 2 : 1) + wpc - 1) / wpc);
 	if(!sv.blob_in_smem)
 	{
 		primary_kernel<GI, STATS, false, true, true><<<blocks, threads, 0, st>>>(sv, fp, q, lp0, n);
@@ -1095,6 +1095,13 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 		const char *no	  = getenv("SKR_NO_STRIP_WORDS");
 		pl.fp.strip_words = (ok && !(no && no[0] == '1')) ? 1 : 0;
 	}
+	{
+		// sample split (primary_kernel): frames whose blocks would fill the GPU's warp slots fewer than three times over --
+		// one rank's share of a frame at world >= 4 -- and that have samples to split
+		const char *no	   = getenv("SKR_NO_SPLIT"), *yes = getenv("SKR_SPLIT");
+		const long long nb = pl.npix_local / 32, slots = (long long) ctx->sm_count * SKR_MIN_BLOCKS * (SKR_BLOCK / 32);
+		pl.fp.split = (!tree && !pl.shaded && pl.fp.spp >= 8 && ((nb < 3 * slots && !(no && no[0] == '1')) || (yes && yes[0] == '1'))) ? 1 : 0;
+	}
 	if(!tree && !pl.shaded)
 	{
 		const int rc_order = tile_launch_order(ctx, pl, pl.rows_per_band, pl.fp);
@@ -1620,7 +1627,12 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	}
 	sv.tri_mat	= ctx->have_tri_mat ? ctx->d_tri_mat : nullptr;
 	sv.tris_raw = T > 0 ? ctx->d_tris_raw : nullptr;
-	CK(cudaStreamSynchronize(ctx->stream));
+	if(T > 0)
+	{
+		CK(cudaStreamSynchronize(ctx->stream)); // the count of outsized triangles comes back from the build
+	}
+	// (sphere scenes: nothing to wait for -- the blob copy above is stream-ordered before every frame, and cudaMemcpyAsync
+	// from the pageable staging vector has consumed it before it returns)
 	sv.nbig			= (T > 0 && sv.bvh) ? std::min((int) *ctx->h_count, BIG_TRI_CAP) : 0;
 	ctx->have_scene = true;
 	ctx->scene_gen++;

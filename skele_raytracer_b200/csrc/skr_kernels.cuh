@@ -56,6 +56,7 @@ struct FrameParams
 	float angle, aspect, inv_w, inv_h;
 	int cull;		  // 1: bundle culling (cull_pairs) for this frame: jittered, >= 4 samples per pixel, <= 64 spheres
 	float cull_delta; // bound on |d(r) - d(0.5)| over the jitter draw r of a pixel (ray directions are un-normalised)
+	int split;		  // 1: the two halves of a pixel's samples are traced by two neighbouring warps (primary_kernel)
 	int strip_words;  // 1: whole 8 x 4 blocks leave as 32-bit words (width % 4 == 0, 4-byte aligned frames)
 	// Launch order of this rank's tiles (single-kernel frames): global tile index per local slot, tiles that can see a sphere
 	// FIRST, so that the tail of the kernel is made of cheap sky tiles (tiles_local entries; padding slots = tiles_total), or null
@@ -430,18 +431,30 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 	const float4 *B = stage_scene<SMEM>(sv, smem);
 	Counters cnt;
 	zero(cnt);
+	__shared__ float s_part[3][SKR_BLOCK]; // first-half sums (see below)
 	const unsigned lane	   = threadIdx.x & 31u;
 	const unsigned nblocks = (unsigned) ((npix + 31) / 32);
-	// the grid covers the frame: warp w of CTA b takes the 8 x 4 pixel block b * (warps per CTA) + w
-	const unsigned blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if(blk < nblocks)
-	{
-	const long long g  = (long long) blk * 32 + lane;
-	const long long lp = lp0 + g;
-	PixelId p		   = decode_pixel(fp, lp);
-	p.valid			   = p.valid && g < npix;
-
+	// The grid covers the frame: warp w of CTA b takes the 8 x 4 pixel block b * (warps per CTA) + w.
+	// A pixel's samples are summed as TWO halves, [0, h) and [h, n), added at the end -- by one warp, or (fp.split: frames
+	// with too few blocks to fill the GPU for long, i.e. one rank's share at world >= 4) by two neighbouring warps of the
+	// CTA that take one half each: twice the work items, half the length of the kernel's tail.  Same arithmetic either
+	// way, so the frame does not depend on the split (bit-identical for any world size, tested).
+	const unsigned nparts = (!GI && fp.split) ? 2u : 1u;
+	const unsigned wg	  = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const unsigned blk = wg / nparts, part = wg % nparts;
+	const bool in_range = blk < nblocks;
+	long long lp		= 0;
+	PixelId p;
+	p.x = p.y = 0;
+	p.valid	  = false;
 	float3 sum = f3(0.0f, 0.0f, 0.0f);
+	if(in_range)
+	{
+	const long long g = (long long) blk * 32 + lane;
+	lp				  = lp0 + g;
+	p				  = decode_pixel(fp, lp);
+	p.valid			  = p.valid && g < npix;
+
 	RngCtx rng;
 	rng.pixel = (uint32_t) (p.y * fp.width + p.x);
 	rng.node  = 0;
@@ -471,7 +484,21 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		}
 		pmask = __reduce_or_sync(0xffffffffu, p.valid ? mk : 0u);
 	}
-	for(int s = 0; s < nsamples; s++)
+	const int half = (nsamples + 1) >> 1;
+	for(int range = 0; range < 2; range++)
+	{
+	if(nparts == 2u && (unsigned) range != part)
+	{
+		continue;
+	}
+	const int s_begin = range == 0 ? 0 : half, s_end = range == 0 ? half : nsamples;
+	if(range == 1 && nparts == 1u)
+	{
+		// (one warp does both halves: park the first half's sum in shared memory instead of three more live registers)
+		s_part[0][threadIdx.x] = sum.x, s_part[1][threadIdx.x] = sum.y, s_part[2][threadIdx.x] = sum.z;
+		sum					   = f3(0.0f, 0.0f, 0.0f);
+	}
+	for(int s = s_begin; s < s_end; s++)
 	{
 		rng.sample = (uint32_t) s;
 		float u, v;
@@ -479,7 +506,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		{
 			// src/main.cpp:52-54: ONE draw for both axes, all-float arithmetic.  Four consecutive samples
 			// share one Philox block.
-			if((s & 3) == 0)
+			if((s & 3) == 0 || s == s_begin)
 			{
 				jit = philox4x32_10(make_uint4(rng.pixel, (uint32_t) s >> 2, 0u, 0u), rng.key);
 			}
@@ -552,7 +579,27 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			queue_push(q0, h >= 0, o, rng.pixel, f3(1.0f, 1.0f, 1.0f), 0u, (uint32_t) s, h, d, t, fp.err);
 		}
 	}
-
+	} // the two halves
+	} // in_range
+	// first half + second half
+	if(nparts == 2u)
+	{
+		if(in_range && part == 1u)
+		{
+			s_part[0][threadIdx.x - 32] = sum.x, s_part[1][threadIdx.x - 32] = sum.y, s_part[2][threadIdx.x - 32] = sum.z; // the partner warp's slots
+		}
+		__syncthreads();
+		if(in_range && part == 0u)
+		{
+			sum = f3(__fadd_rn(sum.x, s_part[0][threadIdx.x]), __fadd_rn(sum.y, s_part[1][threadIdx.x]), __fadd_rn(sum.z, s_part[2][threadIdx.x]));
+		}
+	}
+	else if(in_range)
+	{
+		sum = f3(__fadd_rn(s_part[0][threadIdx.x], sum.x), __fadd_rn(s_part[1][threadIdx.x], sum.y), __fadd_rn(s_part[2][threadIdx.x], sum.z));
+	}
+	if(in_range && part == 0u)
+	{
 	if(GI)
 	{
 		if(p.valid)

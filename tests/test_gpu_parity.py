@@ -800,3 +800,25 @@ def test_render_bands_device_sends_each_row_band_to_its_owner(gpu, gscenes):
         gpu.render_bands_device(S.Options(rank=r, world=2, **kw), [f.data_ptr() for f in frames], 28)
     gpu.sync()
     assert np.array_equal(frames[0].cpu().numpy()[:28], full8[:28]) and np.array_equal(frames[1].cpu().numpy()[28:], full8[28:])
+
+
+@pytest.mark.parametrize("scene,kw", [("spheres2", dict(width=640, height=360, grid_size=5, use_shadows=True, seed=5)),      # config 2 shape: 25 samples
+                                      ("bear", dict(width=333, height=187, grid_size=3, use_shadows=True, seed=6)),           # 9 samples: halves of 5 and 4
+                                      ("test", dict(width=200, height=120, grid_size=3, seed=7, rank=2, world=4, tile=16))])  # triangles, a rank's share
+def test_sample_split_over_two_warps_does_not_change_the_frame(gpu, gscenes, scene, kw):
+    """primary_kernel sums a pixel's samples as two halves; small launches (one rank's share at world >= 4) give the halves
+    to two neighbouring warps.  Forced on and off (SKR_SPLIT / SKR_NO_SPLIT) the frame must not change by a bit."""
+    gpu.upload(gscenes[scene])
+    o = S.Options(collect_stats=True, **kw)
+    os.environ["SKR_SPLIT"] = "1"
+    try:
+        a32, a8, sa = gpu.render(o)
+    finally:
+        del os.environ["SKR_SPLIT"]
+    os.environ["SKR_NO_SPLIT"] = "1"
+    try:
+        b32, b8, sb = gpu.render(o)
+    finally:
+        del os.environ["SKR_NO_SPLIT"]
+    assert np.array_equal(a32.view(np.uint32), b32.view(np.uint32)) and np.array_equal(a8, b8)
+    assert sa.closest_hit_rays == sb.closest_hit_rays and sa.shadow_rays == sb.shadow_rays and sa.sphere_tests == sb.sphere_tests
