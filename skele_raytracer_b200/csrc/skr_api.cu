@@ -268,27 +268,29 @@ void launch_primary(skr_ctx *ctx, const FrameParams &fp, const Queue &q, long lo
 	}
 	const long long wpc		= threads / 32;
 	const unsigned blocks = (unsigned) (((n + 31) / 32 * ((!GI && fp.split) ? 2 : 1) + wpc - 1) / wpc);
+	const bool halves = !GI && fp.spp >= 8; // two-half sample sums (and the split over two warps): frames with samples to split
+	const auto go = [&](auto kernel, size_t bytes) { kernel<<<blocks, threads, bytes, st>>>(sv, fp, q, lp0, n); };
 	if(!sv.blob_in_smem)
 	{
-		primary_kernel<GI, STATS, false, true, true><<<blocks, threads, 0, st>>>(sv, fp, q, lp0, n);
+		halves ? go(primary_kernel<GI, STATS, false, true, true, !GI>, 0) : go(primary_kernel<GI, STATS, false, true, true, false>, 0);
 		return;
 	}
 	const bool tris = sv.T > 0, fog = sv.F > 0;
 	if(tris && fog)
 	{
-		primary_kernel<GI, STATS, true, true, true><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n);
+		halves ? go(primary_kernel<GI, STATS, true, true, true, !GI>, sm) : go(primary_kernel<GI, STATS, true, true, true, false>, sm);
 	}
 	else if(tris)
 	{
-		primary_kernel<GI, STATS, true, true, false><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n);
+		halves ? go(primary_kernel<GI, STATS, true, true, false, !GI>, sm) : go(primary_kernel<GI, STATS, true, true, false, false>, sm);
 	}
 	else if(fog)
 	{
-		primary_kernel<GI, STATS, true, false, true><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n);
+		halves ? go(primary_kernel<GI, STATS, true, false, true, !GI>, sm) : go(primary_kernel<GI, STATS, true, false, true, false>, sm);
 	}
 	else
 	{
-		primary_kernel<GI, STATS, true, false, false><<<blocks, threads, sm, st>>>(sv, fp, q, lp0, n);
+		halves ? go(primary_kernel<GI, STATS, true, false, false, !GI>, sm) : go(primary_kernel<GI, STATS, true, false, false, false>, sm);
 	}
 }
 
@@ -341,7 +343,11 @@ void launch_shade_expand(skr_ctx *ctx, unsigned blocks, const FrameParams &fp, c
 template <bool GI, bool STATS, bool TRIS, bool FOG>
 cudaError_t smem_attr_one(int bytes)
 {
-	cudaError_t e = cudaFuncSetAttribute(primary_kernel<GI, STATS, true, TRIS, FOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	cudaError_t e = cudaFuncSetAttribute(primary_kernel<GI, STATS, true, TRIS, FOG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if(e == cudaSuccess && !GI)
+	{
+		e = cudaFuncSetAttribute(primary_kernel<GI, STATS, true, TRIS, FOG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	}
 	if(e == cudaSuccess && GI)
 	{
 		e = cudaFuncSetAttribute(shade_expand_kernel<STATS, true, TRIS, FOG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -552,9 +558,15 @@ void frame_kernels(const skr_ctx *ctx, bool tree, bool leaf, bool fresnel, std::
 	 tris			   ? (const void *) K<__VA_ARGS__, true, true, false SKR_TAIL> :                                           \
 	 fog			   ? (const void *) K<__VA_ARGS__, true, false, true SKR_TAIL> :                                           \
 						 (const void *) K<__VA_ARGS__, true, false, false SKR_TAIL>)
-#define SKR_TAIL
+#define SKR_TAIL , false
 	out.push_back(tree ? SKR_PICK(primary_kernel, true, STATS) : SKR_PICK(primary_kernel, false, STATS));
 #undef SKR_TAIL
+	if(!tree)
+	{
+#define SKR_TAIL , true
+		out.push_back(SKR_PICK(primary_kernel, false, STATS));
+#undef SKR_TAIL
+	}
 	if(tree)
 	{
 #define SKR_TAIL , false
@@ -1096,11 +1108,13 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 		pl.fp.strip_words = (ok && !(no && no[0] == '1')) ? 1 : 0;
 	}
 	{
-		// sample split (primary_kernel): frames whose blocks would fill the GPU's warp slots fewer than three times over --
-		// one rank's share of a frame at world >= 4 -- and that have samples to split
+		// sample split (primary_kernel): frames whose blocks would fill the GPU's warp slots fewer than nine times over -- one
+		// rank's share of a 1080p frame at world >= 2 -- and that have samples to split.  Measured (config 2, one rank's share,
+		// split / no split): world 2 0.537 / 0.541 ms, world 4 0.279 / 0.285, world 8 0.156 / 0.176; whole frame 1.049 / 0.992
 		const char *no	   = getenv("SKR_NO_SPLIT"), *yes = getenv("SKR_SPLIT");
 		const long long nb = pl.npix_local / 32, slots = (long long) ctx->sm_count * SKR_MIN_BLOCKS * (SKR_BLOCK / 32);
-		pl.fp.split = (!tree && !pl.shaded && pl.fp.spp >= 8 && ((nb < 3 * slots && !(no && no[0] == '1')) || (yes && yes[0] == '1'))) ? 1 : 0;
+		// (spp >= 8: the frames launch_primary gives the HALVES variant)
+		pl.fp.split = (!tree && !pl.shaded && pl.fp.spp >= 8 && ((nb < 9 * slots && !(no && no[0] == '1')) || (yes && yes[0] == '1'))) ? 1 : 0;
 	}
 	if(!tree && !pl.shaded)
 	{

@@ -11,7 +11,9 @@
 // Node layout (built by skr_bvh_build.cuh), 4 x float4 = 64 B per internal node, both child boxes in the parent,
 // interleaved Left/Right so that the slab arithmetic of the two boxes runs as packed FP32x2 (FADD2/FMUL2):
 //   n0 = (Lmin.x, Rmin.x, Lmin.y, Rmin.y)  n1 = (Lmin.z, Rmin.z, Lmax.x, Rmax.x)
-//   n2 = (Lmax.y, Rmax.y, Lmax.z, Rmax.z)  n3 = (bits(left), bits(right), -, -)
+//   n2 = (Lmax.y, Rmax.y, Lmax.z, Rmax.z)  n3 = (bits(left), bits(right), gL, gR)
+// gL / gR: the largest dead-triangle bound under the child (skr_bvh_build.cuh: tri_bounds_kernel): a ray with
+// |dir| * g < 1e-5 cannot pass the reference's fabs(det) >= 1e-5 test on any triangle there, so the child is skipped.
 // child index >= 0: internal node; < 0: leaf ~idx, whose triangle is tri_v[4*idx .. 4*idx+2] (leaf order, 64 B each).
 #pragma once
 
@@ -80,6 +82,7 @@ struct TriWalk
 {
 	float3 o, d, inv;
 	float tmax;
+	float dlen; // |d| rounded up: the child's dead-triangle bound g is tested against 1e-5 / dlen
 	int node, sp, base; // stack entries [base, sp) are pending (base > 0 once entries have been given away, tri_deferred_kernel)
 };
 SKR_DEV void tri_walk_begin(TriWalk &w, float3 o, float3 d, float tmax)
@@ -88,6 +91,7 @@ SKR_DEV void tri_walk_begin(TriWalk &w, float3 o, float3 d, float tmax)
 	w.d	   = d;
 	w.inv  = f3(__fdiv_rn(1.0f, d.x), __fdiv_rn(1.0f, d.y), __fdiv_rn(1.0f, d.z));
 	w.tmax = tmax;
+	w.dlen = sqrtf(dot(d, d)) * 1.00001f;
 	w.node = 0;
 	w.sp   = 0;
 	w.base = 0;
@@ -105,6 +109,8 @@ SKR_DEV int tri_walk_step(const SceneView &sv, TriWalk &w, int *stack, Counters 
 	}
 	bool hl, hr;
 	line_hits_boxes(w.o, w.inv, w.tmax, n0, n1, n2, hl, hr);
+	hl = hl && n3.z * w.dlen >= 0.99999e-5f; // dead subtrees: no triangle there can reach fabs(det) >= 1e-5 for this ray
+	hr = hr && n3.w * w.dlen >= 0.99999e-5f;
 	const int cl = (int) f2u(n3.x), cr = (int) f2u(n3.y);
 	int next = -1; // next internal node to visit, if any
 	if(hl)

@@ -79,8 +79,18 @@ __global__ void tri_bounds_kernel(const float *__restrict__ tris, int T, float4 
 		const float pad	 = 1.0e-3f * diag + 4.0e-6f * mag + 1.0e-30f;
 		lo				 = f3(lo.x - pad, lo.y - pad, lo.z - pad);
 		hi				 = f3(hi.x + pad, hi.y + pad, hi.z + pad);
-		box_lo[i]		 = make_float4(lo.x, lo.y, lo.z, 0.0f);
-		box_hi[i]		 = make_float4(hi.x, hi.y, hi.z, 0.0f);
+		// DEAD-TRIANGLE BOUND.  The reference rejects a triangle when fabs(det) < 1e-5 (src/utils.h:190), det = e1 . (dir x e2)
+		// = -dir . (e1 x e2): whatever the ray, |det| <= |dir| * |e1 x e2|, and the float evaluation (uncontracted cross and
+		// dot, tri_test_ref) adds at most ~11 eps |dir| |e1| |e2|.  With g = |e1 x e2| + 1e-6 |e1| |e2| (rounded up), a ray
+		// with |dir| * g < 1e-5 cannot pass the test: traversal skips the triangle -- and every subtree whose largest g fails
+		// (refit_kernel keeps the maximum per child).  dragon.scn's triangles are ~2 mm across (|e1 x e2| ~ 4e-6): for the
+		// shorter camera rays most of the model can never be hit, which is exactly why the reference's render of it is sparse.
+		const double e1x = (double) v1.x - v0.x, e1y = (double) v1.y - v0.y, e1z = (double) v1.z - v0.z;
+		const double e2x = (double) v2.x - v0.x, e2y = (double) v2.y - v0.y, e2z = (double) v2.z - v0.z;
+		const double nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+		const double g	= sqrt(nx * nx + ny * ny + nz * nz) + 1.0e-6 * sqrt((e1x * e1x + e1y * e1y + e1z * e1z) * (e2x * e2x + e2y * e2y + e2z * e2z));
+		box_lo[i]		= make_float4(lo.x, lo.y, lo.z, __double2float_ru(g * 1.000001));
+		box_hi[i]		= make_float4(hi.x, hi.y, hi.z, 0.0f);
 	}
 	// block reduction of the scene box through shared memory, one atomic per block per component
 	__shared__ float red[6][32];
@@ -161,7 +171,7 @@ __global__ void morton_kernel(float4 *box_lo, float4 *box_hi, const float *__res
 				big_v[3 * slot + 0] = make_float4(t[0], t[1], t[2], __int_as_float(i)); // w: original triangle index
 				big_v[3 * slot + 1] = make_float4(t[3], t[4], t[5], 0.0f);
 				big_v[3 * slot + 2] = make_float4(t[6], t[7], t[8], 0.0f);
-				box_lo[i] = box_hi[i] = make_float4(cx, cy, cz, 0.0f);
+				box_lo[i] = box_hi[i] = make_float4(cx, cy, cz, 0.0f); // (w = 0: its leaf in the tree is never worth a test -- the big list has it)
 			}
 		}
 	}
@@ -432,8 +442,9 @@ __global__ void refit_kernel(int n, const unsigned *__restrict__ sorted_ids, con
 		nodes[4 * node + 0] = make_float4(llo.x, rlo.x, llo.y, rlo.y);
 		nodes[4 * node + 1] = make_float4(llo.z, rlo.z, lhi.x, rhi.x);
 		nodes[4 * node + 2] = make_float4(lhi.y, rhi.y, lhi.z, rhi.z);
-		nodes[4 * node + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), 0.0f, 0.0f);
-		__stcg(node_lo + node, make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f));
+		// (.z, .w: the largest dead-triangle bound g under the left / right child, see tri_bounds_kernel)
+		nodes[4 * node + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), llo.w, rlo.w);
+		__stcg(node_lo + node, make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), fmaxf(llo.w, rlo.w)));
 		__stcg(node_hi + node, make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f));
 		node = parent[node];
 	}

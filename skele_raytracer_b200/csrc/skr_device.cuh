@@ -397,7 +397,6 @@ SKR_DEV uint32_t cull_pairs(const float4 *__restrict__ C, int NP, int S, float3 
 
 // closest_sphere_table<ORIGIN_TABLE = true, COHERENT = true> over the pairs of `mask` only (ascending, so the first
 // sphere still wins ties).  `mask` is uniform across the warp: no divergence, broadcast shared-memory reads.
-// EXACT_T: tmin by IEEE division (it bounds the triangle query); otherwise tmin is only sphere_t_ref's fallback.
 template <bool STATS, bool EXACT_T>
 SKR_DEV int closest_sphere_masked(const float4 *__restrict__ G, uint32_t mask, int S, float3 d, float &tmin, Counters &cnt)
 {
@@ -441,7 +440,9 @@ SKR_DEV int closest_sphere_masked(const float4 *__restrict__ G, uint32_t mask, i
 			}
 		}
 	}
-	tmin = best >= 0 ? (EXACT_T ? __fdiv_rn(umin, a) : __fdividef(umin, a)) : CUDART_INF_F;
+	// (IEEE division like closest_sphere_table: tmin is sphere_t_ref's fallback for grazing hits, and the frame must not depend
+	// on which of the two loops found the sphere -- one pixel in 130 000 differed by an ulp between culling on and off)
+	tmin = best >= 0 ? __fdiv_rn(umin, a) : CUDART_INF_F;
 	return best;
 }
 

@@ -423,7 +423,8 @@ SKR_DEV float3 queue_hit_point(const float4 *__restrict__ B, const SceneView &sv
 // config 1 0.062 against 0.057 -- the 64 800 fetches of a 1080p frame serialise on one L2 address.  DESIGN.md.)
 // Finished pixels bound for another device or for page-locked host memory (skr_render_peers_device) are quantised into
 // shared memory and leave as 32-bit words, 24 B per pixel row of the block, instead of 3 byte stores each.
-template <bool GI, bool STATS, bool SMEM, bool TRIS, bool FOG>
+// HALVES: frames with >= 8 samples per pixel (see below); single-sample frames run the lean single-loop variant.
+template <bool GI, bool STATS, bool SMEM, bool TRIS, bool FOG, bool HALVES>
 __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(const SceneView sv, const FrameParams fp, const Queue q0, long long lp0, long long npix)
 {
 	extern __shared__ float4 smem[];
@@ -431,15 +432,15 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 	const float4 *B = stage_scene<SMEM>(sv, smem);
 	Counters cnt;
 	zero(cnt);
-	__shared__ float s_part[3][SKR_BLOCK]; // first-half sums (see below)
+	__shared__ float s_part[HALVES ? 3 : 1][HALVES ? SKR_BLOCK : 1]; // first-half sums (see below)
 	const unsigned lane	   = threadIdx.x & 31u;
 	const unsigned nblocks = (unsigned) ((npix + 31) / 32);
 	// The grid covers the frame: warp w of CTA b takes the 8 x 4 pixel block b * (warps per CTA) + w.
-	// A pixel's samples are summed as TWO halves, [0, h) and [h, n), added at the end -- by one warp, or (fp.split: frames
+	// HALVES: a pixel's samples are summed as TWO halves, [0, h) and [h, n), added at the end -- by one warp, or (fp.split: frames
 	// with too few blocks to fill the GPU for long, i.e. one rank's share at world >= 4) by two neighbouring warps of the
 	// CTA that take one half each: twice the work items, half the length of the kernel's tail.  Same arithmetic either
 	// way, so the frame does not depend on the split (bit-identical for any world size, tested).
-	const unsigned nparts = (!GI && fp.split) ? 2u : 1u;
+	const unsigned nparts = (HALVES && !GI && fp.split) ? 2u : 1u;
 	const unsigned wg	  = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	const unsigned blk = wg / nparts, part = wg % nparts;
 	const bool in_range = blk < nblocks;
@@ -484,15 +485,16 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		}
 		pmask = __reduce_or_sync(0xffffffffu, p.valid ? mk : 0u);
 	}
-	const int half = (nsamples + 1) >> 1;
-	for(int range = 0; range < 2; range++)
+	const int half = HALVES ? (nsamples + 1) >> 1 : nsamples;
+#pragma unroll 1
+	for(int range = 0; range < (HALVES ? 2 : 1); range++)
 	{
-	if(nparts == 2u && (unsigned) range != part)
+	if(HALVES && nparts == 2u && (unsigned) range != part)
 	{
 		continue;
 	}
 	const int s_begin = range == 0 ? 0 : half, s_end = range == 0 ? half : nsamples;
-	if(range == 1 && nparts == 1u)
+	if(HALVES && range == 1 && nparts == 1u)
 	{
 		// (one warp does both halves: park the first half's sum in shared memory instead of three more live registers)
 		s_part[0][threadIdx.x] = sum.x, s_part[1][threadIdx.x] = sum.y, s_part[2][threadIdx.x] = sum.z;
@@ -582,7 +584,10 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 	} // the two halves
 	} // in_range
 	// first half + second half
-	if(nparts == 2u)
+	if(!HALVES)
+	{
+	}
+	else if(nparts == 2u)
 	{
 		if(in_range && part == 1u)
 		{
@@ -1125,7 +1130,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 	uint2 px			 = make_uint2(0u, 0u);
 	TriWalk wk;
 	wk.o = wk.d = wk.inv = f3(0.0f, 0.0f, 0.0f);
-	wk.tmax = 0.0f;
+	wk.tmax = wk.dlen = 0.0f;
 	wk.node = wk.sp = wk.base = 0;
 	int stack[SKR_BVH_STACK];
 	for(;;)
@@ -1185,12 +1190,13 @@ __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneV
 				const float ox = __shfl_sync(0xffffffffu, wk.o.x, src), oy = __shfl_sync(0xffffffffu, wk.o.y, src), oz = __shfl_sync(0xffffffffu, wk.o.z, src);
 				const float dx = __shfl_sync(0xffffffffu, wk.d.x, src), dy = __shfl_sync(0xffffffffu, wk.d.y, src), dz = __shfl_sync(0xffffffffu, wk.d.z, src);
 				const float ix = __shfl_sync(0xffffffffu, wk.inv.x, src), iy = __shfl_sync(0xffffffffu, wk.inv.y, src), iz = __shfl_sync(0xffffffffu, wk.inv.z, src);
-				const float tm = __shfl_sync(0xffffffffu, wk.tmax, src);
+				const float tm = __shfl_sync(0xffffffffu, wk.tmax, src), dl = __shfl_sync(0xffffffffu, wk.dlen, src);
 				const unsigned pxx = __shfl_sync(0xffffffffu, px.x, src), pxy = __shfl_sync(0xffffffffu, px.y, src);
 				if(thief)
 				{
 					wk.o = f3(ox, oy, oz), wk.d = f3(dx, dy, dz), wk.inv = f3(ix, iy, iz);
 					wk.tmax = tm;
+					wk.dlen = dl;
 					wk.node = node;
 					wk.sp = wk.base = 0;
 					px	   = make_uint2(pxx, pxy);

@@ -52,6 +52,53 @@ def test_committed_bench_lines_keep_the_contract(name, n):
         assert d["cpu_baseline"] is None                    # timed on rank 0 at N = 1 only
 
 
+R02 = [("r02_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n4.json", 4), ("r02_bench_n8.json", 8)]
+
+
+@pytest.mark.parametrize("name,n", R02)
+def test_round2_bench_lines_carry_every_config(name, n):
+    """Round 2: the line holds all five BASELINE configs at every N, each with its own device time, e2e, roofline (frac =
+    EXECUTED arithmetic; the reference algorithm's count is a separate sub-object) and -- at N = 1 -- the CPU baseline of the
+    reference's own code in both builds."""
+    if not os.path.exists(os.path.join(PROFILES, name)):
+        pytest.skip(f"{name} not committed yet")
+    d = load(name)
+    assert LINE_KEYS | {"configs", "build", "peaks_measured_live"} <= set(d), (LINE_KEYS | {"configs"}) - set(d)
+    assert d["metric"] == "Mrays/s" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True and d["n_gpus"] == n
+    assert d["warmup"] >= 3 and d["scaling"] == "strong" and d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert d["value"] == pytest.approx(d["config"]["rays_per_frame"] / (d["ms_per_step"] * 1e-3) / 1e6, rel=1e-6)
+    c = d["clocks"]
+    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert 0 < d["e2e"]["value"] < d["value"] and d["e2e"]["d2h_bytes_per_step"] == 1920 * 1080 * 3 and d["e2e"]["h2d_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "fp32" and r["frac"] == pytest.approx(r["achieved"] / r["peak"]) and 0 < r["frac"] < r["algorithmic"]["frac"] < 1
+    assert set(d["configs"]) == {"c1", "c2", "c3", "c4", "c5"}
+    for k, cfg in d["configs"].items():
+        assert cfg["ms_per_frame"] > 0 and cfg["mrays_per_s"] > 0 and cfg["first_frame_ms"] > 0, k
+        assert cfg["mrays_per_s"] == pytest.approx(cfg["rays_per_frame"] / (cfg["ms_per_frame"] * 1e-3) / 1e6, rel=1e-6), k
+        e = cfg["e2e"]
+        assert 0 < e["value"] < cfg["mrays_per_s"] and e["d2h_bytes_per_step"] > 0 and e["h2d_bytes_per_step"] > 0, k
+        rf = cfg["roofline"]
+        assert rf["bound"] == ("l1" if k == "c4" else "fp32") and 0 < rf["frac"] < 1 and rf["peak"] > 0, k
+        if n == 1:
+            b = cfg["cpu_baseline"]
+            assert b["kind"] in ("reference", "port") and b["cores"] >= 1 and b["value"] > 0 and b["sample"], k
+            assert b["reference_flags_build"]["value"] > 0 and "no -O" in b["reference_flags_build"]["flags"], k
+            assert cfg["mrays_per_s"] > 100 * b["value"], k           # (a sanity bound, not a target)
+        else:
+            assert cfg["cpu_baseline"] is None and e.get("host_frame_identical_to_one_gpu") is True, k
+            assert cfg["e2e_native"]["value"] > 0, k
+    assert d["configs"]["c2"]["ms_per_frame"] == pytest.approx(d["ms_per_step"])
+
+
+def test_round2_config5_scales_over_the_gpus():
+    names = [n for n, _ in R02 if os.path.exists(os.path.join(PROFILES, n))]
+    if len(names) < 4:
+        pytest.skip("round-2 lines not all committed yet")
+    ms = [load(n)["configs"]["c5"]["ms_per_frame"] for n in names]
+    assert ms[0] > ms[1] > ms[2] > ms[3] and ms[0] / ms[3] > 6.0     # bear 4K --gillum 64: >= 0.75 efficiency on eight GPUs
+
+
 def test_strong_scaling_is_monotonic_in_the_committed_lines():
     ms = [load(f"r01_bench_n{n}.json")["ms_per_step"] for n in (1, 2, 4, 8)]
     assert ms[0] > ms[1] > ms[2] > ms[3]
