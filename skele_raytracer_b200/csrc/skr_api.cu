@@ -677,11 +677,11 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	pl.npix_local  = pl.tiles_local * tile * tile;
 	pl.levels	   = ((fp.gi || fp.fresnel) && fp.max_depth > 0) ? fp.max_depth : 0;
 	{
-		// deferred triangle query (tri_deferred_kernel): single-sample frames without a wavefront tree, over a real hierarchy.
-		// OFF by default -- measured on B200 (config 4): 0.40 ms against 0.30 ms for the walk in place; SKR_DEFER=1 enables it.
-		const char *yes = getenv("SKR_DEFER");
-		pl.defer		= !pl.shaded && !fp.gi && !fp.fresnel && fp.spp == 1 && fp.max_depth > 0 && ctx->sv.bvh != nullptr && !ctx->sv.bvh_root_is_leaf &&
-				   pl.npix_local <= 0xffffffffLL && (yes && yes[0] == '1');
+		// deferred triangle query (tri_deferred_kernel: teams of lanes per heavy ray): single-sample frames without a wavefront
+		// tree, over a real hierarchy.  Config 4: 0.228 ms against 0.279 for the walk in place (SKR_NO_DEFER=1); same frame.
+		const char *no = getenv("SKR_NO_DEFER");
+		pl.defer	   = !pl.shaded && !fp.gi && !fp.fresnel && fp.spp == 1 && fp.max_depth > 0 && ctx->sv.bvh != nullptr && !ctx->sv.bvh_root_is_leaf &&
+				   pl.npix_local <= 0xffffffffLL && !(no && no[0] == '1');
 	}
 	{
 		// leaves in place: plain --gillum trees (the fresnel pass pushes its own leaf children through the queue)
@@ -1108,13 +1108,13 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 		pl.fp.strip_words = (ok && !(no && no[0] == '1')) ? 1 : 0;
 	}
 	{
-		// sample split (primary_kernel): frames whose blocks would fill the GPU's warp slots fewer than nine times over -- one
-		// rank's share of a 1080p frame at world >= 2 -- and that have samples to split.  Measured (config 2, one rank's share,
+		// sample split (primary_kernel): frames whose blocks would fill the GPU's warp slots fewer than five times over -- one
+		// rank's share of a 1080p frame at world >= 4 -- and that have samples to split.  Measured (config 2, one rank's share,
 		// split / no split): world 2 0.537 / 0.541 ms, world 4 0.279 / 0.285, world 8 0.156 / 0.176; whole frame 1.049 / 0.992
 		const char *no	   = getenv("SKR_NO_SPLIT"), *yes = getenv("SKR_SPLIT");
 		const long long nb = pl.npix_local / 32, slots = (long long) ctx->sm_count * SKR_MIN_BLOCKS * (SKR_BLOCK / 32);
 		// (spp >= 8: the frames launch_primary gives the HALVES variant)
-		pl.fp.split = (!tree && !pl.shaded && pl.fp.spp >= 8 && ((nb < 9 * slots && !(no && no[0] == '1')) || (yes && yes[0] == '1'))) ? 1 : 0;
+		pl.fp.split = (!tree && !pl.shaded && pl.fp.spp >= 8 && ((nb < 5 * slots && !(no && no[0] == '1')) || (yes && yes[0] == '1'))) ? 1 : 0;
 	}
 	if(!tree && !pl.shaded)
 	{

@@ -83,7 +83,7 @@ struct TriWalk
 	float3 o, d, inv;
 	float tmax;
 	float dlen; // |d| rounded up: the child's dead-triangle bound g is tested against 1e-5 / dlen
-	int node, sp, base; // stack entries [base, sp) are pending (base > 0 once entries have been given away, tri_deferred_kernel)
+	int node, sp;
 };
 SKR_DEV void tri_walk_begin(TriWalk &w, float3 o, float3 d, float tmax)
 {
@@ -94,7 +94,6 @@ SKR_DEV void tri_walk_begin(TriWalk &w, float3 o, float3 d, float tmax)
 	w.dlen = sqrtf(dot(d, d)) * 1.00001f;
 	w.node = 0;
 	w.sp   = 0;
-	w.base = 0;
 }
 // one node visit.  Returns 1: a triangle was hit (query over), 0: no node left (query over, no hit), -1: keep going.
 template <bool STATS>
@@ -151,7 +150,7 @@ SKR_DEV int tri_walk_step(const SceneView &sv, TriWalk &w, int *stack, Counters 
 	}
 	if(next < 0)
 	{
-		if(w.sp == w.base)
+		if(w.sp == 0)
 		{
 			return 0;
 		}
@@ -159,6 +158,55 @@ SKR_DEV int tri_walk_step(const SceneView &sv, TriWalk &w, int *stack, Counters 
 	}
 	w.node = next;
 	return -1;
+}
+
+// One node for a TEAM walk (tri_deferred_kernel): tests both children of `node`; leaf children are tested at once (true =
+// a triangle was hit), internal children that the line reaches are returned in kid[0 .. nk).
+template <bool STATS>
+SKR_DEV bool tri_node_visit(const SceneView &sv, const TriWalk &w, int node, int (&kid)[2], int &nk, Counters &cnt)
+{
+	float4 n0, n1, n2, n3;
+	ldg256(sv.bvh + 4 * node, n0, n1);
+	ldg256(sv.bvh + 4 * node + 2, n2, n3);
+	if(STATS)
+	{
+		cnt.nv++;
+	}
+	bool hl, hr;
+	line_hits_boxes(w.o, w.inv, w.tmax, n0, n1, n2, hl, hr);
+	hl = hl && n3.z * w.dlen >= 0.99999e-5f;
+	hr = hr && n3.w * w.dlen >= 0.99999e-5f;
+	const int cl = (int) f2u(n3.x), cr = (int) f2u(n3.y);
+	nk = 0;
+	if(hl)
+	{
+		if(cl < 0)
+		{
+			if(tri_leaf_hit<STATS>(sv, ~cl, w.o, w.d, w.tmax, cnt))
+			{
+				return true;
+			}
+		}
+		else
+		{
+			kid[nk++] = cl;
+		}
+	}
+	if(hr)
+	{
+		if(cr < 0)
+		{
+			if(tri_leaf_hit<STATS>(sv, ~cr, w.o, w.d, w.tmax, cnt))
+			{
+				return true;
+			}
+		}
+		else
+		{
+			kid[nk++] = cr;
+		}
+	}
+	return false;
 }
 
 template <bool STATS>

@@ -1080,17 +1080,23 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 // ------------------------------------------------------------------------------------------------
 // tri_deferred_kernel: the triangle half of shade() (src/raytrace.h:169-186) for the CANDIDATES primary_kernel set aside.
 //
-// In a frame like dragon.scn's most camera rays are settled by two outsized triangles or within a few nodes (primary_kernel
-// walks up to SKR_DEFER_STEPS in place); the rest walk 20-40 nodes each.  Traced in place they leave most lanes and most warp slots idle
-// (round 1: 18.7 of 32 lanes, 22 % of the warp slots, 0.29 ms).  Here they are ONE dense work list and the kernel is
-// persistent: a wave of CTAs; each lane walks one line, one node per loop iteration.  Lanes whose query is over are
-// REFILLED from the list, 8 rays per fetch, and idle lanes beyond that take over part of a busy lane's walk (WORK
-// SPLITTING below): a warp never waits for its slowest ray, and the heavy rays -- neighbours in the image and in the list
-// -- end up spread over every warp of the grid.  A hit blackens the pixel primary_kernel wrote
-// (any accepted triangle shades black, src/raytrace.h:221-224); no hit leaves it.  Same arithmetic, same answer as the
-// in-place query (tested bit for bit).  OFF by default (SKR_DEFER=1): measured slower on config 4, see skr_api.cu make_plan.
+// What bounds a frame like dragon.scn's: 2.6 % of the camera rays -- lines that thread the model without an
+// accepted hit -- walk 100-640 nodes each, and walked one ray per lane the frame lasts as long as its heaviest warp's
+// serial chain (640 iterations x ~100 instructions x ~9 cycles).  primary_kernel therefore walks at most SKR_DEFER_STEPS
+// nodes in place (enough for the ~97 % of rays that only graze the model's bounds) and hands the rest over as ONE dense
+// list; here TEAMS of SKR_TEAM lanes walk one ray each from a shared stack in shared memory: every iteration the team pops
+// up to SKR_TEAM pending nodes, one per lane, tests their children (leaf triangles at once) and pushes the internal
+// children back (ballot + popc give each lane its slot).  A heavy ray's walk is SKR_TEAM times shorter; teams fetch
+// their next ray from the list as they finish (persistent CTAs, one warp-aggregated atomic per refill), so nothing waits
+// for the slowest ray but the end of the kernel.  Any accepted triangle blackens the pixel primary_kernel wrote
+// (src/raytrace.h:221-224); the walk order is irrelevant to an any-hit query: same frame as the walk in place, bit for bit.
 // ------------------------------------------------------------------------------------------------
-#define SKR_DEFER_REFILL 8
+#ifndef SKR_TEAM
+// measured on B200, config 4 (walk in place 0.279 ms): teams of 4 0.245 ms, of 8 0.230, of 16 0.263; one pool of (ray, node)
+// items per warp instead of team stacks (every lane pops any ray's node): 0.28-0.34
+#define SKR_TEAM 8
+#endif
+#define SKR_TEAM_STACK 128
 SKR_DEV void write_black(const FrameParams &fp, uint2 px) // the pixel of a candidate whose line hit a triangle
 {
 	const size_t at = 3 * (size_t) px.x;
@@ -1121,101 +1127,117 @@ SKR_DEV void write_black(const FrameParams &fp, uint2 px) // the pixel of a cand
 template <bool STATS>
 __global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneView sv, const FrameParams fp)
 {
+	constexpr int T		= SKR_TEAM;
+	constexpr int TEAMS = 32 / T;
+	__shared__ int s_stack[SKR_BLOCK / 32][TEAMS][SKR_TEAM_STACK];
 	Counters cnt;
 	zero(cnt);
 	const unsigned count = *reinterpret_cast<volatile unsigned *>(fp.cand_count);
 	const unsigned lane	 = threadIdx.x & 31u;
-	bool active			 = false;
-	bool more			 = true; // (uniform) the list may still hold rays
-	uint2 px			 = make_uint2(0u, 0u);
+	const unsigned team = lane / T, j = lane % T;
+	const unsigned team_mask = (T == 32 ? 0xffffffffu : ((1u << T) - 1u)) << (team * T); // this team's lanes
+	const unsigned team_lt	 = team_mask & ((1u << lane) - 1u);							  // ... below this one
+	int *stk = s_stack[threadIdx.x >> 5][team];
+	bool active = false; // (uniform within a team)
+	bool more	= true;	 // (uniform within the warp) the list may still hold rays
+	int sp		= 0;	 // (uniform within a team)
+	uint2 px	= make_uint2(0u, 0u);
 	TriWalk wk;
 	wk.o = wk.d = wk.inv = f3(0.0f, 0.0f, 0.0f);
 	wk.tmax = wk.dlen = 0.0f;
-	wk.node = wk.sp = wk.base = 0;
-	int stack[SKR_BVH_STACK];
+	wk.node = wk.sp = 0;
 	for(;;)
 	{
-		unsigned idle = __ballot_sync(0xffffffffu, !active);
-		if(more && __popc(idle) >= SKR_DEFER_REFILL)
+		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+		if(more && idle != 0u)
 		{
-			// REFILL: SKR_DEFER_REFILL idle lanes take the next rays of the list (one fetch per warp).  Never more at a time: the
-			// heavy rays of a frame sit next to each other in the list, and small bites spread them over all warps of the grid
-			// while the rest of a warp's lanes join in by work splitting (below).
-			unsigned base = 0;
+			// REFILL: the idle teams take the next rays of the list (one fetch per warp)
+			const unsigned n_idle = (unsigned) __popc(idle) / T;
+			unsigned base		  = 0;
 			if(lane == 0)
 			{
-				base = atomicAdd(fp.cand_count + 2, (unsigned) SKR_DEFER_REFILL);
+				base = atomicAdd(fp.cand_count + 2, n_idle);
 			}
 			base = __shfl_sync(0xffffffffu, base, 0);
-			more = base + (unsigned) SKR_DEFER_REFILL < count;
-			const unsigned ri = (unsigned) __popc(idle & ((1u << lane) - 1u));
-			if(!active && ri < (unsigned) SKR_DEFER_REFILL && base + ri < count)
+			more = base + n_idle < count;
+			if(!active)
 			{
-				const float4 c = __ldg(fp.cand_d + base + ri);
-				px			   = __ldg(fp.cand_px + base + ri);
-				tri_walk_begin(wk, sv.cam_pos, f3(c), c.w);
-				active = true;
+				const unsigned g = base + (unsigned) __popc(idle & ((1u << (team * T)) - 1u)) / T;
+				if(g < count)
+				{
+					const float4 c = __ldg(fp.cand_d + g);
+					px			   = __ldg(fp.cand_px + g);
+					tri_walk_begin(wk, sv.cam_pos, f3(c), c.w);
+					if(j == 0)
+					{
+						stk[0] = 0; // the root
+					}
+					sp	   = 1;
+					active = true;
+				}
 			}
-			idle = __ballot_sync(0xffffffffu, !active);
+			__syncwarp();
 		}
-		if(idle == 0xffffffffu)
+		if(__ballot_sync(0xffffffffu, active) == 0u)
 		{
 			if(!more)
 			{
 				break;
 			}
-			continue; // (fewer than SKR_DEFER_REFILL cannot be idle when all are: the refill above runs next time round)
+			continue;
 		}
-		if(idle != 0u && (!more || __popc(idle) >= 4))
+		// every lane of an active team takes one pending node (as far as there are any); when the stack is nearly full only one
+		int take = sp < T ? sp : T;
+		if(sp + take > SKR_TEAM_STACK - 2)
 		{
-			// WORK SPLITTING.  Some lanes are idle while others are deep inside the mesh (a line that threads the model without
-			// an accepted hit walks hundreds of nodes; the 32 rays of one warp used to be as slow as their slowest).  A busy lane
-			// gives the OLDEST entry of its stack -- the biggest pending subtree -- to an idle lane, which walks it for the
-			// same ray; the answers combine by OR (any accepted triangle blackens the pixel).
-			const unsigned donors = __ballot_sync(0xffffffffu, active && wk.sp > wk.base);
-			if(donors != 0u)
-			{
-				const unsigned lt = (1u << lane) - 1u;
-				const int n		  = min(__popc(idle), __popc(donors));
-				const int ri = __popc(idle & lt), rd = __popc(donors & lt);
-				const bool thief = !active && ri < n;
-				const int src	 = thief ? (int) __fns(donors, 0u, ri + 1) : (int) lane;
-				int give		 = 0;
-				if(active && wk.sp > wk.base && rd < n)
-				{
-					give = stack[wk.base];
-					wk.base++;
-				}
-				const int node = __shfl_sync(0xffffffffu, give, src);
-				const float ox = __shfl_sync(0xffffffffu, wk.o.x, src), oy = __shfl_sync(0xffffffffu, wk.o.y, src), oz = __shfl_sync(0xffffffffu, wk.o.z, src);
-				const float dx = __shfl_sync(0xffffffffu, wk.d.x, src), dy = __shfl_sync(0xffffffffu, wk.d.y, src), dz = __shfl_sync(0xffffffffu, wk.d.z, src);
-				const float ix = __shfl_sync(0xffffffffu, wk.inv.x, src), iy = __shfl_sync(0xffffffffu, wk.inv.y, src), iz = __shfl_sync(0xffffffffu, wk.inv.z, src);
-				const float tm = __shfl_sync(0xffffffffu, wk.tmax, src), dl = __shfl_sync(0xffffffffu, wk.dlen, src);
-				const unsigned pxx = __shfl_sync(0xffffffffu, px.x, src), pxy = __shfl_sync(0xffffffffu, px.y, src);
-				if(thief)
-				{
-					wk.o = f3(ox, oy, oz), wk.d = f3(dx, dy, dz), wk.inv = f3(ix, iy, iz);
-					wk.tmax = tm;
-					wk.dlen = dl;
-					wk.node = node;
-					wk.sp = wk.base = 0;
-					px	   = make_uint2(pxx, pxy);
-					active = true;
-				}
-			}
+			take = 1;
 		}
+		const bool have = active && (int) j < take;
+		const int node	= have ? stk[sp - 1 - (int) j] : 0;
+		__syncwarp(); // all reads of the stacks before any write
+		int kid[2];
+		int nk	 = 0;
+		bool hit = false;
+		if(have)
+		{
+			hit = tri_node_visit<STATS>(sv, wk, node, kid, nk, cnt);
+		}
+		const unsigned b1 = __ballot_sync(0xffffffffu, nk >= 1), b2 = __ballot_sync(0xffffffffu, nk == 2), bh = __ballot_sync(0xffffffffu, hit);
 		if(active)
 		{
-			const int r = tri_walk_step<STATS>(sv, wk, stack, cnt);
-			if(r >= 0)
+			const int below = sp - take;
+			const int off	= below + __popc(b1 & team_lt) + __popc(b2 & team_lt);
+			const int total = __popc(b1 & team_mask) + __popc(b2 & team_mask);
+			if(below + total > SKR_TEAM_STACK)
 			{
-				if(r == 1)
+				atomicOr(sv.err, 2); // cannot happen below a depth of ~60 with the guard above; reported, never silent
+			}
+			else
+			{
+				if(nk >= 1)
+				{
+					stk[off] = kid[0];
+				}
+				if(nk == 2)
+				{
+					stk[off + 1] = kid[1];
+				}
+			}
+			sp = below + total;
+			if(bh & team_mask)
+			{
+				if(j == 0)
 				{
 					write_black(fp, px);
 				}
 				active = false;
 			}
+			else if(sp == 0)
+			{
+				active = false;
+			}
 		}
+		__syncwarp();
 	}
 	__syncthreads();
 	if(threadIdx.x == 0)
