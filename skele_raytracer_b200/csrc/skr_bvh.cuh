@@ -177,35 +177,21 @@ SKR_DEV bool tri_node_visit(const SceneView &sv, const TriWalk &w, int node, int
 	hl = hl && n3.z * w.dlen >= 0.99999e-5f;
 	hr = hr && n3.w * w.dlen >= 0.99999e-5f;
 	const int cl = (int) f2u(n3.x), cr = (int) f2u(n3.y);
-	nk = 0;
-	if(hl)
+	if(hl && cl < 0 && tri_leaf_hit<STATS>(sv, ~cl, w.o, w.d, w.tmax, cnt))
 	{
-		if(cl < 0)
-		{
-			if(tri_leaf_hit<STATS>(sv, ~cl, w.o, w.d, w.tmax, cnt))
-			{
-				return true;
-			}
-		}
-		else
-		{
-			kid[nk++] = cl;
-		}
+		nk = 0;
+		return true;
 	}
-	if(hr)
+	if(hr && cr < 0 && tri_leaf_hit<STATS>(sv, ~cr, w.o, w.d, w.tmax, cnt))
 	{
-		if(cr < 0)
-		{
-			if(tri_leaf_hit<STATS>(sv, ~cr, w.o, w.d, w.tmax, cnt))
-			{
-				return true;
-			}
-		}
-		else
-		{
-			kid[nk++] = cr;
-		}
+		nk = 0;
+		return true;
 	}
+	// internal children the line reaches (no indexed stores: kid[] stays in registers)
+	const bool li = hl && cl >= 0, ri = hr && cr >= 0;
+	kid[0] = li ? cl : cr;
+	kid[1] = cr;
+	nk	   = (li ? 1 : 0) + (ri ? 1 : 0);
 	return false;
 }
 
