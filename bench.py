@@ -58,9 +58,17 @@ WORKLOADS = {
 MAX_STEPS = {"c1": 20, "c2": 1000, "c3": 10, "c4": 20, "c5": 3}   # timed steps per config in the `configs` block
 CPU_BUDGET_S = {"c1": 1.0, "c2": 2.0, "c3": 2.0, "c4": 2.0, "c5": 2.0}  # seconds per sample and build; the headline gets 8 s
 SEED = 1
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu captures
-# (bench.py cannot run ncu on itself)
-NCU_TRAFFIC_BYTES = {"c2": (583680 + 129536, "profiles/r01_c2_primary_ncu_raw.txt"), "c4": (613376 + 1024, "profiles/r01_c4_primary_ncu_raw.txt")}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu captures of this
+# round (bench.py cannot run ncu on itself).  Tree configs launch the kernel several times per frame with different loads:
+# the figure is the mean over the captured launches.
+NCU_TRAFFIC_BYTES = {
+    "c2": (600320 + 48128, "profiles/r02_c2_ncu_raw.txt (primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=0,FOG=1,HALVES=1>)"),
+    "c3": (int((99.703808 + 165.637376 + 120.5568 + 338.73152 + 117.56928 + 682.632448 + 703.89248 + 9.904896 + 116.811776 + 690.066688) * 1e6 / 5),
+           "profiles/r02_c3_ncu_raw.txt (mean of 5 shade_expand_kernel launches: queue entries in, queue entries out)"),
+    "c4": (3033856, "profiles/r02_c4_ncu_raw.txt (tri_deferred_kernel; primary_kernel: 67 584)"),
+    "c5": (int((113.852416 + 272.909312 + 329.109504 + 10.732544 + 114.915072 + 147.599104) * 1e6 / 3),
+           "profiles/r02_c5_ncu_raw.txt (mean of 3 shade_expand_kernel launches: expand, leaves in place, expand)"),
+}
 STAT_KEYS = ["closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "tri_tests", "bvh_node_visits", "sphere_hits", "light_evals",
              "sphere_tests_executed"]
 
@@ -478,8 +486,8 @@ def roofline_of(m, world, peaks, peaks_src, fp32_peak, bw):
         gbs = b / (dom_ms * 1e-3) / 1e9
         fl = algorithmic_flops(st0, m["primary_samples"] / world)
         return {"bound": "l1", "achieved": gbs, "peak": bw["l1_gbs"], "unit": "GB/s", "frac": gbs / bw["l1_gbs"] if bw["l1_gbs"] > 0 else None,
-                "traffic": traffic[0], "traffic_source": traffic[1], "kernel": "primary_kernel (BVH line any-hit)", "kernel_ms_per_frame": dom_ms,
-                "kernel_launches_per_frame": dom_launches, "bytes_per_frame_algorithmic_this_rank": b,
+                "traffic": traffic[0], "traffic_source": traffic[1], "kernel": "primary_kernel (<= 6 nodes in place) + tri_deferred_kernel (teams of 8 lanes per undecided ray)", "kernel_ms_per_frame": dom_ms,
+                "kernel_launches_per_frame": 2, "bytes_per_frame_algorithmic_this_rank": b,
                 "bytes_per_unit": "64 B per BVH node visit (both child boxes) + 48 B per triangle leaf test",
                 "levels": {"l1": {"achieved_gbs": gbs, "peak_gbs": bw["l1_gbs"]}, "l2": {"peak_gbs": bw["l2_gbs"]}, "shared": {"peak_gbs": bw["lds_gbs"]}, "hbm": hbm},
                 "fp32": {"tflops": fl / (dom_ms * 1e-3) / 1e12, "frac": fl / (dom_ms * 1e-3) / 1e12 / fp32_peak},
