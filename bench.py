@@ -279,18 +279,21 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
     t_first0 = time.time()
     r.reserve(base)   # queue arena / accumulators / kernels loaded ahead of the first frame
     reserve_ms = (time.time() - t_first0) * 1e3
-
-    # untimed counting pass (same seed -> same rays)
+    # the first frame of this context with these options (device time of the whole render, as every later frame is timed)
     if world == 1:
-        first = r.render_device(dataclasses.replace(base, collect_stats=True), 0, 0)
-        cst = first.as_dict()
-        cst_local = dict(cst)
-        peer_frames = None
+        first = r.render_device(base, 0, 0)
         tiles = gathered = None
     else:
         tiles = torch.empty(r.tiles_bytes(base), dtype=torch.uint8, device=dev)
-        first = r.render_tiles_device(dataclasses.replace(base, collect_stats=True), tiles.data_ptr())
-        cst = first.as_dict()
+        first = r.render_tiles_device(base, tiles.data_ptr())
+
+    # untimed counting pass (same seed -> same rays)
+    if world == 1:
+        cst = r.render_device(dataclasses.replace(base, collect_stats=True), 0, 0).as_dict()
+        cst_local = dict(cst)
+        peer_frames = None
+    else:
+        cst = r.render_tiles_device(dataclasses.replace(base, collect_stats=True), tiles.data_ptr()).as_dict()
         cst_local = dict(cst)
         t = torch.tensor([float(cst[k]) for k in STAT_KEYS], dtype=torch.float64, device=dev)
         dist.all_reduce(t)

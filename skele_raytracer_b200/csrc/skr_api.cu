@@ -127,7 +127,7 @@ struct skr_ctx
 	size_t tile_order_bytes = 0;
 	std::vector<int> tile_order_host;
 	std::vector<float> host_spheres;
-	unsigned long long scene_gen = 0; // bumped by every skr_scene_upload
+	unsigned long long scene_gen = 0; // hash of the uploaded spheres and camera (an e2e loop re-uploads the same scene every frame)
 	struct OrderKey
 	{
 		unsigned long long gen;
@@ -1649,8 +1649,22 @@ int skr_scene_upload(skr_ctx *ctx, const skr_scene_desc *sc)
 	// from the pageable staging vector has consumed it before it returns)
 	sv.nbig			= (T > 0 && sv.bvh) ? std::min((int) *ctx->h_count, BIG_TRI_CAP) : 0;
 	ctx->have_scene = true;
-	ctx->scene_gen++;
 	ctx->host_spheres.assign(sc->spheres, sc->spheres + 18 * (size_t) S); // (geometry for the tile classification of tile_launch_order)
+	{
+		// FNV-1a over what tile_launch_order reads: the same scene uploaded again keeps its cached tile order
+		unsigned long long h = 1469598103934665603ull;
+		const auto mix		 = [&h](const void *p, size_t n) {
+			  const unsigned char *b = static_cast<const unsigned char *>(p);
+			  for(size_t i = 0; i < n; i++)
+			  {
+				  h = (h ^ b[i]) * 1099511628211ull;
+			  }
+		};
+		mix(ctx->host_spheres.data(), sizeof(float) * ctx->host_spheres.size());
+		mix(sc->camera, sizeof sc->camera);
+		mix(&T, sizeof T);
+		ctx->scene_gen = h;
+	}
 	return SKR_OK;
 }
 
