@@ -400,29 +400,35 @@ def measure_gpu(S, torch, dist, r, workload, steps, warmup, rank, world, flush_b
             rows = 0 if peer_frames is None else peer_frames.band_rows(base.height, world)
             row_bytes = base.width * 3
 
+            if peer_frames is not None:
+                hdl, buf = peer_frames.hdls[0], peer_frames.bufs[0]
+                ptrs = list(hdl.buffer_ptrs)
+                y0, y1 = min(base.height, rank * rows), min(base.height, (rank + 1) * rows)
+                src, dst, nb = buf.data_ptr() + y0 * row_bytes, shf.host_ptr + y0 * row_bytes, (y1 - y0) * row_bytes
+
             def e2e_step():
+                # (called with the library's stream current: the barriers are enqueued behind the render and the copy)
                 r.upload(scene)
                 if peer_frames is None:
-                    st = r.render_peers_device(base, [shf.dev_ptr], want_stats=tree)
+                    r.render_peers_device(base, [shf.dev_ptr], want_stats=tree)
                     r.sync()
                     dist.barrier()
-                    return st
-                with torch.cuda.stream(ext):
-                    buf, st = peer_frames.render(r, base, rank, world, want_stats=tree, bands=True)
-                    y0, y1 = min(base.height, rank * rows), min(base.height, (rank + 1) * rows)
-                    r.copy_to_host(shf.host_ptr + y0 * row_bytes, buf.data_ptr() + y0 * row_bytes, (y1 - y0) * row_bytes)
-                    peer_frames.barrier_again()
+                    return
+                r.render_bands_device(base, ptrs, rows, want_stats=tree)
+                hdl.barrier()                      # every rank's kernel is done: this rank's band is whole
+                r.copy_to_host(dst, src, nb)       # ... and leaves over this rank's own PCIe link
+                hdl.barrier(channel=1)             # every rank's copy is done
                 r.sync()
-                return st
 
-            e2e_step()
-            e2e_step()
-            torch.cuda.synchronize()
-            dist.barrier()
-            t0 = time.time()
-            for _ in range(n_e2e):
+            with torch.cuda.stream(ext):
                 e2e_step()
-            t1 = time.time()
+                e2e_step()
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.time()
+                for _ in range(n_e2e):
+                    e2e_step()
+                t1 = time.time()
             t = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t1 = t0 + float(t.item())

@@ -101,7 +101,7 @@ typedef struct skr_options
 	int32_t world;
 	int32_t tile;			/* tile edge in pixels; 0 = default (32) */
 	int32_t collect_stats;	/* nonzero: count rays/tests on the device (slower; not for timed runs) */
-	int32_t queue_capacity; /* entries (52 B each) per wavefront queue level; 0 = default: sized to the frame, 1 M .. 128 M */
+	int32_t queue_capacity; /* entries (52 B each) per wavefront queue level; 0 = default: four fan-outs of the frame's samples, 32 M .. 128 M */
 	/* ABI 3.  0 = behaviour of HEAD: any triangle hit shades black (src/raytrace.h:221-224).  1 = opt-in, explicitly
 	 * NON-PARITY extension: triangles are shaded with their own Material -- closest hit on the actual
 	 * (un-mirrored) triangle in front of the ray, geometric normal facing the ray, the Blinn-Phong terms of

@@ -42,7 +42,7 @@ struct Span
 
 constexpr size_t SMEM_BLOB_LIMIT = 64 * 1024;
 constexpr unsigned MAX_QUEUE_CAP = 128u << 20; // entries per level (52 B each, 6.7 GB): fewer, fuller chunks -- config 5: 228 ms at 32 M, 213 ms at 128 M
-constexpr unsigned MIN_QUEUE_CAP = 1u << 20;
+constexpr unsigned MIN_QUEUE_CAP = 32u << 20;
 constexpr int DEFAULT_TILE = 32;
 constexpr int MAX_BANDS = 8;
 constexpr int BRUTE_FORCE_TRIS = 4;
@@ -867,9 +867,12 @@ int prepare_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	unsigned cap	   = (unsigned) o->queue_capacity;
 	if(o->queue_capacity <= 0)
 	{
-		// default: what one fan-out of all primary samples could need, between 1 M and 128 M entries, and never more
-		// than a quarter of the free memory over all levels; an allocation that is already big enough is kept
-		const unsigned long long want = (unsigned long long) pl.npix_local * (unsigned) fp.spp * (fan ? fan : 1u);
+		// default: four times what one fan-out of all primary samples could need, between 32 M and 128 M entries (1.7 - 6.7 GB
+		// per level of 180), and never more than a quarter of the free memory over all levels; an allocation that is
+		// already big enough is kept.  Generous on purpose: a level that fits its queue is ONE launch and one count read-back
+		// (config 3: 19 launches / 6.13 ms at 33 M entries, 8 launches / 5.86 ms at 128 M; one rank's share at world = 8:
+		// 12 launches / 0.99 ms at 8 M, 6 launches / 0.85 ms at 32 M).
+		const unsigned long long want = 4ull * (unsigned long long) pl.npix_local * (unsigned) fp.spp * (fan ? fan : 1u);
 		cap = want > MAX_QUEUE_CAP ? MAX_QUEUE_CAP : (want < MIN_QUEUE_CAP ? MIN_QUEUE_CAP : (unsigned) want);
 		if(ctx->queue_cap >= cap && ctx->n_levels_alloc >= pl.qlevels)
 		{
