@@ -600,6 +600,25 @@ struct Plan
 	bool leaf_inline; // depth-1 hits are shaded by the warp that found them (shade_expand_kernel<..., LEAF>)
 };
 
+// constants of fdiv (skr_kernels.cuh): l = ceil(log2 d), m = floor(2^32 (2^l - d) / d) + 1, shifts min(l, 1) and max(l - 1, 0)
+FastDiv make_fastdiv(uint32_t d)
+{
+	FastDiv f;
+	if(d == 0)
+	{
+		d = 1;
+	}
+	uint32_t l = 0;
+	while(l < 32 && (1ull << l) < d)
+	{
+		l++;
+	}
+	f.m	 = (uint32_t) ((((1ull << l) - d) << 32) / d + 1ull);
+	f.s1 = l < 1 ? l : 1;
+	f.s2 = l > 1 ? l - 1 : 0;
+	return f;
+}
+
 int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 {
 	if(!o || o->width <= 0 || o->height <= 0)
@@ -675,6 +694,14 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	fp.slot_gi	 = 1u + (uint32_t) ctx->sv.L * (uint32_t) ctx->sv.F;
 	pl.tiles_local = (fp.tiles_total + world - 1) / world;
 	pl.npix_local  = pl.tiles_local * tile * tile;
+	fp.fd_tpix		= make_fastdiv((uint32_t) (tile * tile));
+	fp.fd_wpr		= make_fastdiv((uint32_t) fp.wpr);
+	fp.fd_tiles_x	= make_fastdiv((uint32_t) fp.tiles_x);
+	fp.fd_tile		= make_fastdiv((uint32_t) tile);
+	fp.fd_world		= make_fastdiv((uint32_t) world);
+	fp.fd_width		= make_fastdiv((uint32_t) o->width);
+	fp.fd_peer_rows = fp.fd_band_ctas = make_fastdiv(1u);
+	fp.fast			= pl.npix_local <= 0xffffffffLL && (long long) fp.tiles_total + world <= 0x7fffffffLL;
 	pl.levels	   = ((fp.gi || fp.fresnel) && fp.max_depth > 0) ? fp.max_depth : 0;
 	{
 		// deferred triangle query (tri_deferred_kernel: teams of lanes per heavy ray): single-sample frames without a wavefront
@@ -1787,6 +1814,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 			pl.fp.band_count = ctx->d_band;
 			pl.fp.band_flag	 = ctx->d_band + MAX_BANDS;
 			pl.fp.band_ctas	 = (unsigned) rpb * (unsigned) fp.tiles_x * (unsigned) (tpix / 32); // blocks per band
+			pl.fp.fd_band_ctas = make_fastdiv(pl.fp.band_ctas);
 			pl.fp.band_seq	 = ++ctx->band_seq;
 			pl.rows_per_band = rpb;
 		}
@@ -1941,6 +1969,7 @@ static int render_to_frames(skr_ctx *ctx, const skr_options *opt, void *const *d
 	}
 	pl.fp.n_peers	= n_frames;
 	pl.fp.peer_rows = rows_per_frame;
+	pl.fp.fd_peer_rows = make_fastdiv((uint32_t) (rows_per_frame > 0 ? rows_per_frame : 1));
 	return render_common(ctx, opt, pl, stats);
 }
 

@@ -47,10 +47,25 @@ struct Queue
 	unsigned cap;
 };
 
+// n / d for any 32-bit n by a multiply-high and two shifts (Granlund & Montgomery's round-up form; constants from
+// make_fastdiv on the host): the frame's divisors (tile size, tiles per row, world size, width) are run-time values, and a
+// hardware-less integer division costs ~25 instructions (32-bit) to ~100 (64-bit) per thread.
+struct FastDiv
+{
+	uint32_t m, s1, s2;
+};
+SKR_DEV uint32_t fdiv(uint32_t n, const FastDiv f)
+{
+	const uint32_t t = __umulhi(f.m, n);
+	return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
 struct FrameParams
 {
 	int width, height;
 	int tile, tiles_x, tiles_total, rank, world, wpr; // wpr = tile / 8 (warps per tile row-block)
+	FastDiv fd_tpix, fd_wpr, fd_tiles_x, fd_tile, fd_world, fd_width, fd_peer_rows, fd_band_ctas;
+	int fast; // 1: local pixel indices fit 32 bits (any frame but absurdly thin ones), fdiv instead of 64-bit divisions
 	int grid, spp;
 	int max_depth, gi, n_gi, shadows, fresnel;
 	float angle, aspect, inv_w, inv_h;
@@ -96,6 +111,22 @@ struct PixelId
 SKR_DEV PixelId decode_pixel(const FrameParams &fp, long long lp)
 {
 	const int tpix = fp.tile * fp.tile;
+	PixelId p;
+	if(fp.fast)
+	{
+		const uint32_t l  = (uint32_t) lp;
+		const uint32_t lt = fdiv(l, fp.fd_tpix);
+		const uint32_t r  = l - lt * (uint32_t) tpix;
+		const uint32_t w = r >> 5, lane = r & 31u;
+		const uint32_t wy = fdiv(w, fp.fd_wpr), wx = w - wy * (uint32_t) fp.wpr;
+		const int px = (int) (wx * 8u + (lane & 7u)), py = (int) (wy * 4u + (lane >> 3));
+		const uint32_t gt = fp.tile_order ? (uint32_t) __ldg(fp.tile_order + lt) : lt * (uint32_t) fp.world + (uint32_t) fp.rank;
+		const uint32_t ty = fdiv(gt, fp.fd_tiles_x), tx = gt - ty * (uint32_t) fp.tiles_x;
+		p.x				  = (int) tx * fp.tile + px;
+		p.y				  = (int) ty * fp.tile + py;
+		p.valid			  = gt < (uint32_t) fp.tiles_total && p.x < fp.width && p.y < fp.height;
+		return p;
+	}
 	const int lt   = (int) (lp / tpix);
 	const int r	   = (int) (lp - (long long) lt * tpix);
 	const int w = r >> 5, lane = r & 31;
@@ -103,7 +134,6 @@ SKR_DEV PixelId decode_pixel(const FrameParams &fp, long long lp)
 	const int px = wx * 8 + (lane & 7), py = wy * 4 + (lane >> 3);
 	// local tile -> global tile: interleaved over the ranks, visited in the order of fp.tile_order when the host supplied one
 	const long long gt = fp.tile_order ? (long long) __ldg(fp.tile_order + lt) : (long long) lt * fp.world + fp.rank;
-	PixelId p;
 	p.valid = gt < fp.tiles_total;
 	const int tx = (int) (gt % fp.tiles_x), ty = (int) (gt / fp.tiles_x);
 	p.x = tx * fp.tile + px;
@@ -114,13 +144,26 @@ SKR_DEV PixelId decode_pixel(const FrameParams &fp, long long lp)
 // image coordinates -> local pixel index (inverse of the above; the pixel must belong to this rank)
 SKR_DEV long long encode_pixel(const FrameParams &fp, int x, int y)
 {
-	const int tx = x / fp.tile, ty = y / fp.tile;
+	const int tx = (int) fdiv((uint32_t) x, fp.fd_tile), ty = (int) fdiv((uint32_t) y, fp.fd_tile);
 	const int px = x - tx * fp.tile, py = y - ty * fp.tile;
 	const long long gt = (long long) ty * fp.tiles_x + tx;
-	const long long lt = gt / fp.world;
+	const long long lt = (long long) fdiv((uint32_t) gt, fp.fd_world); // gt < tiles_total, an int
 	const int w		   = (py >> 2) * fp.wpr + (px >> 3);
 	const int lane	   = ((py & 3) << 3) | (px & 7);
 	return lt * (long long) (fp.tile * fp.tile) + (w << 5) + lane;
+}
+
+// image coordinates -> pixel index in the compact tile-major RGB8 buffer (tiles8): slot of the tile on this rank, row-major inside
+SKR_DEV size_t tile_slot_pixel(const FrameParams &fp, int x, int y)
+{
+	const uint32_t tx = fdiv((uint32_t) x, fp.fd_tile), ty = fdiv((uint32_t) y, fp.fd_tile);
+	const uint32_t lt = fdiv(ty * (uint32_t) fp.tiles_x + tx, fp.fd_world); // whatever the launch order
+	const uint32_t px = (uint32_t) x - tx * (uint32_t) fp.tile, py = (uint32_t) y - ty * (uint32_t) fp.tile;
+	return (size_t) lt * (size_t) (fp.tile * fp.tile) + (size_t) (py * (uint32_t) fp.tile + px);
+}
+SKR_DEV int peer_of_row(const FrameParams &fp, int y)
+{
+	return min((int) fdiv((uint32_t) y, fp.fd_peer_rows), fp.n_peers - 1);
 }
 
 // Accumulators (--gillum / fresnel frames): per local pixel 3 x int64 fixed point (2^-32) + one flags word.  Integer
@@ -214,7 +257,7 @@ SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, 
 		// peers travel over NVLink while the rest of the kernel is still tracing
 		const uint8_t r = quantise(c.x), g = quantise(c.y), b = quantise(c.z);
 		const size_t at = 3 * ((size_t) p.y * fp.width + p.x);
-		const int k0 = fp.peer_rows > 0 ? min(p.y / fp.peer_rows, fp.n_peers - 1) : 0;
+		const int k0 = fp.peer_rows > 0 ? peer_of_row(fp, p.y) : 0;
 		const int k1 = fp.peer_rows > 0 ? k0 + 1 : fp.n_peers;
 		for(int k = k0; k < k1; k++)
 		{
@@ -226,10 +269,7 @@ SKR_DEV void write_pixel(const FrameParams &fp, long long lp, const PixelId &p, 
 	}
 	if(fp.tiles8)
 	{
-		const int tpix = fp.tile * fp.tile;
-		const long long lt = ((long long) (p.y / fp.tile) * fp.tiles_x + p.x / fp.tile) / fp.world; // slot in the compact buffer (whatever the launch order)
-		const int tx = p.x % fp.tile, ty = p.y % fp.tile;
-		uint8_t *o = fp.tiles8 + 3 * ((size_t) lt * tpix + (size_t) ty * fp.tile + tx);
+		uint8_t *o = fp.tiles8 + 3 * tile_slot_pixel(fp, p.x, p.y);
 		o[0]	   = quantise(c.x);
 		o[1]	   = quantise(c.y);
 		o[2]	   = quantise(c.z);
@@ -266,9 +306,7 @@ SKR_DEV void write_block(const FrameParams &fp, long long lp, const PixelId &p, 
 	}
 	if(fp.tiles8 && p.valid)
 	{
-		const int tpix	   = fp.tile * fp.tile;
-		const long long lt = ((long long) (p.y / fp.tile) * fp.tiles_x + p.x / fp.tile) / fp.world;
-		uint8_t *t		   = fp.tiles8 + 3 * ((size_t) lt * tpix + (size_t) (p.y % fp.tile) * fp.tile + (p.x % fp.tile));
+		uint8_t *t = fp.tiles8 + 3 * tile_slot_pixel(fp, p.x, p.y);
 		t[0] = o[0], t[1] = o[1], t[2] = o[2];
 	}
 	__syncwarp();
@@ -283,7 +321,7 @@ SKR_DEV void write_block(const FrameParams &fp, long long lp, const PixelId &p, 
 			{
 				reinterpret_cast<uint32_t *>(fp.rgb8)[at] = v;
 			}
-			const int k0 = fp.peer_rows > 0 ? min((y0 + r) / fp.peer_rows, fp.n_peers - 1) : 0;
+			const int k0 = fp.peer_rows > 0 ? peer_of_row(fp, y0 + r) : 0;
 			const int k1 = fp.peer_rows > 0 ? k0 + 1 : fp.n_peers;
 			for(int k = k0; k < k1; k++)
 			{
@@ -397,10 +435,7 @@ SKR_DEV void cand_push(const FrameParams &fp, bool want, long long lp, const Pix
 	{
 		const unsigned idx = base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
 		fp.cand_d[idx]	   = make_float4(d.x, d.y, d.z, tmax);
-		const int tpix	   = fp.tile * fp.tile;
-		fp.cand_px[idx]	   = make_uint2((uint32_t) (p.y * fp.width + p.x),
-										(uint32_t) ((((long long) (p.y / fp.tile) * fp.tiles_x + p.x / fp.tile) / fp.world) * tpix + (long long) (p.y % fp.tile) * fp.tile +
-													(p.x % fp.tile)));
+		fp.cand_px[idx]	   = make_uint2((uint32_t) (p.y * fp.width + p.x), (uint32_t) tile_slot_pixel(fp, p.x, p.y)); // (deferral needs npix_local < 2^32)
 	}
 }
 // consumer side: the hit point of an entry, src/raytrace.h:197-204 (exact t, then P = o + d * t)
@@ -628,7 +663,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		if(lane == 0)
 		{
 			__threadfence_system();
-			const unsigned b	= blk / fp.band_ctas;
+			const unsigned b	= fdiv(blk, fp.fd_band_ctas);
 			const unsigned left = nblocks - b * fp.band_ctas;
 			const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
 			if((atomicAdd(fp.band_count + b, 1u) + 1u) % want == 0u) // counters run on from frame to frame (same geometry)
@@ -956,7 +991,7 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) shade_expand_kernel
 	}
 	if(valid)
 	{
-		const int x = (int) (rng.pixel % (uint32_t) fp.width), y = (int) (rng.pixel / (uint32_t) fp.width);
+		const int y = (int) fdiv(rng.pixel, fp.fd_width), x = (int) (rng.pixel - (uint32_t) y * (uint32_t) fp.width);
 		const long long lp = encode_pixel(fp, x, y);
 		if constexpr(LEAF)
 		{
@@ -1070,7 +1105,7 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 	}
 	if(valid && (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f))
 	{
-		const int x = (int) (pixel % (uint32_t) fp.width), y = (int) (pixel / (uint32_t) fp.width);
+		const int y = (int) fdiv(pixel, fp.fd_width), x = (int) (pixel - (uint32_t) y * (uint32_t) fp.width);
 		const long long lp = encode_pixel(fp, x, y);
 		accum_add(fp.accum, lp, contrib);
 	}
@@ -1109,8 +1144,8 @@ SKR_DEV void write_black(const FrameParams &fp, uint2 px) // the pixel of a cand
 		fp.rgb8[at] = fp.rgb8[at + 1] = fp.rgb8[at + 2] = 0;
 	}
 	{
-		const int y	 = (int) (px.x / (unsigned) fp.width);
-		const int k0 = fp.peer_rows > 0 ? min(y / fp.peer_rows, fp.n_peers - 1) : 0;
+		const int y	 = (int) fdiv(px.x, fp.fd_width);
+		const int k0 = fp.peer_rows > 0 ? peer_of_row(fp, y) : 0;
 		const int k1 = fp.peer_rows > 0 ? k0 + 1 : fp.n_peers;
 		for(int k = k0; k < k1; k++)
 		{
