@@ -477,7 +477,7 @@ def test_queue_capacity_does_not_change_the_image(gpu, gscenes):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
-@pytest.mark.parametrize("world,tile", [(2, 32), (3, 16), (8, 32)])
+@pytest.mark.parametrize("world,tile", [(2, 32), (3, 16), (8, 32), (5, 24), (7, 40)])   # (divisors that are not powers of two: fdiv)
 def test_frame_split_is_bit_identical_for_any_world(gpu, gscenes, world, tile):
     gpu.upload(gscenes["spheres2"])
     full32, full8, _ = gpu.render(S.Options(**GI_KW))
@@ -493,7 +493,7 @@ def test_frame_split_is_bit_identical_for_any_world(gpu, gscenes, world, tile):
     assert np.array_equal(acc32.view(np.uint32), full32.view(np.uint32)) and np.array_equal(acc8, full8)
 
 
-@pytest.mark.parametrize("world,tile", [(1, 32), (2, 32), (4, 16)])
+@pytest.mark.parametrize("world,tile", [(1, 32), (2, 32), (4, 16), (3, 24)])
 def test_compact_tiles_and_deinterleave_on_device(gpu, gscenes, world, tile):
     import torch
     from skele_raytracer_b200 import tiles as T
