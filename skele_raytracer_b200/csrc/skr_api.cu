@@ -126,6 +126,9 @@ struct skr_ctx
 	int *d_tile_order = nullptr;
 	size_t tile_order_bytes = 0;
 	std::vector<int> tile_order_host;
+	int order_band_perm[MAX_BANDS] = {};		   // cached with the order: launch position -> band of rows (skr_render's overlapped copy-out)
+	unsigned order_band_start[MAX_BANDS + 1] = {}; // ... and the first launch block of every position
+	bool order_has_bands = false;
 	std::vector<float> host_spheres;
 	unsigned long long scene_gen = 0; // hash of the uploaded spheres and camera (an e2e loop re-uploads the same scene every frame)
 	struct OrderKey
@@ -595,6 +598,7 @@ struct Plan
 	int levels;		  // depth levels of the --gillum / fresnel tree (0: none)
 	bool shaded;	  // opt-in shaded-triangles mode (skr_shaded.cuh)
 	int rows_per_band; // tile rows per band of skr_render's overlapped copy-out (0: the frame does not leave in bands)
+	int band_perm[MAX_BANDS]; // launch position -> band of rows (identity unless tile_launch_order reorders the bands)
 	bool defer;		  // triangle queries of the camera rays go through tri_deferred_kernel
 	int qlevels;	  // queue levels needed: `levels`, or one less when the leaves are shaded in place
 	bool leaf_inline; // depth-1 hits are shaded by the warp that found them (shade_expand_kernel<..., LEAF>)
@@ -700,7 +704,7 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	fp.fd_tile		= make_fastdiv((uint32_t) tile);
 	fp.fd_world		= make_fastdiv((uint32_t) world);
 	fp.fd_width		= make_fastdiv((uint32_t) o->width);
-	fp.fd_peer_rows = fp.fd_band_ctas = make_fastdiv(1u);
+	fp.fd_peer_rows = make_fastdiv(1u);
 	fp.fast			= pl.npix_local <= 0xffffffffLL && (long long) fp.tiles_total + world <= 0x7fffffffLL;
 	pl.levels	   = ((fp.gi || fp.fresnel) && fp.max_depth > 0) ? fp.max_depth : 0;
 	{
@@ -1007,12 +1011,16 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 // bottom rows of the image -- the ground, the most expensive pixels of most scenes -- and with the frame split over 8 GPUs
 // (two waves of CTAs each) that tail was a third of the step.  The host classifies this rank's tiles: can any line
 // through a pixel of the tile pass a sphere's test?  (The bundle test of cull_pairs, skr_device.cuh, evaluated in double
-// for the cone around the tile's centre ray.)  Tiles that can go first, sky tiles last; within a band of tile rows when
-// the frame leaves in bands (skr_render's overlapped copy-out), so that bands still complete in order.  Purely a
-// permutation of the launch: every pixel computes what it computed before.
-int tile_launch_order(skr_ctx *ctx, const Plan &pl, int rows_per_band, FrameParams &fp)
+// for the cone around the tile's centre ray.)  Tiles that can go first, sky tiles last.  When the frame leaves in bands of
+// tile rows (skr_render's overlapped copy-out) the order is band by band -- a band's copy starts when its last block is
+// done -- with the BANDS heaviest first too: the last band launched, whose copy cannot hide behind the kernel and whose
+// tiles are the kernel's tail, is then the lightest one (pl.band_perm tells skr_render which rows complete k-th).
+// Purely a permutation of the launch: every pixel computes what it computed before.
+int tile_launch_order(skr_ctx *ctx, Plan &pl)
 {
-	fp.tile_order = nullptr;
+	FrameParams &fp			= pl.fp;
+	const int rows_per_band = pl.rows_per_band;
+	fp.tile_order			= nullptr;
 	const char *no = getenv("SKR_NO_TILE_ORDER");
 	if(ctx->sv.S == 0 || ctx->sv.T > 0 || (no && no[0] == '1') || pl.tiles_local < 8)
 	{
@@ -1031,31 +1039,22 @@ int tile_launch_order(skr_ctx *ctx, const Plan &pl, int rows_per_band, FramePara
 			 d[1] = sv.cam_dir.y + u * sv.cam_right.y + v * sv.cam_up.y;
 			 d[2] = sv.cam_dir.z + u * sv.cam_right.z + v * sv.cam_up.z;
 		};
-		std::vector<int> heavy, light;
+		// per band of tile rows (one band when the frame does not leave in bands): tiles that can see a sphere, tiles that cannot
+		const int tile_rows = (fp.height + fp.tile - 1) / fp.tile;
+		const int nbands	= rows_per_band > 0 ? (tile_rows + rows_per_band - 1) / rows_per_band : 1;
+		std::vector<std::vector<int>> heavy((size_t) nbands), light((size_t) nbands);
 		std::vector<int> &order = ctx->tile_order_host;
 		order.clear();
-		int band_of_last = -1;
-		const auto flush = [&]() {
-			order.insert(order.end(), heavy.begin(), heavy.end());
-			order.insert(order.end(), light.begin(), light.end());
-			heavy.clear();
-			light.clear();
-		};
 		for(long long lt = 0; lt < pl.tiles_local; lt++)
 		{
 			const long long gt = lt * fp.world + fp.rank;
 			if(gt >= fp.tiles_total)
 			{
-				light.push_back(fp.tiles_total); // padding slot: decode_pixel marks it invalid
+				light[(size_t) nbands - 1].push_back(fp.tiles_total); // padding slot: decode_pixel marks it invalid
 				continue;
 			}
 			const int tx = (int) (gt % fp.tiles_x), ty = (int) (gt / fp.tiles_x);
 			const int band = rows_per_band > 0 ? ty / rows_per_band : 0;
-			if(band != band_of_last)
-			{
-				flush();
-				band_of_last = band;
-			}
 			// cone of the tile: centre ray w, half angle beta from the farthest corner (+ one pixel for the jitter)
 			const double x0 = tx * fp.tile - 1.0, x1 = std::min(fp.width, (tx + 1) * fp.tile) + 1.0;
 			const double y0 = ty * fp.tile - 1.0, y1 = std::min(fp.height, (ty + 1) * fp.tile) + 1.0;
@@ -1079,15 +1078,51 @@ int tile_launch_order(skr_ctx *ctx, const Plan &pl, int rows_per_band, FramePara
 				const double X	= fabs((double) p[3]) * 1.01 + sqrt(uu) * beta + 1e-4 * (1.0 + sqrt(uu));
 				sees			= !(uu - hw * hw / ww > X * X);
 			}
-			(sees ? heavy : light).push_back((int) gt);
+			(sees ? heavy : light)[(size_t) band].push_back((int) gt);
 		}
-		flush();
+		// Bands are launched heaviest first (share of tiles that see a sphere; ties in row order), so that the LAST band --
+		// the one whose copy-out cannot hide behind the kernel, and whose tiles make the kernel's tail -- is the lightest
+		std::vector<int> perm((size_t) nbands);
+		for(int b = 0; b < nbands; b++)
+		{
+			perm[(size_t) b] = b;
+		}
+		std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+			const double na = (double) (heavy[(size_t) a].size() + light[(size_t) a].size()), nb = (double) (heavy[(size_t) b].size() + light[(size_t) b].size());
+			return (double) heavy[(size_t) a].size() * nb > (double) heavy[(size_t) b].size() * na;
+		});
+		const unsigned blocks_per_tile = (unsigned) (fp.tile * fp.tile / 32);
+		ctx->order_has_bands		   = rows_per_band > 0 && nbands <= MAX_BANDS;
+		for(int k = 0; k < nbands; k++)
+		{
+			const int b = perm[(size_t) k];
+			if(ctx->order_has_bands)
+			{
+				ctx->order_band_perm[k]	 = b;
+				ctx->order_band_start[k] = (unsigned) order.size() * blocks_per_tile;
+			}
+			order.insert(order.end(), heavy[(size_t) b].begin(), heavy[(size_t) b].end());
+			order.insert(order.end(), light[(size_t) b].begin(), light[(size_t) b].end());
+		}
+		if(ctx->order_has_bands)
+		{
+			ctx->order_band_start[nbands] = (unsigned) order.size() * blocks_per_tile;
+		}
 		CK(ensure(ctx->d_tile_order, ctx->tile_order_bytes, sizeof(int) * order.size()));
 		CK(cudaMemcpyAsync(ctx->d_tile_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
 		ctx->order_key	 = key;
 		ctx->order_valid = true;
 	}
 	fp.tile_order = ctx->d_tile_order;
+	if(rows_per_band > 0 && ctx->order_has_bands)
+	{
+		for(unsigned k = 0; k < fp.n_bands && k < (unsigned) MAX_BANDS; k++)
+		{
+			fp.band_start[k] = ctx->order_band_start[k];
+			pl.band_perm[k]	 = ctx->order_band_perm[k];
+		}
+		fp.band_start[fp.n_bands] = ctx->order_band_start[fp.n_bands];
+	}
 	return SKR_OK;
 }
 
@@ -1108,8 +1143,10 @@ int check_error_word(skr_ctx *ctx, const char *what)
 }
 
 // common driver: outputs already set in pl.fp
-// `after_launch` (optional) runs once the frame's kernels are enqueued, before anything waits for them.
-int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats, const std::function<int()> &after_launch = nullptr)
+// `after_launch` (optional) runs once the frame's kernels are enqueued, before anything waits for them; `before_launch`
+// (optional) once the frame is planned (launch order known), before anything is enqueued for it.
+int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats, const std::function<int()> &after_launch = nullptr,
+				  const std::function<int()> &before_launch = nullptr)
 {
 	cudaStream_t st = ctx->stream;
 	ctx->spans_used = 0;
@@ -1148,7 +1185,7 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 	}
 	if(!tree && !pl.shaded)
 	{
-		const int rc_order = tile_launch_order(ctx, pl, pl.rows_per_band, pl.fp);
+		const int rc_order = tile_launch_order(ctx, pl);
 		if(rc_order)
 		{
 			return rc_order;
@@ -1162,6 +1199,14 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 		if(rc_prep)
 		{
 			return rc_prep;
+		}
+	}
+	if(before_launch)
+	{
+		const int rc_before = before_launch();
+		if(rc_before)
+		{
+			return rc_before;
 		}
 	}
 	if(!async)
@@ -1776,7 +1821,42 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 			CK(cudaMemsetAsync(ctx->d_rgb32, 0, npx * 3 * sizeof(float), ctx->stream));
 		}
 	}
-	// Copy-out overlapped with the kernel, for frames that are ONE kernel: the frame leaves in bands of whole tile rows; the
+	// Frames that are ONE long kernel and leave as RGB8 only, into page-locked memory this device can address: the kernel
+	// stores the finished 8 x 4 blocks STRAIGHT into the host frame as 32-bit words (write_block, the path of
+	// skr_render_peers_device), which cross PCIe while the rest of the frame is still being traced -- no copy engine, no
+	// flags, and the tiles keep the frame-wide heavy-first launch order.  Config 2: 1.07 ms per upload + frame against 1.13
+	// for the band copies below and 1.17 for a copy after the kernel; the kernel itself is not slowed (0.995 ms), whereas
+	// copy-engine traffic running beside it costs it ~0.045 ms.  Short kernels (single-sample frames) would wait for PCIe.
+	{
+		const char *no = getenv("SKR_NO_OVERLAP"), *nod = getenv("SKR_NO_HOST_STORES");
+		cudaPointerAttributes a;
+		if(rgb8 && !rgb32 && pl.levels == 0 && !pl.shaded && pl.fp.world == 1 && pl.fp.spp >= 4 && opt->width % 4 == 0 && npx * 3 >= (1u << 20) &&
+		   (reinterpret_cast<uintptr_t>(rgb8) & 3u) == 0u && !(no && no[0] == '1') && !(nod && nod[0] == '1'))
+		{
+			if(cudaPointerGetAttributes(&a, rgb8) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer != nullptr)
+			{
+				pl.fp.rgb8		= nullptr;
+				pl.fp.peers[0]	= static_cast<uint8_t *>(a.devicePointer);
+				pl.fp.n_peers	= 1;
+				pl.fp.peer_rows = 0;
+				skr_stats local;
+				rc = render_common(ctx, opt, pl, &local); // (returns once the stream has drained: the stores have landed)
+				if(rc)
+				{
+					return rc;
+				}
+				local.ms_d2h = 0.0f; // no copy: the frame's bytes crossed PCIe inside ms_total
+				if(stats)
+				{
+					*stats = local;
+				}
+				return SKR_OK;
+			}
+			cudaGetLastError();
+		}
+	}
+	// Otherwise (float frame wanted too, or memory the device cannot address) the copy-out is overlapped with the kernel by
+	// the copy engine: the frame leaves in bands of whole tile rows; the
 	// copy of band b sits on a second stream behind a stream-ordered wait (cuStreamWaitValue32) on the flag that the last
 	// CTA of the band sets (primary_kernel), so all but the last band cross PCIe while the kernel is still tracing.
 	struct Band
@@ -1804,7 +1884,9 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 		   (!rgb8 || pinned(rgb8)) && (!rgb32 || pinned(rgb32)) && (rgb8 || rgb32))
 		{
 			const int tile_rows = (opt->height + fp.tile - 1) / fp.tile;
-			const int rpb		= (tile_rows + 3) / 4;
+			const char *nbe		= getenv("SKR_BANDS"); // (tuning aid) bands per frame, 1 .. 8; default 6
+			const int nwant		= nbe && atoi(nbe) >= 1 && atoi(nbe) <= MAX_BANDS ? atoi(nbe) : 6;
+			const int rpb		= (tile_rows + nwant - 1) / nwant;
 			nb					= (tile_rows + rpb - 1) / rpb;
 			for(int b = 0; b < nb; b++)
 			{
@@ -1813,8 +1895,16 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 			}
 			pl.fp.band_count = ctx->d_band;
 			pl.fp.band_flag	 = ctx->d_band + MAX_BANDS;
-			pl.fp.band_ctas	 = (unsigned) rpb * (unsigned) fp.tiles_x * (unsigned) (tpix / 32); // blocks per band
-			pl.fp.fd_band_ctas = make_fastdiv(pl.fp.band_ctas);
+			pl.fp.n_bands	 = (unsigned) nb;
+			for(int b = 0; b <= nb; b++) // scan order; tile_launch_order may permute the bands
+			{
+				const size_t rows	= std::min((size_t) tile_rows, (size_t) b * rpb);
+				pl.fp.band_start[b] = (unsigned) (rows * (size_t) fp.tiles_x * (size_t) (tpix / 32));
+				if(b < nb)
+				{
+					pl.band_perm[b] = b;
+				}
+			}
 			pl.fp.band_seq	 = ++ctx->band_seq;
 			pl.rows_per_band = rpb;
 		}
@@ -1824,12 +1914,21 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 	{
 		// the per-band CTA counters run on from frame to frame; reset when the band geometry changes (and now and then,
 		// far from 32-bit wrap-around) or after a frame that did not complete
-		const unsigned long long geom = ((unsigned long long) pl.fp.band_ctas << 32) | (unsigned) (pl.npix_local / 32);
-		if(geom != ctx->band_geom || (pl.fp.band_seq & 0xffffu) == 0u)
-		{
-			CK(cudaMemsetAsync(ctx->d_band, 0, sizeof(unsigned) * MAX_BANDS, ctx->stream));
-			ctx->band_geom = geom;
-		}
+		// (the launch order of the bands is part of that geometry and is only known once the frame is planned: the reset sits
+		// in `before_launch`, which render_common calls after tile_launch_order and before the kernel)
+		const auto reset_counters = [&]() -> int {
+			unsigned long long geom = 1469598103934665603ull;
+			for(unsigned k = 0; k <= pl.fp.n_bands; k++)
+			{
+				geom = (geom ^ pl.fp.band_start[k]) * 1099511628211ull;
+			}
+			if(geom != ctx->band_geom || (pl.fp.band_seq & 0xffffu) == 0u)
+			{
+				CK(cudaMemsetAsync(ctx->d_band, 0, sizeof(unsigned) * MAX_BANDS, ctx->stream));
+				ctx->band_geom = geom;
+			}
+			return SKR_OK;
+		};
 		// The waits are enqueued AFTER the kernel they wait for: should the two streams share a hardware queue, the copies
 		// then merely line up behind the kernel; a wait enqueued first could block the kernel behind it for ever.
 		bool enqueued		   = false;
@@ -1845,7 +1944,8 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 				{
 					CK(cudaEventRecord(ctx->ev_x0, ctx->copy_stream));
 				}
-				const size_t y0 = bands[b].y0, rows = bands[b].y1 - bands[b].y0;
+				const int rb	= pl.band_perm[b]; // the band of rows launched b-th
+				const size_t y0 = bands[rb].y0, rows = bands[rb].y1 - bands[rb].y0;
 				if(rgb8)
 				{
 					CK(cudaMemcpyAsync(rgb8 + y0 * row8, ctx->d_rgb8 + y0 * row8, rows * row8, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -1859,7 +1959,7 @@ int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32
 			return SKR_OK;
 		};
 		skr_stats local;
-		rc = render_common(ctx, opt, pl, &local, copy_bands);
+		rc = render_common(ctx, opt, pl, &local, copy_bands, reset_counters);
 		if(enqueued)
 		{
 			if(rc)

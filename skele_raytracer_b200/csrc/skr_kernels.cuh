@@ -64,7 +64,7 @@ struct FrameParams
 {
 	int width, height;
 	int tile, tiles_x, tiles_total, rank, world, wpr; // wpr = tile / 8 (warps per tile row-block)
-	FastDiv fd_tpix, fd_wpr, fd_tiles_x, fd_tile, fd_world, fd_width, fd_peer_rows, fd_band_ctas;
+	FastDiv fd_tpix, fd_wpr, fd_tiles_x, fd_tile, fd_world, fd_width, fd_peer_rows;
 	int fast; // 1: local pixel indices fit 32 bits (any frame but absurdly thin ones), fdiv instead of 64-bit divisions
 	int grid, spp;
 	int max_depth, gi, n_gi, shadows, fresnel;
@@ -84,11 +84,13 @@ struct FrameParams
 	uint8_t *peers[8]; // skr_render_peers_device: row-major RGB8 frames (one per GPU of the box, peer-mapped) or null
 	int n_peers;
 	int peer_rows; // 0: every pixel goes to ALL peers[]; > 0: to peers[min(y / peer_rows, n_peers - 1)] only (skr_render_bands_device)
-	// Copy-out overlapped with the kernel (skr_render, single-kernel frames): CTAs are grouped by blockIdx into bands of
-	// `band_ctas` (whole tile rows); the CTA that completes a band publishes band_seq in band_flag[band], which a
+	// Copy-out overlapped with the kernel (skr_render, single-kernel frames): the frame leaves in bands of whole tile rows.
+	// Band k (in LAUNCH order: the host launches the bands heaviest first, tile_launch_order) owns the blocks
+	// [band_start[k], band_start[k + 1]); the block that completes a band publishes band_seq in band_flag[k], which a
 	// stream-ordered wait on the copy stream is parked on.  Null when unused.
 	unsigned *band_count, *band_flag;
-	unsigned band_ctas, band_seq;
+	unsigned band_start[9]; // (MAX_BANDS + 1)
+	unsigned n_bands, band_seq;
 	// Deferred triangle query (single-sample frames over a real hierarchy, see tri_deferred_kernel): candidates = camera rays
 	// whose line reaches the hierarchy under the root; (direction, tmax) + local pixel index, counter pair (count, CTAs done)
 	float4 *cand_d;
@@ -662,10 +664,14 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 		__syncwarp();
 		if(lane == 0)
 		{
-			__threadfence_system();
-			const unsigned b	= fdiv(blk, fp.fd_band_ctas);
-			const unsigned left = nblocks - b * fp.band_ctas;
-			const unsigned want = left < fp.band_ctas ? left : fp.band_ctas;
+			// (device scope is enough for the blocks that only count: the publishing block's system fence below is cumulative)
+			__threadfence();
+			unsigned b = 0;
+			while(b + 1u < fp.n_bands && blk >= fp.band_start[b + 1u])
+			{
+				b++;
+			}
+			const unsigned want = fp.band_start[b + 1u] - fp.band_start[b];
 			if((atomicAdd(fp.band_count + b, 1u) + 1u) % want == 0u) // counters run on from frame to frame (same geometry)
 			{
 				__threadfence_system();

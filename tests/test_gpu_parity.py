@@ -460,13 +460,25 @@ def test_overlapped_copy_out_into_pinned_host_memory(gpu, gscenes, scene, kw):
         h8b = torch.zeros((o.height, o.width, 3), dtype=torch.uint8).pin_memory()
         gpu.render(o, rgb8=h8b.numpy(), want_rgb32=False)
         assert np.array_equal(h8b.numpy(), ref8)
-    os.environ["SKR_NO_OVERLAP"] = "1"
-    try:
-        h8 = torch.zeros((o.height, o.width, 3), dtype=torch.uint8).pin_memory()
-        gpu.render(o, rgb8=h8.numpy(), want_rgb32=False)
-    finally:
-        del os.environ["SKR_NO_OVERLAP"]
-    assert np.array_equal(h8.numpy(), ref8)
+    # RGB8 alone into page-locked memory is stored by the kernel itself (no copy); SKR_NO_HOST_STORES=1 sends it through the
+    # band copies instead, SKR_NO_OVERLAP=1 through a plain copy after the kernel: the same bytes every way
+    for env in ("SKR_NO_HOST_STORES", "SKR_NO_OVERLAP"):
+        os.environ[env] = "1"
+        try:
+            h8 = torch.zeros((o.height, o.width, 3), dtype=torch.uint8).pin_memory()
+            gpu.render(o, rgb8=h8.numpy(), want_rgb32=False)
+        finally:
+            del os.environ[env]
+        assert np.array_equal(h8.numpy(), ref8), env
+    for nb in ("1", "3", "8"):                      # band count (tuning aid): bands are launched heaviest first
+        os.environ["SKR_BANDS"] = nb
+        try:
+            h8 = torch.zeros((o.height, o.width, 3), dtype=torch.uint8).pin_memory()
+            h32 = torch.zeros((o.height, o.width, 3), dtype=torch.float32).pin_memory()
+            gpu.render(o, rgb8=h8.numpy(), rgb32=h32.numpy())
+        finally:
+            del os.environ["SKR_BANDS"]
+        assert np.array_equal(h8.numpy(), ref8) and np.array_equal(h32.numpy().view(np.uint32), ref32.view(np.uint32)), nb
 
 
 def test_queue_capacity_does_not_change_the_image(gpu, gscenes):
