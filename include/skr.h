@@ -157,7 +157,10 @@ int skr_reserve(skr_ctx *ctx, const skr_options *opt);
 /* Renders one frame (or this rank's tiles of it) and copies the result to HOST buffers.
  *   rgb8  : H*W*3 bytes, row-major top-down RGB, (unsigned char)(min(1,c)*255) as src/main.cpp:96; may be NULL
  *   rgb32 : H*W*3 floats, the pre-clamp image (for tests); may be NULL
- * With world > 1 only this rank's tiles are rendered; the other ranks' pixels are written as 0. */
+ * With world > 1 only this rank's tiles are rendered; the other ranks' pixels are written as 0.
+ * Page-locked destinations (cudaHostAlloc / cudaHostRegister / skr_pin_host) are the fast path: frames that are one long
+ * kernel (>= 4 samples per pixel, no --gillum) are stored into an RGB8-only host frame by the kernel itself, or leave in
+ * bands copied while the kernel is still running; pageable memory gets a plain copy after the frame.  Same bytes each way. */
 int skr_render(skr_ctx *ctx, const skr_options *opt, uint8_t *rgb8, float *rgb32, skr_stats *stats);
 
 /* Same, results left in DEVICE memory (pointers valid on ctx's device; either may be NULL).
