@@ -9,7 +9,7 @@ python bench.py --steps 3 --warmup 3 --only-headline --no-cpu-baseline > $O/plai
 NCU="ncu --set full --clock-control none --import-source on -f"
 $NCU -k regex:primary_kernel -s 1 -c 1 -o $O/r02_c2 python scripts/prof_one.py c2 2 > $O/ncu_c2.log 2>&1
 $NCU -k regex:"primary_kernel|tri_deferred" -s 2 -c 2 -o $O/r02_c4 python scripts/prof_one.py c4 2 > $O/ncu_c4.log 2>&1
-$NCU -k regex:shade_expand -s 17 -c 5 -o $O/r02_c3 python scripts/prof_one.py c3 2 > $O/ncu_c3.log 2>&1
+$NCU -k regex:shade_expand -s 7 -c 7 -o $O/r02_c3 python scripts/prof_one.py c3 2 > $O/ncu_c3.log 2>&1
 $NCU -k regex:shade_expand -s 24 -c 3 -o $O/r02_c5 python scripts/prof_one.py c5 2 > $O/ncu_c5.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches_bench_c2.csv python bench.py --steps 3 --warmup 3 --only-headline --no-cpu-baseline > $O/ncu_bench.log 2>&1
 # text summaries (what profiles/ keeps); the reports themselves exceed what gpurun brings back (64 MiB): keep only config 4's

@@ -968,7 +968,7 @@ int render_frame(skr_ctx *ctx, const skr_options *o, Plan &pl)
 		ctx->launches++;
 		if(pl.defer)
 		{
-			tri_deferred_kernel<STATS><<<(unsigned) ctx->sm_count * 8u, SKR_BLOCK, 0, st>>>(ctx->sv, fp);
+			tri_deferred_kernel<STATS><<<(unsigned) ctx->sm_count * (unsigned) SKR_DEFER_CTAS, SKR_BLOCK, 0, st>>>(ctx->sv, fp);
 			ctx->launches++;
 		}
 		span_end(ctx);

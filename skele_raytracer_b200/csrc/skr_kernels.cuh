@@ -1138,6 +1138,12 @@ __global__ void __launch_bounds__(SKR_BLOCK) fresnel_expand_kernel(const SceneVi
 #define SKR_TEAM 8
 #endif
 #define SKR_TEAM_STACK 128
+#ifndef SKR_DEFER_CTAS
+// resident CTAs per SM (register budget) = persistent CTAs launched per SM.  Config 4 on B200: 6: 0.235 ms, 8: 0.218, 10: 0.230
+// (48 registers), 12: 0.257, 16: 0.316 -- the kernel keeps the L1 tag stage 71 % busy (each lane loads its own 64 B node:
+// ~20 distinct lines per warp load), so more resident teams add spills and evict each other's nodes rather than hide latency
+#define SKR_DEFER_CTAS 8
+#endif
 SKR_DEV void write_black(const FrameParams &fp, uint2 px) // the pixel of a candidate whose line hit a triangle
 {
 	const size_t at = 3 * (size_t) px.x;
@@ -1166,7 +1172,7 @@ SKR_DEV void write_black(const FrameParams &fp, uint2 px) // the pixel of a cand
 	}
 }
 template <bool STATS>
-__global__ void __launch_bounds__(SKR_BLOCK, 8) tri_deferred_kernel(const SceneView sv, const FrameParams fp)
+__global__ void __launch_bounds__(SKR_BLOCK, SKR_DEFER_CTAS) tri_deferred_kernel(const SceneView sv, const FrameParams fp)
 {
 	constexpr int T		= SKR_TEAM;
 	constexpr int TEAMS = 32 / T;
