@@ -62,11 +62,11 @@ SEED = 1
 # round (bench.py cannot run ncu on itself).  Tree configs launch the kernel several times per frame with different loads:
 # the figure is the mean over the captured launches.
 NCU_TRAFFIC_BYTES = {
-    "c2": (600320 + 48128, "profiles/r02_c2_ncu_raw.txt (primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=0,FOG=1,HALVES=1>)"),
-    "c3": (int((99.703808 + 165.637376 + 120.5568 + 338.73152 + 117.56928 + 682.632448 + 703.89248 + 9.904896 + 116.811776 + 690.066688) * 1e6 / 5),
-           "profiles/r02_c3_ncu_raw.txt (mean of 5 shade_expand_kernel launches: queue entries in, queue entries out)"),
-    "c4": (3033856, "profiles/r02_c4_ncu_raw.txt (tri_deferred_kernel; primary_kernel: 67 584)"),
-    "c5": (int((113.852416 + 272.909312 + 329.109504 + 10.732544 + 114.915072 + 147.599104) * 1e6 / 3),
+    "c2": (595968 + 94720, "profiles/r02_c2_ncu_raw.txt (primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=0,FOG=1,HALVES=1>)"),
+    "c3": (int((838.494 + 3154.648 + 2658.218 + 966.383 + 759.633) * 1e6 / 5),
+           "profiles/r02_c3_ncu_raw.txt (mean of 5 shade_expand_kernel launches of the final build: queue entries in, queue entries out)"),
+    "c4": (3032832, "profiles/r02_c4_ncu_raw.txt (tri_deferred_kernel; primary_kernel: 67 328)"),
+    "c5": (int((114.027776 + 274.185472 + 328.451072 + 8.628224 + 115.257088 + 149.899776) * 1e6 / 3),
            "profiles/r02_c5_ncu_raw.txt (mean of 3 shade_expand_kernel launches: expand, leaves in place, expand)"),
 }
 STAT_KEYS = ["closest_hit_rays", "shadow_rays", "sphere_tests", "sphere_tests_pos", "tri_tests", "bvh_node_visits", "sphere_hits", "light_evals",
