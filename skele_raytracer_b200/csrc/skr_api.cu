@@ -1183,6 +1183,14 @@ int render_common(skr_ctx *ctx, const skr_options *o, Plan &pl, skr_stats *stats
 		// (spp >= 8: the frames launch_primary gives the HALVES variant)
 		pl.fp.split = (!tree && !pl.shaded && pl.fp.spp >= 8 && ((nb < 5 * slots && !(no && no[0] == '1')) || (yes && yes[0] == '1'))) ? 1 : 0;
 	}
+	{
+		// whole 32 x 4 strips per CTA (write_strip): 32 x 32 tiles, one block per warp of a 4-warp CTA, RGB8 frames only
+		const char *no	= getenv("SKR_NO_STRIP_CTA");
+		pl.fp.strip_cta = (pl.fp.strip_words && !pl.fp.split && pl.fp.tile == 32 && SKR_BLOCK == 128 && !pl.fp.rgb32 && !pl.fp.tiles8 && !tree && !pl.shaded &&
+						   !(no && no[0] == '1'))
+							  ? 1
+							  : 0;
+	}
 	if(!tree && !pl.shaded)
 	{
 		const int rc_order = tile_launch_order(ctx, pl);

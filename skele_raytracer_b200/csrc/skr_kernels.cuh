@@ -73,6 +73,7 @@ struct FrameParams
 	float cull_delta; // bound on |d(r) - d(0.5)| over the jitter draw r of a pixel (ray directions are un-normalised)
 	int split;		  // 1: the two halves of a pixel's samples are traced by two neighbouring warps (primary_kernel)
 	int strip_words;  // 1: whole 8 x 4 blocks leave as 32-bit words (width % 4 == 0, 4-byte aligned frames)
+	int strip_cta;	  // 1: ... and the four blocks of a CTA (a 32 x 4 strip of a 32 x 32 tile) leave together, 96 B per row (write_strip)
 	// Launch order of this rank's tiles (single-kernel frames): global tile index per local slot, tiles that can see a sphere
 	// FIRST, so that the tail of the kernel is made of cheap sky tiles (tiles_local entries; padding slots = tiles_total), or null
 	const int *tile_order;
@@ -334,6 +335,58 @@ SKR_DEV void write_block(const FrameParams &fp, long long lp, const PixelId &p, 
 	__syncwarp();
 }
 
+// The same for the FOUR blocks of a CTA at once (fp.strip_cta: 32 x 32 tiles, one block per warp, so a CTA covers a 32 x 4 strip
+// of its tile): every warp quantises its block into its 96 B of `stage4`, and the LAST warp of the CTA to get there stores
+// the strip -- 4 rows x 96 B, 32-byte aligned, whole sectors -- where four warps would each store 4 x 24 B that straddle
+// sector boundaries.  That matters for frames stored straight into page-locked HOST memory (skr_render): partial-sector
+// writes cross PCIe one small packet each.  Strips that are not wholly inside the image go block by block as before.
+SKR_DEV void write_strip(const FrameParams &fp, long long lp, const PixelId &p, float3 c, uint32_t (*stage4)[24], unsigned *done)
+{
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const int x0 = __shfl_sync(0xffffffffu, p.x, 0), y0 = __shfl_sync(0xffffffffu, p.y, 0);
+	const int xs = x0 - 8 * (int) warp; // origin of the strip: the CTA's warps are neighbours along x
+	const bool whole = __shfl_sync(0xffffffffu, (int) p.valid, 0) && xs >= 0 && xs + 32 <= fp.width && y0 + 4 <= fp.height; // (uniform in the CTA)
+	if(!whole)
+	{
+		write_block(fp, lp, p, c, stage4[warp]);
+		return;
+	}
+	uint8_t *o = reinterpret_cast<uint8_t *>(stage4[warp]) + (lane >> 3) * 24 + (lane & 7) * 3;
+	o[0]	   = quantise(c.x);
+	o[1]	   = quantise(c.y);
+	o[2]	   = quantise(c.z);
+	__syncwarp();
+	unsigned arrived = 0;
+	if(lane == 0)
+	{
+		__threadfence_block();
+		arrived = atomicAdd(done, 1u);
+	}
+	arrived = __shfl_sync(0xffffffffu, arrived, 0);
+	if(arrived != SKR_BLOCK / 32 - 1)
+	{
+		return;
+	}
+	__threadfence_block();
+#pragma unroll
+	for(int k = (int) lane; k < 96; k += 32) // word k of the strip: row k / 24, word k % 24 of the row = word (k % 24) % 6 of block (k % 24) / 6
+	{
+		const int r = k / 24, w = k - r * 24;
+		const uint32_t v = stage4[w / 6][r * 6 + w % 6];
+		const size_t at	 = (((size_t) (y0 + r) * fp.width + xs) * 3) / 4 + w;
+		if(fp.rgb8)
+		{
+			reinterpret_cast<uint32_t *>(fp.rgb8)[at] = v;
+		}
+		const int k0 = fp.peer_rows > 0 ? peer_of_row(fp, y0 + r) : 0;
+		const int k1 = fp.peer_rows > 0 ? k0 + 1 : fp.n_peers;
+		for(int q = k0; q < k1; q++)
+		{
+			reinterpret_cast<uint32_t *>(fp.peers[q])[at] = v;
+		}
+	}
+}
+
 // Stage the scene blob into shared memory (all threads of the CTA).  SMEM is a template parameter so that the test
 // loops compile to LDS (not generic loads) in the common case; scenes too big for shared memory read the blob in place.
 template <bool SMEM>
@@ -466,7 +519,16 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 {
 	extern __shared__ float4 smem[];
 	__shared__ uint32_t s_px[SKR_BLOCK / 32][24]; // per warp: one block of RGB8, 4 rows x 24 B
+	__shared__ unsigned s_done;					  // warps of this CTA whose block is staged (write_strip)
+	if(threadIdx.x == 0)
+	{
+		s_done = 0u;
+	}
 	const float4 *B = stage_scene<SMEM>(sv, smem);
+	if(!SMEM && fp.strip_cta)
+	{
+		__syncthreads();
+	}
 	Counters cnt;
 	zero(cnt);
 	__shared__ float s_part[HALVES ? 3 : 1][HALVES ? SKR_BLOCK : 1]; // first-half sums (see below)
@@ -656,7 +718,14 @@ __global__ void __launch_bounds__(SKR_BLOCK, SKR_MIN_BLOCKS) primary_kernel(cons
 			const float n2 = (float) fp.spp; // image[y][x] /= (grid*grid), src/main.cpp:68
 			sum			   = f3(__fdiv_rn(sum.x, n2), __fdiv_rn(sum.y, n2), __fdiv_rn(sum.z, n2));
 		}
-		write_block(fp, lp, p, sum, s_px[threadIdx.x >> 5]);
+		if(fp.strip_cta)
+		{
+			write_strip(fp, lp, p, sum, s_px, &s_done);
+		}
+		else
+		{
+			write_block(fp, lp, p, sum, s_px[threadIdx.x >> 5]);
+		}
 	}
 	if(!GI && fp.band_flag)
 	{
