@@ -425,7 +425,8 @@ int build_bvh(skr_ctx *ctx, int T, BvhSet &set, bool mirror)
 	int *big_count	  = reinterpret_cast<int *>(set.d_big + 3 * BIG_TRI_CAP);
 	const int big_cap = T >= BIG_TRI_MIN_T ? BIG_TRI_CAP : 0;
 	CK(ensure(set.d_bvh, set.bvh_bytes, sizeof(float4) * 4 * (size_t) (T - 1)));
-	const int nwarps  = (T + SORT_ITEMS_PER_WARP - 1) / SORT_ITEMS_PER_WARP;
+	const int ipw	  = sort_items_per_warp(T);
+	const int nwarps  = (T + ipw - 1) / ipw;
 	const int sblocks = (nwarps + SORT_WARPS - 1) / SORT_WARPS;
 
 	// build scratch: one arena, carved with 256-byte alignment
@@ -480,9 +481,9 @@ int build_bvh(skr_ctx *ctx, int T, BvhSet &set, bool mirror)
 		for(int pass = 0; pass < 8; pass++)
 		{
 			const int shift = 8 * pass;
-			sort_hist_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], T, shift, hist, nwarps);
+			sort_hist_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], T, shift, hist, nwarps, ipw);
 			sort_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * nwarps);
-			sort_scatter_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], T, shift, hist, nwarps, keys[cur ^ 1], vals[cur ^ 1]);
+			sort_scatter_kernel<<<sblocks, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], T, shift, hist, nwarps, keys[cur ^ 1], vals[cur ^ 1], ipw);
 			cur ^= 1;
 		}
 		cudaMemsetAsync(flags, 0, sizeof(int) * T, st);

@@ -21,7 +21,10 @@ namespace bvhb
 {
 constexpr int SORT_THREADS		  = 256;
 constexpr int SORT_WARPS		  = SORT_THREADS / 32;
-constexpr int SORT_ITEMS_PER_WARP = 32 * 32; // each warp owns 1024 consecutive keys
+constexpr int SORT_ITEMS_PER_WARP = 32 * 32; // each warp owns 1024 consecutive keys (256 for small scenes: sort_items_per_warp)
+// Small scenes are launch- and latency-bound: 10 002 triangles in chunks of 1024 keep 10 warps of the whole GPU busy, each
+// walking its chunk in 32 dependent steps (18 + 29 us per pass, 8 passes).  Chunks of 256 give 40 warps and 8 steps.
+inline int sort_items_per_warp(int n) { return n <= 65536 ? 256 : SORT_ITEMS_PER_WARP; }
 
 struct Box
 {
@@ -184,9 +187,9 @@ __global__ void morton_kernel(float4 *box_lo, float4 *box_hi, const float *__res
 }
 
 // ---- radix sort -------------------------------------------------------------------------------
-// Table layout: hist[digit * nwarps + warp].  Warp w owns keys [w*1024, (w+1)*1024).
+// Table layout: hist[digit * nwarps + warp].  Warp w owns keys [w*ipw, (w+1)*ipw), ipw = sort_items_per_warp(n).
 
-__global__ void sort_hist_kernel(const unsigned long long *__restrict__ keys, int n, int shift, unsigned *__restrict__ hist, int nwarps)
+__global__ void sort_hist_kernel(const unsigned long long *__restrict__ keys, int n, int shift, unsigned *__restrict__ hist, int nwarps, int ipw)
 {
 	__shared__ unsigned cnt[SORT_WARPS][256];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -198,8 +201,8 @@ __global__ void sort_hist_kernel(const unsigned long long *__restrict__ keys, in
 	__syncwarp();
 	if(warp < nwarps)
 	{
-		const int base = warp * SORT_ITEMS_PER_WARP;
-		for(int it = 0; it < 32; it++)
+		const int base = warp * ipw;
+		for(int it = 0; it < ipw / 32; it++)
 		{
 			const int i = base + it * 32 + lane;
 			if(i < n)
@@ -226,6 +229,62 @@ __global__ void sort_scan_kernel(unsigned *__restrict__ data, int len)
 	}
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	if(len <= 16 * (int) blockDim.x)
+	{
+		// small tables (small scenes): ONE round -- every thread scans its own run of up to 16 consecutive entries, the block
+		// scans the run totals -- instead of len / blockDim.x rounds of four barriers each
+		const int per = (len + (int) blockDim.x - 1) / (int) blockDim.x, b = (int) threadIdx.x * per;
+		unsigned loc[16];
+		unsigned sum = 0;
+#pragma unroll
+		for(int k = 0; k < 16; k++)
+		{
+			const int i = b + k;
+			loc[k]		= sum;
+			sum += (k < per && i < len) ? data[i] : 0u;
+		}
+		unsigned s = sum;
+#pragma unroll
+		for(int off = 1; off < 32; off <<= 1)
+		{
+			const unsigned o = __shfl_up_sync(0xffffffffu, s, off);
+			if(lane >= off)
+			{
+				s += o;
+			}
+		}
+		if(lane == 31)
+		{
+			warp_sums[wib] = s;
+		}
+		__syncthreads();
+		if(wib == 0)
+		{
+			unsigned ws = lane < nw ? warp_sums[lane] : 0u;
+#pragma unroll
+			for(int off = 1; off < 32; off <<= 1)
+			{
+				const unsigned o = __shfl_up_sync(0xffffffffu, ws, off);
+				if(lane >= off)
+				{
+					ws += o;
+				}
+			}
+			warp_sums[lane] = ws; // inclusive
+		}
+		__syncthreads();
+		const unsigned prefix = (wib > 0 ? warp_sums[wib - 1] : 0u) + s - sum;
+#pragma unroll
+		for(int k = 0; k < 16; k++)
+		{
+			const int i = b + k;
+			if(k < per && i < len)
+			{
+				data[i] = prefix + loc[k];
+			}
+		}
+		return;
+	}
 	for(int base = 0; base < len; base += blockDim.x)
 	{
 		const int i		 = base + threadIdx.x;
@@ -276,7 +335,7 @@ __global__ void sort_scan_kernel(unsigned *__restrict__ data, int len)
 
 __global__ void sort_scatter_kernel(const unsigned long long *__restrict__ keys_in, const unsigned *__restrict__ vals_in, int n, int shift,
 									const unsigned *__restrict__ offs, int nwarps, unsigned long long *__restrict__ keys_out,
-									unsigned *__restrict__ vals_out)
+									unsigned *__restrict__ vals_out, int ipw)
 {
 	__shared__ unsigned run[SORT_WARPS][256]; // running output cursor per digit for this warp
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -290,9 +349,9 @@ __global__ void sort_scatter_kernel(const unsigned long long *__restrict__ keys_
 		run[wib][d] = offs[(size_t) d * nwarps + warp];
 	}
 	__syncwarp();
-	const int base			 = warp * SORT_ITEMS_PER_WARP;
+	const int base			 = warp * ipw;
 	const unsigned lt_mask = (1u << lane) - 1u;
-	for(int it = 0; it < 32; it++)
+	for(int it = 0; it < ipw / 32; it++)
 	{
 		const int i				   = base + it * 32 + lane;
 		const bool valid		   = i < n;
