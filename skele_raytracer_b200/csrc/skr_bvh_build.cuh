@@ -23,8 +23,22 @@ constexpr int SORT_THREADS		  = 256;
 constexpr int SORT_WARPS		  = SORT_THREADS / 32;
 constexpr int SORT_ITEMS_PER_WARP = 32 * 32; // each warp owns 1024 consecutive keys (256 for small scenes: sort_items_per_warp)
 // Small scenes are launch- and latency-bound: 10 002 triangles in chunks of 1024 keep 10 warps of the whole GPU busy, each
-// walking its chunk in 32 dependent steps (18 + 29 us per pass, 8 passes).  Chunks of 256 give 40 warps and 8 steps.
-inline int sort_items_per_warp(int n) { return n <= 65536 ? 256 : SORT_ITEMS_PER_WARP; }
+// walking its chunk in 32 dependent steps (18 + 29 us per pass, 8 passes).  Chunks of 256 give 40 warps and 8 steps;
+// between 11 k and 45 k keys the chunk grows so that the table of 256 counters per warp still fits the one-round scan.
+constexpr int SCAN_SMALL = 11264; // entries of a histogram table scanned in one round (44 KB of shared memory): 44 warps x 256 digits
+inline int sort_items_per_warp(int n)
+{
+	const int max_warps = SCAN_SMALL / 256; // so that the table is scanned in one round
+	if(n <= 256 * max_warps)
+	{
+		return 256;
+	}
+	if(n <= SORT_ITEMS_PER_WARP * max_warps)
+	{
+		return ((n + max_warps - 1) / max_warps + 31) / 32 * 32;
+	}
+	return SORT_ITEMS_PER_WARP;
+}
 
 struct Box
 {
@@ -229,19 +243,27 @@ __global__ void sort_scan_kernel(unsigned *__restrict__ data, int len)
 	}
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-	if(len <= 16 * (int) blockDim.x)
+	__shared__ unsigned buf[SCAN_SMALL];
+	if(len <= SCAN_SMALL)
 	{
-		// small tables (small scenes): ONE round -- every thread scans its own run of up to 16 consecutive entries, the block
-		// scans the run totals -- instead of len / blockDim.x rounds of four barriers each
+		// small tables (small scenes): ONE round through shared memory (coalesced in, coalesced out) -- every thread scans its
+		// own run of consecutive entries, the block scans the run totals -- instead of len / blockDim.x rounds of four barriers
+		for(int i = threadIdx.x; i < len; i += blockDim.x)
+		{
+			buf[i] = data[i];
+		}
+		__syncthreads();
 		const int per = (len + (int) blockDim.x - 1) / (int) blockDim.x, b = (int) threadIdx.x * per;
-		unsigned loc[16];
 		unsigned sum = 0;
-#pragma unroll
-		for(int k = 0; k < 16; k++)
+		for(int k = 0; k < per; k++)
 		{
 			const int i = b + k;
-			loc[k]		= sum;
-			sum += (k < per && i < len) ? data[i] : 0u;
+			if(i < len)
+			{
+				const unsigned v = buf[i];
+				buf[i]			 = sum; // exclusive within the run
+				sum += v;
+			}
 		}
 		unsigned s = sum;
 #pragma unroll
@@ -274,14 +296,18 @@ __global__ void sort_scan_kernel(unsigned *__restrict__ data, int len)
 		}
 		__syncthreads();
 		const unsigned prefix = (wib > 0 ? warp_sums[wib - 1] : 0u) + s - sum;
-#pragma unroll
-		for(int k = 0; k < 16; k++)
+		for(int k = 0; k < per; k++)
 		{
 			const int i = b + k;
-			if(k < per && i < len)
+			if(i < len)
 			{
-				data[i] = prefix + loc[k];
+				buf[i] += prefix;
 			}
+		}
+		__syncthreads();
+		for(int i = threadIdx.x; i < len; i += blockDim.x)
+		{
+			data[i] = buf[i];
 		}
 		return;
 	}

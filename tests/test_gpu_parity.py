@@ -275,7 +275,7 @@ def test_gillum_64_single_sample(gpu, port, scenes, gscenes):
 
 # ---- BVH ------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("ntris", [1, 2, 3, 33, 1000, 20000])
+@pytest.mark.parametrize("ntris", [1, 2, 3, 33, 1000, 11264, 11265, 20000, 50000])   # (sort chunk sizes: 256, 288, 480, 1024 keys per warp)
 def test_bvh_equals_brute_force(gpu, ntris):
     rng = np.random.default_rng(ntris)
     sc = random_scene(rng, nspheres=3, nplights=1, ntris=ntris)
