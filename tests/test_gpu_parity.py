@@ -481,6 +481,31 @@ def test_overlapped_copy_out_into_pinned_host_memory(gpu, gscenes, scene, kw):
         assert np.array_equal(h8.numpy(), ref8) and np.array_equal(h32.numpy().view(np.uint32), ref32.view(np.uint32)), nb
 
 
+@pytest.mark.parametrize("w,h", [(1000, 700), (1920, 1080), (644, 600), (100, 60), (36, 8)])
+def test_word_and_strip_stores_stay_inside_the_frame(gpu, gscenes, w, h):
+    """Frames bound for other devices / page-locked host memory leave as 32-bit words, whole 32 x 4 strips per CTA where the
+    strip lies inside the image: canaries right before and after the frame must survive, ragged right and bottom edges included,
+    and the frame must be the one the plain path renders."""
+    import torch
+    gpu.upload(gscenes["spheres2"])
+    o = S.Options(width=w, height=h, grid_size=2, use_shadows=True, seed=3)
+    _, ref8, _ = gpu.render(o, want_rgb32=False)
+    n, pad = w * h * 3, 4096
+    # (a) device frame through skr_render_peers_device
+    buf = torch.full((n + 2 * pad,), 0xAB, dtype=torch.uint8, device="cuda")
+    gpu.render_peers_device(o, [buf.data_ptr() + pad])
+    gpu.sync()
+    got = buf.cpu().numpy()
+    assert (got[:pad] == 0xAB).all() and (got[pad + n:] == 0xAB).all()
+    assert np.array_equal(got[pad:pad + n].reshape(h, w, 3), ref8)
+    # (b) page-locked host frame through skr_render (stored by the kernel itself when the frame is large enough)
+    hbuf = torch.full((n + 2 * pad,), 0xCD, dtype=torch.uint8).pin_memory()
+    gpu.render(o, rgb8=hbuf.numpy()[pad:pad + n].reshape(h, w, 3), want_rgb32=False)
+    got = hbuf.numpy()
+    assert (got[:pad] == 0xCD).all() and (got[pad + n:] == 0xCD).all()
+    assert np.array_equal(got[pad:pad + n].reshape(h, w, 3), ref8)
+
+
 def test_queue_capacity_does_not_change_the_image(gpu, gscenes):
     gpu.upload(gscenes["spheres2"])
     a, _, sa = gpu.render(S.Options(**GI_KW))
