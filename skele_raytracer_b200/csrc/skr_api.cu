@@ -476,7 +476,7 @@ int build_bvh(skr_ctx *ctx, int T, BvhSet &set, bool mirror)
 		init_scene_box_kernel<<<1, 32, 0, st>>>(scene_box);
 		cudaMemsetAsync(big_count, 0, sizeof(int), st);
 		tri_bounds_kernel<<<gridT, B, 0, st>>>(ctx->d_tris_raw, T, box_lo, box_hi, scene_box, mirror ? 1 : 0);
-		morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0], ctx->d_tris_raw, big_count, set.d_big, big_cap);
+		morton_kernel<<<gridT, B, 0, st>>>(box_lo, box_hi, scene_box, T, keys[0], vals[0], ctx->d_tris_raw, big_count, set.d_big, big_cap, mirror ? SKR_GCLASS_BITS : 0);
 		int cur = 0;
 		for(int pass = 0; pass < 8; pass++)
 		{

@@ -163,8 +163,17 @@ __device__ __forceinline__ unsigned long long expand21(unsigned v) // spread 21 
 // big_cap entries) that traversal tests first -- any hit ends the query -- and its leaf box collapses to its centre, so
 // it no longer widens its ancestors.  (The leaf stays in the tree: harmless, its test is exact whatever the box.)
 #define SKR_BIG_TRI_FRACTION 0.1f
+// measured on config 4 (dragon.scn 1080p): no class bits 0.218 ms / 15.3 M node visits; 1 bit 0.202 / 14.0 M; 2 bits 0.206; 3 bits
+// 0.208-0.211 (13.8-14.0 M visits, but three more levels above every class)
+#ifndef SKR_GCLASS_BITS
+#define SKR_GCLASS_BITS 1
+#endif
+#ifndef SKR_GCLASS_PER_OCTAVE
+#define SKR_GCLASS_PER_OCTAVE 2
+#endif
 __global__ void morton_kernel(float4 *box_lo, float4 *box_hi, const float *__restrict__ scene_box, int T, unsigned long long *__restrict__ keys,
-							  unsigned *__restrict__ vals, const float *__restrict__ tris, int *big_count, float4 *__restrict__ big_v, int big_cap)
+							  unsigned *__restrict__ vals, const float *__restrict__ tris, int *big_count, float4 *__restrict__ big_v, int big_cap,
+							  int gclass_bits)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= T)
@@ -196,8 +205,24 @@ __global__ void morton_kernel(float4 *box_lo, float4 *box_hi, const float *__res
 	const unsigned qx = (unsigned) fmin(fmax((double) (cx - slo.x) / (double) ex * 2097152.0, 0.0), 2097151.0);
 	const unsigned qy = (unsigned) fmin(fmax((double) (cy - slo.y) / (double) ey * 2097152.0, 0.0), 2097151.0);
 	const unsigned qz = (unsigned) fmin(fmax((double) (cz - slo.z) / (double) ez * 2097152.0, 0.0), 2097151.0);
-	keys[i]			  = expand21(qx) << 2 | expand21(qy) << 1 | expand21(qz);
-	vals[i]			  = (unsigned) i;
+	unsigned long long key = expand21(qx) << 2 | expand21(qy) << 1 | expand21(qz);
+	if(gclass_bits > 0)
+	{
+		// CLASSES BY DEAD-TRIANGLE BOUND (line query only).  Whether a triangle can be hit at all depends on the ray's length:
+		// g |dir| >= 1e-5 (tri_bounds_kernel).  In a purely spatial order dead and live triangles alternate, so no subtree is
+		// ever dead as a whole and a line that crosses the mesh THROUGH its dead triangles (57 % of dragon.scn's for a unit
+		// ray) still descends around every live neighbour's box next to many dead ones.  The class -- 0: g >= 1e-5 (live for
+		// every ray of length >= 1), then SKR_GCLASS_PER_OCTAVE classes per halving of g -- goes ABOVE the spatial bits of the
+		// key: the top levels of the tree split by class, each class is its own spatial hierarchy with boxes around ITS
+		// triangles only, and a ray prunes every class that is dead for it at the top (the per-child g of refit_kernel).
+		const float g  = box_lo[i].w; // (0 for a triangle moved to the big list: last class)
+		const float r  = g > 0.0f ? 1.0e-5f / g : 3.0e38f;
+		const int cmax = (1 << gclass_bits) - 1;
+		const int c	   = r <= 1.0f ? 0 : min(cmax, 1 + (int) floorf((float) SKR_GCLASS_PER_OCTAVE * log2f(r)));
+		key			   = (key >> gclass_bits) | ((unsigned long long) c << (63 - gclass_bits));
+	}
+	keys[i] = key;
+	vals[i] = (unsigned) i;
 }
 
 // ---- radix sort -------------------------------------------------------------------------------
