@@ -495,8 +495,8 @@ def roofline_of(m, world, peaks, peaks_src, fp32_peak, bw):
         gbs = b / (dom_ms * 1e-3) / 1e9
         fl = algorithmic_flops(st0, m["primary_samples"] / world)
         return {"bound": "l1", "achieved": gbs, "peak": bw["l1_gbs"], "unit": "GB/s", "frac": gbs / bw["l1_gbs"] if bw["l1_gbs"] > 0 else None,
-                "traffic": traffic[0], "traffic_source": traffic[1], "kernel": "primary_kernel (<= 6 nodes in place) + tri_deferred_kernel (teams of 8 lanes per undecided ray)", "kernel_ms_per_frame": dom_ms,
-                "kernel_launches_per_frame": 2, "bytes_per_frame_algorithmic_this_rank": b,
+                "traffic": traffic[0], "traffic_source": traffic[1], "kernel": "primary_kernel<TRIS=1> (LBVH line any-hit query walked in place)", "kernel_ms_per_frame": dom_ms,
+                "kernel_launches_per_frame": 1, "bytes_per_frame_algorithmic_this_rank": b,
                 "bytes_per_unit": "64 B per BVH node visit (both child boxes) + 48 B per triangle leaf test",
                 "levels": {"l1": {"achieved_gbs": gbs, "peak_gbs": bw["l1_gbs"]}, "l2": {"peak_gbs": bw["l2_gbs"]}, "shared": {"peak_gbs": bw["lds_gbs"]}, "hbm": hbm},
                 "fp32": {"tflops": fl / (dom_ms * 1e-3) / 1e12, "frac": fl / (dom_ms * 1e-3) / 1e12 / fp32_peak},

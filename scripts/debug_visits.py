@@ -4,7 +4,6 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["SKR_NO_DEFER"] = "1"
 import skele_raytracer_b200 as S
 from bench import WORKLOADS
 scene, kw, desc = WORKLOADS["c4"]

@@ -710,10 +710,13 @@ int make_plan(skr_ctx *ctx, const skr_options *o, Plan &pl)
 	pl.levels	   = ((fp.gi || fp.fresnel) && fp.max_depth > 0) ? fp.max_depth : 0;
 	{
 		// deferred triangle query (tri_deferred_kernel: teams of lanes per heavy ray): single-sample frames without a wavefront
-		// tree, over a real hierarchy.  Config 4: 0.228 ms against 0.279 for the walk in place (SKR_NO_DEFER=1); same frame.
-		const char *no = getenv("SKR_NO_DEFER");
-		pl.defer	   = !pl.shaded && !fp.gi && !fp.fresnel && fp.spp == 1 && fp.max_depth > 0 && ctx->sv.bvh != nullptr && !ctx->sv.bvh_root_is_leaf &&
-				   pl.npix_local <= 0xffffffffLL && !(no && no[0] == '1');
+		// tree, over a real hierarchy.  OPT-IN (SKR_DEFER=1) since the hierarchy is built over cubic Morton cells: with the
+		// slab-shaped top levels of the first build, config 4 had lines of 640 node visits and the teams won (0.218 ms against
+		// 0.279 for the walk in place); now (4.7 M visits per frame instead of 21 M) the walk in place takes 0.124 ms, teams of
+		// 8 / 4 lanes 0.157 / 0.128-0.136.  Same frame either way.
+		const char *yes = getenv("SKR_DEFER");
+		pl.defer		= !pl.shaded && !fp.gi && !fp.fresnel && fp.spp == 1 && fp.max_depth > 0 && ctx->sv.bvh != nullptr && !ctx->sv.bvh_root_is_leaf &&
+				   pl.npix_local <= 0xffffffffLL && yes && yes[0] == '1';
 	}
 	{
 		// leaves in place: plain --gillum trees (the fresnel pass pushes its own leaf children through the queue)

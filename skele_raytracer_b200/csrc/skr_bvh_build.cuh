@@ -166,7 +166,10 @@ __device__ __forceinline__ unsigned long long expand21(unsigned v) // spread 21 
 // measured on config 4 (dragon.scn 1080p): no class bits 0.218 ms / 15.3 M node visits; 1 bit 0.202 / 14.0 M; 2 bits 0.206; 3 bits
 // 0.208-0.211 (13.8-14.0 M visits, but three more levels above every class)
 #ifndef SKR_GCLASS_BITS
-#define SKR_GCLASS_BITS 1
+#define SKR_GCLASS_BITS 0
+#endif
+#ifndef SKR_MORTON_CUBIC
+#define SKR_MORTON_CUBIC 1
 #endif
 #ifndef SKR_GCLASS_PER_OCTAVE
 #define SKR_GCLASS_PER_OCTAVE 2
@@ -202,9 +205,19 @@ __global__ void morton_kernel(float4 *box_lo, float4 *box_hi, const float *__res
 		}
 	}
 	// quantise in double: 21 bits exceed the float mantissa's headroom near the top of the range
+#if SKR_MORTON_CUBIC
+	// ONE cell size for the three axes (the scene box's longest side): with each axis scaled by its own extent a flat scene --
+	// dragon.scn: a 0.2-high model on a 40 x 40 ground -- has cells 200 times longer than high, and the top levels of the
+	// model's hierarchy are horizontal slabs that span its whole footprint
+	const double emax = fmax((double) ex, fmax((double) ey, (double) ez));
+	const unsigned qx = (unsigned) fmin(fmax((double) (cx - slo.x) / emax * 2097152.0, 0.0), 2097151.0);
+	const unsigned qy = (unsigned) fmin(fmax((double) (cy - slo.y) / emax * 2097152.0, 0.0), 2097151.0);
+	const unsigned qz = (unsigned) fmin(fmax((double) (cz - slo.z) / emax * 2097152.0, 0.0), 2097151.0);
+#else
 	const unsigned qx = (unsigned) fmin(fmax((double) (cx - slo.x) / (double) ex * 2097152.0, 0.0), 2097151.0);
 	const unsigned qy = (unsigned) fmin(fmax((double) (cy - slo.y) / (double) ey * 2097152.0, 0.0), 2097151.0);
 	const unsigned qz = (unsigned) fmin(fmax((double) (cz - slo.z) / (double) ez * 2097152.0, 0.0), 2097151.0);
+#endif
 	unsigned long long key = expand21(qx) << 2 | expand21(qy) << 1 | expand21(qz);
 	if(gclass_bits > 0)
 	{

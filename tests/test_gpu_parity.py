@@ -301,17 +301,17 @@ def test_bvh_equals_brute_force(gpu, ntris):
 @pytest.mark.parametrize("scene,kw", [("dragon", dict(width=1920, height=1080)), ("dragon", dict(width=333, height=187, fov=25.0)),
                                       ("test", dict(width=640, height=360, use_shadows=True)), ("test", dict(width=200, height=120, rank=1, world=3, tile=16))])
 def test_deferred_triangle_query_equals_the_query_in_place(gpu, gscenes, scene, kw):
-    """Single-sample frames hand the camera rays that are not settled within a few nodes to tri_deferred_kernel (a dense
-    list walked by teams of 8 lanes per ray from a shared stack); the frame must be the one the in-place query gives
-    (SKR_NO_DEFER=1), bit for bit."""
+    """With SKR_DEFER=1 single-sample frames hand the camera rays that are not settled within a few nodes to
+    tri_deferred_kernel (a dense list walked by teams of 8 lanes per ray from a shared stack); the frame must be the one the
+    in-place query (the default) gives, bit for bit."""
     gpu.upload(gscenes[scene])
     o = S.Options(collect_stats=True, **kw)
-    a32, a8, sa = gpu.render(o)
-    os.environ["SKR_NO_DEFER"] = "1"
+    b32, b8, sb = gpu.render(o)
+    os.environ["SKR_DEFER"] = "1"
     try:
-        b32, b8, sb = gpu.render(o)
+        a32, a8, sa = gpu.render(o)
     finally:
-        del os.environ["SKR_NO_DEFER"]
+        del os.environ["SKR_DEFER"]
     assert np.array_equal(a32.view(np.uint32), b32.view(np.uint32)) and np.array_equal(a8, b8)
     # (node / leaf-test counts differ: a team visits the hierarchy in another order and finishes the iteration a hit falls in)
     assert sa.kernel_launches == sb.kernel_launches + 1 and sa.closest_hit_rays == sb.closest_hit_rays
