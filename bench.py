@@ -65,7 +65,7 @@ NCU_TRAFFIC_BYTES = {
     "c2": (595968 + 94720, "profiles/r02_c2_ncu_raw.txt (primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=0,FOG=1,HALVES=1>)"),
     "c3": (int((838.494 + 3154.648 + 2658.218 + 966.383 + 759.633) * 1e6 / 5),
            "profiles/r02_c3_ncu_raw.txt (mean of 5 shade_expand_kernel launches of the final build: queue entries in, queue entries out)"),
-    "c4": (3032832, "profiles/r02_c4_ncu_raw.txt (tri_deferred_kernel; primary_kernel: 67 328)"),
+    "c4": (477184 + 768, "profiles/r02_c4_ncu_raw.txt (primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=1,FOG=0,HALVES=0>)"),
     "c5": (int((114.027776 + 274.185472 + 328.451072 + 8.628224 + 115.257088 + 149.899776) * 1e6 / 3),
            "profiles/r02_c5_ncu_raw.txt (mean of 3 shade_expand_kernel launches: expand, leaves in place, expand)"),
 }
