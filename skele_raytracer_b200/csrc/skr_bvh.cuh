@@ -200,8 +200,15 @@ SKR_DEV bool tri_any_hit_line(const SceneView &sv, float3 o, float3 d, float tma
 {
 	if(sv.bvh == nullptr) // brute force (a handful of triangles, or validation mode SKR_NO_BVH=1)
 	{
+		// triangles that are dead for this ray (|d| g < 1e-5: the reference's fabs(det) test must fail, skr_bvh_build.cuh) are
+		// skipped without the test -- spheres1.scn's two triangles are collinear points, dead for every camera ray
+		const float dlen = sqrtf(dot(d, d)) * 1.00001f;
 		for(int i = 0; i < sv.T; i++)
 		{
+			if(__ldg(sv.tri_v + 4 * i + 1).w * dlen < 0.99999e-5f)
+			{
+				continue;
+			}
 			if(tri_leaf_hit<STATS>(sv, i, o, d, tmax, cnt))
 			{
 				return true;

@@ -69,6 +69,16 @@ __device__ __forceinline__ void atomic_max_f(float *addr, float v)
 	}
 }
 
+// DEAD-TRIANGLE BOUND g (see tri_bounds_kernel): a ray with |dir| * g < 1e-5 cannot pass the reference's fabs(det) >= 1e-5 test
+__device__ __forceinline__ float tri_dead_bound(float3 v0, float3 v1, float3 v2)
+{
+	const double e1x = (double) v1.x - v0.x, e1y = (double) v1.y - v0.y, e1z = (double) v1.z - v0.z;
+	const double e2x = (double) v2.x - v0.x, e2y = (double) v2.y - v0.y, e2z = (double) v2.z - v0.z;
+	const double nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+	const double g	= sqrt(nx * nx + ny * ny + nz * nz) + 1.0e-6 * sqrt((e1x * e1x + e1y * e1y + e1z * e1z) * (e2x * e2x + e2y * e2y + e2z * e2z));
+	return __double2float_ru(g * 1.000001);
+}
+
 __global__ void init_scene_box_kernel(float *scene_box) // (min.xyz, max.xyz) = (+3e38, -3e38)
 {
 	if(threadIdx.x < 6)
@@ -102,11 +112,7 @@ __global__ void tri_bounds_kernel(const float *__restrict__ tris, int T, float4 
 		// with |dir| * g < 1e-5 cannot pass the test: traversal skips the triangle -- and every subtree whose largest g fails
 		// (refit_kernel keeps the maximum per child).  dragon.scn's triangles are ~2 mm across (|e1 x e2| ~ 4e-6): for the
 		// shorter camera rays most of the model can never be hit, which is exactly why the reference's render of it is sparse.
-		const double e1x = (double) v1.x - v0.x, e1y = (double) v1.y - v0.y, e1z = (double) v1.z - v0.z;
-		const double e2x = (double) v2.x - v0.x, e2y = (double) v2.y - v0.y, e2z = (double) v2.z - v0.z;
-		const double nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
-		const double g	= sqrt(nx * nx + ny * ny + nz * nz) + 1.0e-6 * sqrt((e1x * e1x + e1y * e1y + e1z * e1z) * (e2x * e2x + e2y * e2y + e2z * e2z));
-		box_lo[i]		= make_float4(lo.x, lo.y, lo.z, __double2float_ru(g * 1.000001));
+		box_lo[i]		= make_float4(lo.x, lo.y, lo.z, tri_dead_bound(v0, v1, v2));
 		box_hi[i]		= make_float4(hi.x, hi.y, hi.z, 0.0f);
 	}
 	// block reduction of the scene box through shared memory, one atomic per block per component
@@ -596,7 +602,8 @@ __global__ void iota_tris_kernel(const float *__restrict__ tris, int n, float4 *
 	}
 	const float *t	 = tris + 9 * (size_t) i;
 	tri_v[4 * i + 0] = make_float4(t[0], t[1], t[2], __int_as_float(i));
-	tri_v[4 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
+	// (.w: the dead-triangle bound -- the brute-force list has no hierarchy to prune it by: tri_any_hit_line skips the test itself)
+	tri_v[4 * i + 1] = make_float4(t[3], t[4], t[5], tri_dead_bound(f3(t[0], t[1], t[2]), f3(t[3], t[4], t[5]), f3(t[6], t[7], t[8])));
 	tri_v[4 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
 	tri_v[4 * i + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
