@@ -272,7 +272,12 @@ void launch_primary(skr_ctx *ctx, const FrameParams &fp, const Queue &q, long lo
 	const long long wpc		= threads / 32;
 	const unsigned blocks = (unsigned) (((n + 31) / 32 * ((!GI && fp.split) ? 2 : 1) + wpc - 1) / wpc);
 	const bool halves = !GI && fp.spp >= 8; // two-half sample sums (and the split over two warps): frames with samples to split
-	const auto go = [&](auto kernel, size_t bytes) { kernel<<<blocks, threads, bytes, st>>>(sv, fp, q, lp0, n); };
+	FrameParams fpl = fp;
+	if(threads != SKR_BLOCK)
+	{
+		fpl.strip_cta = 0; // (write_strip counts on four warps per CTA)
+	}
+	const auto go = [&](auto kernel, size_t bytes) { kernel<<<blocks, threads, bytes, st>>>(sv, fpl, q, lp0, n); };
 	if(!sv.blob_in_smem)
 	{
 		halves ? go(primary_kernel<GI, STATS, false, true, true, !GI>, 0) : go(primary_kernel<GI, STATS, false, true, true, false>, 0);

@@ -498,6 +498,18 @@ def test_word_and_strip_stores_stay_inside_the_frame(gpu, gscenes, w, h):
     got = buf.cpu().numpy()
     assert (got[:pad] == 0xAB).all() and (got[pad + n:] == 0xAB).all()
     assert np.array_equal(got[pad:pad + n].reshape(h, w, 3), ref8)
+    # (CTAs of other sizes -- SKR_PRIMARY_BLOCK, a tuning aid -- cannot pair up into strips and must fall back to blocks)
+    for threads in ("64", "32"):
+        os.environ["SKR_PRIMARY_BLOCK"] = threads
+        try:
+            buf.fill_(0xAB)
+            gpu.render_peers_device(o, [buf.data_ptr() + pad])
+            gpu.sync()
+        finally:
+            del os.environ["SKR_PRIMARY_BLOCK"]
+        got = buf.cpu().numpy()
+        assert (got[:pad] == 0xAB).all() and (got[pad + n:] == 0xAB).all()
+        assert np.array_equal(got[pad:pad + n].reshape(h, w, 3), ref8), threads
     # (b) page-locked host frame through skr_render (stored by the kernel itself when the frame is large enough)
     hbuf = torch.full((n + 2 * pad,), 0xCD, dtype=torch.uint8).pin_memory()
     gpu.render(o, rgb8=hbuf.numpy()[pad:pad + n].reshape(h, w, 3), want_rgb32=False)
