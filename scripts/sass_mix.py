@@ -10,10 +10,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "skele_raytracer_b200", "libskr.so")
 KERNELS = {
-    "primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=0,FOG=1>  (config 2)": "_Z14primary_kernelILb0ELb0ELb1ELb0ELb1EE",
-    "primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=1,FOG=0>  (config 4)": "_Z14primary_kernelILb0ELb0ELb1ELb1ELb0EE",
-    "shade_expand_kernel<STATS=0,SMEM=1,TRIS=0,FOG=0>  (config 5)": "_Z19shade_expand_kernelILb0ELb1ELb0ELb0EE",
-    "shade_expand_kernel<STATS=0,SMEM=1,TRIS=0,FOG=1>  (config 3)": "_Z19shade_expand_kernelILb0ELb1ELb0ELb1EE",
+    "primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=0,FOG=1,HALVES=1>  (config 2)": "_Z14primary_kernelILb0ELb0ELb1ELb0ELb1ELb1EE",
+    "primary_kernel<GI=0,STATS=0,SMEM=1,TRIS=1,FOG=0,HALVES=0>  (config 4)": "_Z14primary_kernelILb0ELb0ELb1ELb1ELb0ELb0EE",
+    "shade_expand_kernel<STATS=0,SMEM=1,TRIS=0,FOG=0,LEAF=0>  (config 5, expand)": "_Z19shade_expand_kernelILb0ELb1ELb0ELb0ELb0EE",
+    "shade_expand_kernel<STATS=0,SMEM=1,TRIS=0,FOG=0,LEAF=1>  (config 5, expand + leaves in place)": "_Z19shade_expand_kernelILb0ELb1ELb0ELb0ELb1EE",
+    "shade_expand_kernel<STATS=0,SMEM=1,TRIS=0,FOG=1,LEAF=0>  (config 3)": "_Z19shade_expand_kernelILb0ELb1ELb0ELb1ELb0EE",
 }
 WATCH = ["FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "MUFU", "VIMNMX3", "FSETP", "FSEL", "LOP3", "IMAD", "LDS", "STS", "LDG", "STG", "LDL", "STL",
          "ATOM", "RED", "SHFL", "VOTE", "BRA", "BSSY", "REDUX"]
